@@ -1,0 +1,193 @@
+/*
+ * firgpu — C ABI of the B200-native fixed-point FIR path.
+ *
+ * This header is the drop-in boundary.  The reference (young-0320/
+ * warmup-fir-filter) has no FFI layer of its own: its hot path is a set of
+ * Python functions.  Each entry point below names the reference interface it
+ * stands behind (paths relative to the reference root); INTEGRATION.md shows
+ * the ctypes stub a reference maintainer would add at those lines.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures
+ *     (streams travel as void* = cudaStream_t, NULL = the legacy default
+ *     stream);
+ *   - every function returns 0 on success, a negative FIRGPU_E_* code for a
+ *     rejected argument, or a positive cudaError_t; firgpu_last_error() gives
+ *     the thread-local message;
+ *   - "device" entry points take DEVICE pointers and are stream-ordered and
+ *     asynchronous; "_host" entry points take HOST pointers, run the
+ *     host->device copy, the kernels and the device->host copy as a chunked
+ *     pipeline, and return when the result is in y;
+ *   - integer taps: the caller quantises real coefficients on the host with
+ *     the reference's own NumPy calls (np.rint, np.clip, astype —
+ *     fir_1d/model/python/fir_1d_fixed_ref.py:79-81) and passes int32 values;
+ *     that float64 step is part of the bit-exact contract and is deliberately
+ *     not re-implemented in C;
+ *   - leading dimensions (ld_*, img_stride_*) are in ELEMENTS of the array's
+ *     own dtype;
+ *   - there is no CPU fallback anywhere behind this ABI: without a CUDA
+ *     device every compute entry point fails with a cudaError_t.
+ *
+ * Sample containers (in_dtype): FIRGPU_U8 is the reference's native pixel
+ * type; FIRGPU_I16/I32 are integer containers whose values the kernel clamps
+ * to [0,255] exactly as the reference clamps any integer input
+ * (fir_1d/model/python/fir_1d_ref.py:40-41); FIRGPU_F32/F64 are rounded with
+ * floor(x + 0.5) in float64 first (fir_1d_ref.py:35-38).  Fixed-point outputs
+ * (out_dtype) are FIRGPU_U8 or the same values in an FIRGPU_I16 container.
+ */
+#ifndef FIRGPU_H
+#define FIRGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIRGPU_VERSION 100          /* 0.1.0 */
+#define FIRGPU_MAX_TAPS 1024        /* per filter; 2-D: kh*kw */
+
+enum firgpu_dtype { FIRGPU_U8 = 0, FIRGPU_I16 = 1, FIRGPU_I32 = 2, FIRGPU_F32 = 3, FIRGPU_F64 = 4 };
+
+enum firgpu_status {
+    FIRGPU_OK = 0,
+    FIRGPU_E_DTYPE = -1,      /* unsupported in/out container */
+    FIRGPU_E_SHAPE = -2,      /* negative size, ld < cols, ... */
+    FIRGPU_E_TAPS = -3,       /* n_taps outside [1, FIRGPU_MAX_TAPS] */
+    FIRGPU_E_BITS = -4,       /* frac_bits < 1 or acc_bits < 1 */
+    FIRGPU_E_DILATION = -5,   /* dilation < 1 */
+    FIRGPU_E_NULL = -6,       /* NULL pointer with non-empty shape */
+    FIRGPU_E_HALO = -7        /* negative halo_*_valid */
+};
+
+/* Which kernel family served the last call on this thread (diagnostics and
+ * tests: proves the fast path ran, or why it did not). */
+enum firgpu_path {
+    FIRGPU_PATH_NONE = 0,
+    FIRGPU_PATH_GENERIC = 1,      /* int64 accumulate, any shape / alignment / acc_bits */
+    FIRGPU_PATH_STAGED = 2,       /* bulk-copy (TMA) staged, packed int32 datapath */
+    FIRGPU_PATH_EMPTY = 3         /* zero-sized input, nothing launched */
+};
+
+int firgpu_version(void);
+const char *firgpu_last_error(void);
+int firgpu_last_path(void);
+/* Number of kernels this library has launched from the calling thread. */
+int64_t firgpu_launch_count(void);
+int firgpu_device_count(int *count);
+
+/* ------------------------------------------------------------------------
+ * 1-D fixed-point FIR, row-batched.
+ *
+ * Stands behind
+ *   fir_1d_fixed_golden(x, h, frac_bits=12, acc_bits=32, coeff_bits=16)
+ *       fir_1d/model/python/fir_1d_fixed_ref.py:12-130      (rows == 1)
+ *   _run_fixed_rowwise(x_u8, h, ...)
+ *       fir_1d/sim/vector/gen_fixed_output.py:34-60          (rows == height)
+ *
+ * For every row r and n in [0, cols):
+ *   acc  = sum_k hq[k] * xs[r][n - (k - n_taps/2) * dilation]
+ *   y    = sat_0^255( (wrap_to_acc_bits(acc) + 2^(frac_bits-1)) >> frac_bits )
+ * xs = input clamped to [0,255]; samples outside [0, cols) are 0, EXCEPT that
+ * up to halo_left_valid samples before and halo_right_valid samples after
+ * each row are real neighbour data the kernel reads in place (they must be
+ * readable memory).  That is how a shard of a longer signal is filtered
+ * without a seam; both are 0 for a whole signal.
+ * dilation == 2 filters interleaved I/Q (Re and Im independently, the only
+ * FIR expressible with lib/mycomplex.cpp:12-22).
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype,
+                       int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                       const int32_t *hq, int n_taps, int dilation,
+                       int frac_bits, int acc_bits,
+                       int64_t halo_left_valid, int64_t halo_right_valid,
+                       void *stream);
+
+/* Same filter applied with n_filters tap sets to one input, reading x once:
+ * hq is [n_filters][n_taps] row-major (host), y is [n_filters] outputs
+ * separated by filter_stride_y elements.  Stands behind the coefficient loop
+ * of _generate_fixed_outputs_for_tap_map (gen_fixed_output.py:91-104). */
+int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype,
+                             int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                             int64_t filter_stride_y,
+                             const int32_t *hq, int n_filters, int n_taps, int dilation,
+                             int frac_bits, int acc_bits, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 1-D ideal (floating-point) FIR, row-batched.
+ *
+ * Stands behind
+ *   fir_1d_ideal(x, h)           fir_1d/model/python/fir_1d_ref.py:43-65
+ *   _run_ideal_rowwise(x_u8, h)  fir_1d/sim/vector/gen_ideal_output.py:37-50
+ *
+ * out_dtype FIRGPU_F64: bit-identical to the reference (float64, taps in
+ * ascending k, separate round-to-nearest multiply and add, no FMA).
+ * out_dtype FIRGPU_F32: float32 arithmetic, |err| <= 1e-6 * sum_k|h[k]|*255.
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype,
+                       int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                       const double *h, int n_taps, int dilation,
+                       int64_t halo_left_valid, int64_t halo_right_valid,
+                       void *stream);
+
+/* ------------------------------------------------------------------------
+ * 2-D fixed-point / ideal FIR over a batch of images.
+ *
+ * The reference has NO fir_2d implementation (fir_2d/model/cpp/CMakeLists.txt
+ * is empty); this is the counterpart BASELINE.json asks for, specified in
+ * same pre/post-processing as the 1-D model, one accumulator
+ * per pixel over the kh x kw window (hq row-major [kh][kw]),
+ *   acc = sum_m sum_n hq[m][n] * xs[i - m + kh/2][j - n + kw/2],
+ * zero outside the image, except that halo_top_valid rows above and
+ * halo_bottom_valid rows below each image are real neighbour rows (row-band
+ * shards).  Would stand behind fir_2d.model.python.fir_2d_fixed_ref /
+ * fir_2d_ref.
+ * ------------------------------------------------------------------------ */
+int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype,
+                       int64_t n_img, int64_t height, int64_t width,
+                       int64_t ld_x, int64_t ld_y, int64_t img_stride_x, int64_t img_stride_y,
+                       const int32_t *hq, int kh, int kw,
+                       int frac_bits, int acc_bits,
+                       int64_t halo_top_valid, int64_t halo_bottom_valid,
+                       void *stream);
+
+int firgpu_fir2d_ideal(const void *x, void *y, int in_dtype, int out_dtype,
+                       int64_t n_img, int64_t height, int64_t width,
+                       int64_t ld_x, int64_t ld_y, int64_t img_stride_x, int64_t img_stride_y,
+                       const double *h, int kh, int kw,
+                       int64_t halo_top_valid, int64_t halo_bottom_valid,
+                       void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer entry points: what a ctypes caller with NumPy arrays uses.
+ * x and y are HOST pointers (pinned memory is copied directly and overlaps
+ * fully; pageable memory goes through the library's pinned staging ring).
+ * The call is a pipeline over chunks: H2D copy, kernel, D2H copy on three
+ * streams, and returns after the last D2H completes.  device < 0 = current.
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
+                            int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                            const int32_t *hq, int n_taps, int dilation,
+                            int frac_bits, int acc_bits, int device);
+
+int firgpu_fir1d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
+                            int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                            const double *h, int n_taps, int dilation, int device);
+
+int firgpu_fir2d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
+                            int64_t n_img, int64_t height, int64_t width,
+                            const int32_t *hq, int kh, int kw,
+                            int frac_bits, int acc_bits, int device);
+
+int firgpu_fir2d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
+                            int64_t n_img, int64_t height, int64_t width,
+                            const double *h, int kh, int kw, int device);
+
+/* Release cached device / pinned buffers and streams held for the _host
+ * pipeline on every device. */
+int firgpu_release_cache(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIRGPU_H */

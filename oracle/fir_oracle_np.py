@@ -1,0 +1,163 @@
+"""Vectorised NumPy (int64 / float64) restatement of the reference FIR models.
+
+TEST INFRASTRUCTURE ONLY — see the header of ``oracle/fir_oracle_py.py`` for
+the rules (never on the product path; only tests / smoke() / bench.py's CPU
+baseline legs import it) and for the parity status (1-D pinned against the
+reference's KATs and reference-made golden vectors; I/Q pinned by composition;
+fir_2d PARITY UNPINNED — the reference has no fir_2d).
+
+Same arithmetic as the scalar oracle, expressed as shift-and-add over whole
+arrays so that 2**28-sample and 16384x16384 inputs finish in seconds.  int64
+is exact here as long as |sum_k hq[k] * x| < 2**62, i.e. for every tap count
+up to MAX_TAPS with 32-bit coefficients (255 * 2**31 * 1024 < 2**50).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAX_TAPS = 1024
+PIXEL_LO, PIXEL_HI = 0, 255          # fir_1d_fixed_ref.py:50-51
+
+
+def prep_samples(x) -> np.ndarray:
+    """round-half-up (floor(x + 0.5) in float64) then clamp to [0, 255]
+    (fir_1d/model/python/fir_1d_ref.py:35-41).  Integer inputs skip the
+    rounding, which is the identity on them."""
+    a = np.asarray(x)
+    if a.dtype == np.uint8:
+        return a
+    if a.dtype.kind in "iub":
+        return np.clip(a, PIXEL_LO, PIXEL_HI).astype(np.uint8)
+    r = np.floor(a.astype(np.float64) + 0.5)
+    return np.clip(r, PIXEL_LO, PIXEL_HI).astype(np.uint8)
+
+
+def quantize_taps(h, frac_bits: int, coeff_bits: int) -> np.ndarray:
+    """rint(h * 2**frac) -> clip to signed coeff_bits -> integer
+    (fir_1d_fixed_ref.py:52-55,75-81)."""
+    lo = -(1 << (coeff_bits - 1))
+    hi = (1 << (coeff_bits - 1)) - 1
+    scaled = np.rint(np.asarray(h, dtype=np.float64) * float(1 << frac_bits))
+    return np.clip(scaled, lo, hi).astype(np.int64)
+
+
+def post_accumulate(acc: np.ndarray, frac_bits: int, acc_bits: int,
+                    out_lo: int = PIXEL_LO, out_hi: int = PIXEL_HI) -> np.ndarray:
+    """wrap to acc_bits two's complement -> + 2**(frac-1), not re-wrapped ->
+    arithmetic shift -> saturate (fir_1d_fixed_ref.py:110-126).  ``acc`` is
+    int64 and is consumed."""
+    if acc_bits < 63:
+        acc &= np.int64((1 << acc_bits) - 1)
+        acc -= (acc >> np.int64(acc_bits - 1)) << np.int64(acc_bits)
+    # acc_bits >= 63: |acc| < 2**62 so the mask + sign restore is the identity.
+    if frac_bits > 62:
+        # acc + 2**(frac-1) lies in [0, 2**frac) for every |acc| < 2**61.
+        acc[...] = 0
+    else:
+        acc += np.int64(1 << (frac_bits - 1))
+        acc >>= np.int64(frac_bits)
+    np.clip(acc, out_lo, out_hi, out=acc)
+    return acc
+
+
+def _shifted_views(xs: np.ndarray, n_taps: int, dilation: int):
+    """Yield (k, view) where view[..., n] == xs[..., n - (k - L//2)*dilation]
+    with zeros outside (fir_1d_fixed_ref.py:86,99-104)."""
+    centre = n_taps // 2
+    n = xs.shape[-1]
+    left = (n_taps - 1 - centre) * dilation      # reach towards lower indices
+    right = centre * dilation                    # reach towards higher indices
+    pad = [(0, 0)] * (xs.ndim - 1) + [(left, right)]
+    xp = np.pad(xs, pad)
+    for k in range(n_taps):
+        start = left - (k - centre) * dilation
+        yield k, xp[..., start:start + n]
+
+
+def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16,
+                *, dilation: int = 1, taps_are_quantized: bool = False,
+                out_dtype=np.uint8) -> np.ndarray:
+    """Fixed-point FIR along the last axis; every leading index is an
+    independent, separately zero-padded row (gen_fixed_output.py:44-59)."""
+    xs = prep_samples(x)
+    hq = np.asarray(h, dtype=np.int64) if taps_are_quantized else quantize_taps(h, frac_bits, coeff_bits)
+    assert 1 <= hq.size <= MAX_TAPS
+    acc = np.zeros(xs.shape, dtype=np.int64)
+    xi = xs.astype(np.int64)
+    for k, view in _shifted_views(xi, hq.size, dilation):
+        if hq[k] != 0:
+            acc += view * hq[k]
+    return post_accumulate(acc, frac_bits, acc_bits).astype(out_dtype)
+
+
+def fir1d_ideal(x, h, *, dilation: int = 1, dtype=np.float64) -> np.ndarray:
+    """float64 model along the last axis: acc = acc + h[k] * xs[...] in
+    ascending k, separate multiply and add (fir_1d_ref.py:55-63).  The padded
+    zeros contribute +-0.0, which never changes a non-negative-zero sum, so
+    including them is bit-identical to the reference's skip."""
+    xs = prep_samples(x).astype(dtype)
+    hh = np.asarray(h, dtype=dtype)
+    acc = np.zeros(xs.shape, dtype=dtype)
+    for k, view in _shifted_views(xs, hh.size, dilation):
+        acc = acc + hh[k] * view
+    return acc
+
+
+def fir1d_fixed_iq(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16,
+                   out_dtype=np.uint8) -> np.ndarray:
+    """Interleaved I/Q with real taps = the 1-D model on z[0::2] and z[1::2]
+    (lib/mycomplex.cpp:12-22: complex*double and complex+complex only)."""
+    z = np.asarray(z)
+    out = np.empty(z.shape, dtype=out_dtype)
+    out[..., 0::2] = fir1d_fixed(z[..., 0::2], h, frac_bits, acc_bits, coeff_bits, out_dtype=out_dtype)
+    out[..., 1::2] = fir1d_fixed(z[..., 1::2], h, frac_bits, acc_bits, coeff_bits, out_dtype=out_dtype)
+    return out
+
+
+# --------------------------------------------------------------------------
+# 2-D (parity unpinned — our spec; see fir_oracle_py.fir2d_fixed)
+# --------------------------------------------------------------------------
+def _shifted_views_2d(xs: np.ndarray, kh: int, kw: int):
+    ch, cw = kh // 2, kw // 2
+    hgt, wid = xs.shape[-2:]
+    top, bottom = kh - 1 - ch, ch
+    left, right = kw - 1 - cw, cw
+    pad = [(0, 0)] * (xs.ndim - 2) + [(top, bottom), (left, right)]
+    xp = np.pad(xs, pad)
+    for m in range(kh):
+        r0 = top - (m - ch)
+        for n in range(kw):
+            c0 = left - (n - cw)
+            yield m, n, xp[..., r0:r0 + hgt, c0:c0 + wid]
+
+
+def fir2d_fixed(x, h2d, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16,
+                *, taps_are_quantized: bool = False, out_dtype=np.uint8) -> np.ndarray:
+    xs = prep_samples(x).astype(np.int64)
+    h2d = np.asarray(h2d)
+    hq = h2d.astype(np.int64) if taps_are_quantized else quantize_taps(h2d, frac_bits, coeff_bits)
+    kh, kw = hq.shape
+    acc = np.zeros(xs.shape, dtype=np.int64)
+    for m, n, view in _shifted_views_2d(xs, kh, kw):
+        if hq[m, n] != 0:
+            acc += view * hq[m, n]
+    return post_accumulate(acc, frac_bits, acc_bits).astype(out_dtype)
+
+
+def fir2d_ideal(x, h2d, dtype=np.float64) -> np.ndarray:
+    xs = prep_samples(x).astype(dtype)
+    hh = np.asarray(h2d, dtype=dtype)
+    kh, kw = hh.shape
+    acc = np.zeros(xs.shape, dtype=dtype)
+    for m, n, view in _shifted_views_2d(xs, kh, kw):
+        acc = acc + hh[m, n] * view
+    return acc
+
+
+def fir2d_separable_fixed(x, h_row, h_col, frac_bits: int = 12, acc_bits: int = 32,
+                          coeff_bits: int = 16) -> np.ndarray:
+    """Row pass then column pass, each a full 1-D reference model (two
+    roundings).  This one IS reference-pinned, by composition."""
+    rows_done = fir1d_fixed(x, h_row, frac_bits, acc_bits, coeff_bits)
+    cols_done = fir1d_fixed(np.swapaxes(rows_done, -1, -2), h_col, frac_bits, acc_bits, coeff_bits)
+    return np.ascontiguousarray(np.swapaxes(cols_done, -1, -2))

@@ -1,0 +1,135 @@
+// Shared declarations for the firgpu CUDA library (sm_100a only).
+//
+// Arithmetic contract (bit-exact with the reference, paths relative to the
+// reference root):
+//   prep    floor(x + 0.5) in float64, clamp [0,255]   fir_1d/model/python/fir_1d_ref.py:35-41
+//   taps    int32, quantised by the caller              fir_1d/model/python/fir_1d_fixed_ref.py:79-81
+//   sum     one accumulator per output, all taps        fir_1d_fixed_ref.py:95-107
+//   post    wrap(acc_bits) -> +2^(frac-1) -> >> frac -> clamp [0,255]   fir_1d_fixed_ref.py:110-126
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/firgpu.h"
+
+namespace firgpu {
+
+constexpr int kPixelMax = 255;
+constexpr int kInlineTaps = 32;   // taps passed by value in the launch parameters
+
+struct InlineTaps {
+    int32_t v[kInlineTaps];
+};
+struct InlineTapsF64 {
+    double v[kInlineTaps];
+};
+
+// ---- error plumbing (api.cu) ------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+void note_launch(int path);
+
+#define FIRGPU_CUDA(call)                                                  \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) return ::firgpu::check_cuda(e__, #call);  \
+    } while (0)
+
+inline int dtype_size(int dt)
+{
+    switch (dt) {
+    case FIRGPU_U8: return 1;
+    case FIRGPU_I16: return 2;
+    case FIRGPU_I32: return 4;
+    case FIRGPU_F32: return 4;
+    case FIRGPU_F64: return 8;
+    default: return 0;
+    }
+}
+
+// ---- device helpers ---------------------------------------------------------
+// Input container -> integer pixel in [0,255].
+__device__ __forceinline__ int prep_sample(uint8_t v) { return v; }
+__device__ __forceinline__ int prep_sample(int16_t v) { return min(max((int)v, 0), kPixelMax); }
+__device__ __forceinline__ int prep_sample(int32_t v) { return min(max(v, 0), kPixelMax); }
+__device__ __forceinline__ int prep_sample(double v)
+{
+    // floor(s + 0.5) with a correctly rounded float64 add, then clamp.  NaN /
+    // inf never reach the device: the host wrapper rejects them like
+    // _validate_x does (fir_1d_ref.py:27-33).
+    double r = floor(__dadd_rn(v, 0.5));
+    r = fmin(fmax(r, 0.0), 255.0);
+    return (int)r;
+}
+__device__ __forceinline__ int prep_sample(float v) { return prep_sample((double)v); }
+
+// wrap -> bias -> shift -> saturate on a 64-bit accumulator.  |acc| < 2^50 for
+// every supported tap count, so int64 itself never overflows and the only
+// wrap is the explicit one the reference performs.
+__device__ __forceinline__ int post_accumulate(long long acc, int frac_bits, int acc_bits)
+{
+    if (acc_bits < 64) {
+        unsigned long long m = (unsigned long long)acc & ((1ULL << acc_bits) - 1ULL);
+        if (m >> (acc_bits - 1)) m -= (1ULL << acc_bits);
+        acc = (long long)m;
+    }
+    long long v;
+    if (frac_bits > 62) {
+        v = 0;   // 0 <= acc + 2^(frac-1) < 2^frac for |acc| < 2^61
+    } else {
+        acc += 1LL << (frac_bits - 1);
+        v = acc >> frac_bits;
+    }
+    return (int)(v < 0 ? 0 : (v > kPixelMax ? kPixelMax : v));
+}
+
+template <typename T> struct DtypeOf;
+template <> struct DtypeOf<uint8_t> { static constexpr int value = FIRGPU_U8; };
+template <> struct DtypeOf<int16_t> { static constexpr int value = FIRGPU_I16; };
+template <> struct DtypeOf<int32_t> { static constexpr int value = FIRGPU_I32; };
+template <> struct DtypeOf<float> { static constexpr int value = FIRGPU_F32; };
+template <> struct DtypeOf<double> { static constexpr int value = FIRGPU_F64; };
+
+// ---- launchers implemented per translation unit -----------------------------
+struct Fir1dArgs {
+    const void *x;
+    void *y;
+    int in_dtype, out_dtype;
+    int64_t rows, cols, ld_x, ld_y;
+    int n_taps, dilation, frac_bits, acc_bits;
+    int64_t halo_left, halo_right;
+    cudaStream_t stream;
+};
+
+struct Fir2dArgs {
+    const void *x;
+    void *y;
+    int in_dtype, out_dtype;
+    int64_t n_img, height, width, ld_x, ld_y, img_stride_x, img_stride_y;
+    int kh, kw, frac_bits, acc_bits;
+    int64_t halo_top, halo_bottom;
+    cudaStream_t stream;
+};
+
+// fir1d_generic.cu
+int launch_fir1d_fixed_generic(const Fir1dArgs &a, const int32_t *hq_host);
+int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host);
+// fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
+// taps are outside the staged kernel's domain (caller falls to generic), <0 / >0 on error.
+int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
+// fir2d.cu
+int launch_fir2d_fixed_generic(const Fir2dArgs &a, const int32_t *hq_host);
+int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);
+int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq_host);
+
+// Device copy of a long tap vector, freed on the stream after the launch.
+template <typename T>
+int upload_taps(const T *host, int n, cudaStream_t s, T **dev)
+{
+    FIRGPU_CUDA(cudaMallocAsync((void **)dev, sizeof(T) * (size_t)n, s));
+    FIRGPU_CUDA(cudaMemcpyAsync(*dev, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+}  // namespace firgpu
