@@ -38,6 +38,7 @@
 #ifndef FIRGPU_H
 #define FIRGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -182,6 +183,11 @@ int firgpu_fir2d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
 int firgpu_fir2d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
                             int64_t n_img, int64_t height, int64_t width,
                             const double *h, int kh, int kw, int device);
+
+/* Page-locked host memory for callers without their own allocator (NumPy
+ * arrays wrapped around it are DMA'd directly by the _host entry points). */
+int firgpu_pinned_alloc(void **ptr, size_t bytes);
+int firgpu_pinned_free(void *ptr);
 
 /* Release cached device / pinned buffers and streams held for the _host
  * pipeline on every device. */

@@ -1,0 +1,614 @@
+// C-ABI of libfirgpu (include/firgpu.h): argument checks, kernel-family
+// dispatch, and the host-buffer pipelines.
+//
+// Nothing here computes a filter on the CPU.  Every compute entry point ends
+// in a CUDA launch or fails with the cudaError_t it got; there is no fallback.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace firgpu {
+
+namespace {
+thread_local char tl_error[512] = "";
+thread_local int tl_path = FIRGPU_PATH_NONE;
+thread_local int64_t tl_launches = 0;
+}  // namespace
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    snprintf(tl_error, sizeof(tl_error), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+void note_launch(int path)
+{
+    tl_path = path;
+    ++tl_launches;
+}
+
+namespace {
+
+bool fixed_in_ok(int dt) { return dt >= FIRGPU_U8 && dt <= FIRGPU_F64; }
+
+int check_1d(const char *fn, const void *x, const void *y, int in_dtype, int64_t rows, int64_t cols,
+             int64_t ld_x, int64_t ld_y, const void *taps, int n_taps, int dilation,
+             int64_t halo_left, int64_t halo_right)
+{
+    if (!fixed_in_ok(in_dtype)) return set_error(FIRGPU_E_DTYPE, "%s: unsupported in_dtype %d", fn, in_dtype);
+    if (rows < 0 || cols < 0) return set_error(FIRGPU_E_SHAPE, "%s: negative shape rows=%lld cols=%lld", fn, (long long)rows, (long long)cols);
+    if (rows > 1 && (ld_x < cols || ld_y < cols))
+        return set_error(FIRGPU_E_SHAPE, "%s: leading dimension smaller than cols (ld_x=%lld ld_y=%lld cols=%lld)", fn,
+                         (long long)ld_x, (long long)ld_y, (long long)cols);
+    if (n_taps < 1 || n_taps > FIRGPU_MAX_TAPS) return set_error(FIRGPU_E_TAPS, "%s: n_taps=%d outside [1,%d]", fn, n_taps, FIRGPU_MAX_TAPS);
+    if (dilation < 1) return set_error(FIRGPU_E_DILATION, "%s: dilation=%d must be >= 1", fn, dilation);
+    if (halo_left < 0 || halo_right < 0) return set_error(FIRGPU_E_HALO, "%s: negative halo", fn);
+    if (!taps) return set_error(FIRGPU_E_NULL, "%s: taps pointer is NULL", fn);
+    if (rows > 0 && cols > 0 && (!x || !y)) return set_error(FIRGPU_E_NULL, "%s: NULL data pointer with non-empty shape", fn);
+    return 0;
+}
+
+int check_2d(const char *fn, const void *x, const void *y, int in_dtype, int64_t n_img, int64_t height, int64_t width,
+             int64_t ld_x, int64_t ld_y, const void *taps, int kh, int kw, int64_t halo_top, int64_t halo_bottom)
+{
+    if (!fixed_in_ok(in_dtype)) return set_error(FIRGPU_E_DTYPE, "%s: unsupported in_dtype %d", fn, in_dtype);
+    if (n_img < 0 || height < 0 || width < 0) return set_error(FIRGPU_E_SHAPE, "%s: negative shape", fn);
+    if (height > 1 && (ld_x < width || ld_y < width)) return set_error(FIRGPU_E_SHAPE, "%s: leading dimension smaller than width", fn);
+    if (kh < 1 || kw < 1 || (int64_t)kh * kw > FIRGPU_MAX_TAPS)
+        return set_error(FIRGPU_E_TAPS, "%s: kernel %dx%d outside [1,%d] taps", fn, kh, kw, FIRGPU_MAX_TAPS);
+    if (halo_top < 0 || halo_bottom < 0) return set_error(FIRGPU_E_HALO, "%s: negative halo", fn);
+    if (!taps) return set_error(FIRGPU_E_NULL, "%s: taps pointer is NULL", fn);
+    if (n_img > 0 && height > 0 && width > 0 && (!x || !y)) return set_error(FIRGPU_E_NULL, "%s: NULL data pointer with non-empty shape", fn);
+    return 0;
+}
+
+int check_bits(const char *fn, int frac_bits, int acc_bits)
+{
+    if (frac_bits < 1 || acc_bits < 1) return set_error(FIRGPU_E_BITS, "%s: frac_bits=%d and acc_bits=%d must be >= 1", fn, frac_bits, acc_bits);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer pipeline: chunks travel H2D -> kernel -> D2H on kSlots streams,
+// so the two copy engines and the SMs overlap.  Pageable host memory is
+// bounced through pinned slot buffers; pinned / registered memory is DMA'd
+// directly.
+// ---------------------------------------------------------------------------
+constexpr int kSlots = 3;
+constexpr size_t kChunkTarget = 32u << 20;   // input bytes per chunk
+
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t stream[kSlots] = {};
+    void *d_in[kSlots] = {}, *d_out[kSlots] = {};
+    void *p_in[kSlots] = {}, *p_out[kSlots] = {};
+    size_t d_in_cap = 0, d_out_cap = 0, p_in_cap = 0, p_out_cap = 0;
+    bool ready = false;
+};
+
+std::mutex g_ctx_mu;
+std::map<int, HostCtx *> g_ctx;
+
+HostCtx *ctx_for(int device)
+{
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) return it->second;
+    HostCtx *c = new HostCtx();
+    g_ctx[device] = c;
+    return c;
+}
+
+int ctx_reserve(HostCtx *c, size_t in_bytes, size_t out_bytes, bool pin_in, bool pin_out)
+{
+    if (!c->ready) {
+        for (int s = 0; s < kSlots; ++s) FIRGPU_CUDA(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
+        c->ready = true;
+    }
+    auto grow = [](void **bufs, size_t *cap, size_t want, bool pinned) -> int {
+        if (want <= *cap) return 0;
+        for (int s = 0; s < kSlots; ++s) {
+            if (bufs[s]) FIRGPU_CUDA(pinned ? cudaFreeHost(bufs[s]) : cudaFree(bufs[s]));
+            bufs[s] = nullptr;
+        }
+        *cap = 0;
+        for (int s = 0; s < kSlots; ++s)
+            FIRGPU_CUDA(pinned ? cudaHostAlloc(&bufs[s], want, cudaHostAllocDefault) : cudaMalloc(&bufs[s], want));
+        *cap = want;
+        return 0;
+    };
+    int rc;
+    if ((rc = grow(c->d_in, &c->d_in_cap, in_bytes, false))) return rc;
+    if ((rc = grow(c->d_out, &c->d_out_cap, out_bytes, false))) return rc;
+    if (pin_in && (rc = grow(c->p_in, &c->p_in_cap, in_bytes, true))) return rc;
+    if (pin_out && (rc = grow(c->p_out, &c->p_out_cap, out_bytes, true))) return rc;
+    return 0;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    int enter(int device)
+    {
+        if (device < 0) return 0;
+        FIRGPU_CUDA(cudaGetDevice(&prev));
+        if (prev != device) {
+            FIRGPU_CUDA(cudaSetDevice(device));
+            active = true;
+        }
+        return 0;
+    }
+    ~DeviceGuard()
+    {
+        if (active) cudaSetDevice(prev);
+    }
+};
+
+// A rectangular piece of a [rows x cols] problem plus the neighbour columns /
+// rows that travel with it.
+struct Piece {
+    int64_t r0, nr;          // rows (1-D) or image rows incl. nothing of the halo (2-D)
+    int64_t c0, nc;          // columns
+    int64_t before, after;   // halo elements (1-D: scalars; 2-D: rows)
+};
+
+// Copy `nr` rows of `row_bytes` bytes between pitched buffers.
+int copy_rows_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t nr,
+                    cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (nr == 0 || row_bytes == 0) return 0;
+    if (nr == 1 || (dpitch == row_bytes && spitch == row_bytes)) {
+        FIRGPU_CUDA(cudaMemcpyAsync(dst, src, row_bytes * nr, kind, s));
+    } else {
+        FIRGPU_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, nr, kind, s));
+    }
+    return 0;
+}
+
+void copy_rows_host(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t nr)
+{
+    if (dpitch == row_bytes && spitch == row_bytes) {
+        memcpy(dst, src, row_bytes * nr);
+        return;
+    }
+    for (size_t r = 0; r < nr; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, row_bytes);
+}
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// 1-D driver.  `run(d_x, d_y, nr, nc, ldd_x, ldd_y, before, after, stream)`
+// launches the device entry point on one piece.
+template <typename Run>
+int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                int64_t reach_before, int64_t reach_after, int device, Run run)
+{
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc) return rc;
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    HostCtx *c = ctx_for(dev);
+    std::lock_guard<std::mutex> lock(c->mu);
+
+    // Pieces: whole rows while a row fits the chunk target, else column
+    // segments of one row with the taps' reach attached on both sides.
+    std::vector<Piece> pieces;
+    const int64_t row_bytes = cols * es;
+    const int64_t q_in = 16 / es;                      // scalars per 16 bytes
+    if ((size_t)row_bytes <= kChunkTarget) {
+        int64_t per = (int64_t)(kChunkTarget / (size_t)row_bytes);
+        if (per < 1) per = 1;
+        // keep at least kSlots pieces in flight when there is enough work
+        if (rows >= 2 * kSlots && per > (rows + 2 * kSlots - 1) / (2 * kSlots) && (size_t)(row_bytes * rows) > (4u << 20))
+            per = (rows + 2 * kSlots - 1) / (2 * kSlots);
+        for (int64_t r = 0; r < rows; r += per) pieces.push_back({r, std::min(per, rows - r), 0, cols, 0, 0});
+    } else {
+        const int64_t seg = round_up((int64_t)(kChunkTarget / es), 16384);
+        for (int64_t r = 0; r < rows; ++r)
+            for (int64_t c0 = 0; c0 < cols; c0 += seg) {
+                const int64_t nc = std::min(seg, cols - c0);
+                pieces.push_back({r, 1, c0, nc, std::min(reach_before, c0), std::min(reach_after, cols - c0 - nc)});
+            }
+    }
+    // Device layout of a piece: rows at a 16-byte-aligned pitch; a column
+    // segment sits 16-byte aligned with its leading halo right before it.
+    int64_t max_in = 0, max_out = 0;
+    for (const Piece &p : pieces) {
+        const int64_t ldd = round_up(p.nc + round_up(p.before, q_in) + p.after, q_in);
+        max_in = std::max(max_in, ldd * p.nr * es + 256);
+        max_out = std::max(max_out, round_up(p.nc, 16) * p.nr * os + 256);
+    }
+    const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
+    if ((rc = ctx_reserve(c, (size_t)max_in, (size_t)max_out, !x_pinned, !y_pinned))) return rc;
+
+    struct Pending {
+        bool busy = false;
+        Piece p;
+        int64_t ldd_y = 0;
+    } pending[kSlots];
+    auto finalize = [&](int s) -> int {
+        if (!pending[s].busy) return 0;
+        FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
+        if (!y_pinned) {
+            const Piece &p = pending[s].p;
+            copy_rows_host((char *)y + (p.r0 * ld_y + p.c0) * os, (size_t)ld_y * os, c->p_out[s],
+                           (size_t)pending[s].ldd_y * os, (size_t)p.nc * os, (size_t)p.nr);
+        }
+        pending[s].busy = false;
+        return 0;
+    };
+
+    for (size_t k = 0; k < pieces.size(); ++k) {
+        const int s = (int)(k % kSlots);
+        if ((rc = finalize(s))) return rc;
+        const Piece &p = pieces[k];
+        const int64_t lead = round_up(p.before, q_in);                 // aligned offset of the segment
+        const int64_t span = p.before + p.nc + p.after;                // scalars copied per row
+        const int64_t ldd_x = round_up(lead + p.nc + p.after, q_in);
+        const int64_t ldd_y = round_up(p.nc, 16);
+        const char *src = (const char *)x + (p.r0 * ld_x + p.c0 - p.before) * es;
+        char *d_first = (char *)c->d_in[s] + (lead - p.before) * es;   // where the halo's first scalar lands
+        if (x_pinned) {
+            if ((rc = copy_rows_async(d_first, (size_t)ldd_x * es, src, (size_t)ld_x * es, (size_t)span * es,
+                                      (size_t)p.nr, cudaMemcpyHostToDevice, c->stream[s])))
+                return rc;
+        } else {
+            copy_rows_host((char *)c->p_in[s], (size_t)span * es, src, (size_t)ld_x * es, (size_t)span * es, (size_t)p.nr);
+            if ((rc = copy_rows_async(d_first, (size_t)ldd_x * es, c->p_in[s], (size_t)span * es, (size_t)span * es,
+                                      (size_t)p.nr, cudaMemcpyHostToDevice, c->stream[s])))
+                return rc;
+        }
+        rc = run((const char *)c->d_in[s] + lead * es, c->d_out[s], p.nr, p.nc, ldd_x, ldd_y, p.before, p.after,
+                 c->stream[s]);
+        if (rc) return rc;
+        char *dst = y_pinned ? (char *)y + (p.r0 * ld_y + p.c0) * os : (char *)c->p_out[s];
+        const size_t dpitch = y_pinned ? (size_t)ld_y * os : (size_t)ldd_y * os;
+        if ((rc = copy_rows_async(dst, dpitch, c->d_out[s], (size_t)ldd_y * os, (size_t)p.nc * os, (size_t)p.nr,
+                                  cudaMemcpyDeviceToHost, c->stream[s])))
+            return rc;
+        pending[s].busy = true;
+        pending[s].p = p;
+        pending[s].ldd_y = ldd_y;
+    }
+    for (int s = 0; s < kSlots; ++s)
+        if ((rc = finalize(s))) return rc;
+    return 0;
+}
+
+// 2-D driver: one image row band per piece, with the kernel's vertical reach
+// attached above and below.
+template <typename Run>
+int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t height, int64_t width,
+                int64_t reach_above, int64_t reach_below, int device, Run run)
+{
+    if (n_img == 0 || height == 0 || width == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc) return rc;
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    HostCtx *c = ctx_for(dev);
+    std::lock_guard<std::mutex> lock(c->mu);
+
+    const int64_t row_bytes = width * es;
+    int64_t band = (int64_t)(kChunkTarget / (size_t)std::max<int64_t>(row_bytes, 1));
+    if (band < 8) band = 8;
+    if (band > height) band = height;
+    std::vector<Piece> pieces;     // r0 = image * height + first row
+    for (int64_t b = 0; b < n_img; ++b)
+        for (int64_t r = 0; r < height; r += band) {
+            const int64_t nr = std::min(band, height - r);
+            pieces.push_back({b * height + r, nr, 0, width, std::min(reach_above, r), std::min(reach_below, height - r - nr)});
+        }
+    const int64_t ldd_x = round_up(width, 16 / es), ldd_y = round_up(width, 16);
+    const size_t max_in = (size_t)(ldd_x * (band + reach_above + reach_below) * es + 256);
+    const size_t max_out = (size_t)(ldd_y * band * os + 256);
+    const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
+    if ((rc = ctx_reserve(c, max_in, max_out, !x_pinned, !y_pinned))) return rc;
+
+    struct Pending {
+        bool busy = false;
+        Piece p;
+    } pending[kSlots];
+    auto finalize = [&](int s) -> int {
+        if (!pending[s].busy) return 0;
+        FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
+        if (!y_pinned) {
+            const Piece &p = pending[s].p;
+            copy_rows_host((char *)y + p.r0 * width * os, (size_t)width * os, c->p_out[s], (size_t)ldd_y * os,
+                           (size_t)width * os, (size_t)p.nr);
+        }
+        pending[s].busy = false;
+        return 0;
+    };
+    for (size_t k = 0; k < pieces.size(); ++k) {
+        const int s = (int)(k % kSlots);
+        if ((rc = finalize(s))) return rc;
+        const Piece &p = pieces[k];
+        const int64_t nrows = p.before + p.nr + p.after;
+        const char *src = (const char *)x + (p.r0 - p.before) * width * es;
+        if (x_pinned) {
+            if ((rc = copy_rows_async(c->d_in[s], (size_t)ldd_x * es, src, (size_t)width * es, (size_t)width * es,
+                                      (size_t)nrows, cudaMemcpyHostToDevice, c->stream[s])))
+                return rc;
+        } else {
+            memcpy(c->p_in[s], src, (size_t)(nrows * width * es));
+            if ((rc = copy_rows_async(c->d_in[s], (size_t)ldd_x * es, c->p_in[s], (size_t)width * es, (size_t)width * es,
+                                      (size_t)nrows, cudaMemcpyHostToDevice, c->stream[s])))
+                return rc;
+        }
+        rc = run((const char *)c->d_in[s] + p.before * ldd_x * es, c->d_out[s], p.nr, width, ldd_x, ldd_y, p.before, p.after,
+                 c->stream[s]);
+        if (rc) return rc;
+        char *dst = y_pinned ? (char *)y + p.r0 * width * os : (char *)c->p_out[s];
+        const size_t dpitch = y_pinned ? (size_t)width * os : (size_t)ldd_y * os;
+        if ((rc = copy_rows_async(dst, dpitch, c->d_out[s], (size_t)ldd_y * os, (size_t)width * os, (size_t)p.nr,
+                                  cudaMemcpyDeviceToHost, c->stream[s])))
+            return rc;
+        pending[s].busy = true;
+        pending[s].p = p;
+    }
+    for (int s = 0; s < kSlots; ++s)
+        if ((rc = finalize(s))) return rc;
+    return 0;
+}
+
+int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtype == FIRGPU_I16 ? 2 : 0; }
+int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
+
+}  // namespace
+}  // namespace firgpu
+
+using namespace firgpu;
+
+extern "C" {
+
+int firgpu_version(void) { return FIRGPU_VERSION; }
+const char *firgpu_last_error(void) { return tl_error; }
+int firgpu_last_path(void) { return tl_path; }
+int64_t firgpu_launch_count(void) { return tl_launches; }
+
+int firgpu_device_count(int *count)
+{
+    if (!count) return set_error(FIRGPU_E_NULL, "firgpu_device_count: NULL");
+    FIRGPU_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                       int64_t ld_y, const int32_t *hq, int n_taps, int dilation, int frac_bits, int acc_bits,
+                       int64_t halo_left_valid, int64_t halo_right_valid, void *stream)
+{
+    int rc = check_1d("firgpu_fir1d_fixed", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation,
+                      halo_left_valid, halo_right_valid);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed", frac_bits, acc_bits))) return rc;
+    if (!out_size_fixed(out_dtype)) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed: out_dtype must be U8 or I16, got %d", out_dtype);
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, frac_bits, acc_bits,
+                halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    rc = try_launch_fir1d_fixed_staged(a, hq);
+    if (rc == 1) return 0;
+    if (rc != 0) return rc;
+    return launch_fir1d_fixed_generic(a, hq);
+}
+
+int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols,
+                             int64_t ld_x, int64_t ld_y, int64_t filter_stride_y, const int32_t *hq, int n_filters,
+                             int n_taps, int dilation, int frac_bits, int acc_bits, void *stream)
+{
+    if (n_filters < 0) return set_error(FIRGPU_E_SHAPE, "firgpu_fir1d_fixed_multi: n_filters=%d", n_filters);
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_multi: out_dtype must be U8 or I16, got %d", out_dtype);
+    // One pass per tap set; the input stays L2-resident between passes for
+    // image-sized inputs (<= 126 MB), so HBM sees it once.
+    for (int f = 0; f < n_filters; ++f) {
+        int rc = firgpu_fir1d_fixed(x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows,
+                                    cols, ld_x, ld_y, hq + (size_t)f * n_taps, n_taps, dilation, frac_bits, acc_bits, 0, 0,
+                                    stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                       int64_t ld_y, const double *h, int n_taps, int dilation, int64_t halo_left_valid,
+                       int64_t halo_right_valid, void *stream)
+{
+    int rc = check_1d("firgpu_fir1d_ideal", x, y, in_dtype, rows, cols, ld_x, ld_y, h, n_taps, dilation, halo_left_valid,
+                      halo_right_valid);
+    if (rc) return rc;
+    if (!out_size_ideal(out_dtype)) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_ideal: out_dtype must be F64 or F32, got %d", out_dtype);
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, 0, 0,
+                halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    return launch_fir1d_ideal(a, h);
+}
+
+int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int64_t n_img, int64_t height, int64_t width,
+                       int64_t ld_x, int64_t ld_y, int64_t img_stride_x, int64_t img_stride_y, const int32_t *hq, int kh,
+                       int kw, int frac_bits, int acc_bits, int64_t halo_top_valid, int64_t halo_bottom_valid, void *stream)
+{
+    int rc = check_2d("firgpu_fir2d_fixed", x, y, in_dtype, n_img, height, width, ld_x, ld_y, hq, kh, kw, halo_top_valid,
+                      halo_bottom_valid);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir2d_fixed", frac_bits, acc_bits))) return rc;
+    if (!out_size_fixed(out_dtype)) return set_error(FIRGPU_E_DTYPE, "firgpu_fir2d_fixed: out_dtype must be U8 or I16, got %d", out_dtype);
+    if (n_img == 0 || height == 0 || width == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir2dArgs a{x, y, in_dtype, out_dtype, n_img, height, width, ld_x, ld_y, img_stride_x, img_stride_y, kh, kw,
+                frac_bits, acc_bits, halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
+    rc = try_launch_fir2d_fixed_tiled(a, hq);
+    if (rc == 1) return 0;
+    if (rc != 0) return rc;
+    return launch_fir2d_fixed_generic(a, hq);
+}
+
+int firgpu_fir2d_ideal(const void *x, void *y, int in_dtype, int out_dtype, int64_t n_img, int64_t height, int64_t width,
+                       int64_t ld_x, int64_t ld_y, int64_t img_stride_x, int64_t img_stride_y, const double *h, int kh,
+                       int kw, int64_t halo_top_valid, int64_t halo_bottom_valid, void *stream)
+{
+    int rc = check_2d("firgpu_fir2d_ideal", x, y, in_dtype, n_img, height, width, ld_x, ld_y, h, kh, kw, halo_top_valid,
+                      halo_bottom_valid);
+    if (rc) return rc;
+    if (!out_size_ideal(out_dtype)) return set_error(FIRGPU_E_DTYPE, "firgpu_fir2d_ideal: out_dtype must be F64 or F32, got %d", out_dtype);
+    if (n_img == 0 || height == 0 || width == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir2dArgs a{x, y, in_dtype, out_dtype, n_img, height, width, ld_x, ld_y, img_stride_x, img_stride_y, kh, kw, 0, 0,
+                halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
+    return launch_fir2d_ideal(a, h);
+}
+
+// ---- host-buffer entry points ---------------------------------------------
+int firgpu_fir1d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                            int64_t ld_y, const int32_t *hq, int n_taps, int dilation, int frac_bits, int acc_bits,
+                            int device)
+{
+    int rc = check_1d("firgpu_fir1d_fixed_host", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed_host", frac_bits, acc_bits))) return rc;
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_host: out_dtype must be U8 or I16, got %d", out_dtype);
+    const int64_t centre = n_taps / 2;
+    return pipeline_1d(x, y, dtype_size(in_dtype), os, rows, cols, ld_x, ld_y, (n_taps - 1 - centre) * (int64_t)dilation,
+                       centre * (int64_t)dilation, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before,
+                           int64_t after, cudaStream_t s) {
+                           return firgpu_fir1d_fixed(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, hq, n_taps, dilation,
+                                                     frac_bits, acc_bits, before, after, (void *)s);
+                       });
+}
+
+int firgpu_fir1d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                            int64_t ld_y, const double *h, int n_taps, int dilation, int device)
+{
+    int rc = check_1d("firgpu_fir1d_ideal_host", x, y, in_dtype, rows, cols, ld_x, ld_y, h, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    const int os = out_size_ideal(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_ideal_host: out_dtype must be F64 or F32, got %d", out_dtype);
+    const int64_t centre = n_taps / 2;
+    return pipeline_1d(x, y, dtype_size(in_dtype), os, rows, cols, ld_x, ld_y, (n_taps - 1 - centre) * (int64_t)dilation,
+                       centre * (int64_t)dilation, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before,
+                           int64_t after, cudaStream_t s) {
+                           return firgpu_fir1d_ideal(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, h, n_taps, dilation,
+                                                     before, after, (void *)s);
+                       });
+}
+
+int firgpu_fir2d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t n_img, int64_t height,
+                            int64_t width, const int32_t *hq, int kh, int kw, int frac_bits, int acc_bits, int device)
+{
+    int rc = check_2d("firgpu_fir2d_fixed_host", x, y, in_dtype, n_img, height, width, width, width, hq, kh, kw, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir2d_fixed_host", frac_bits, acc_bits))) return rc;
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir2d_fixed_host: out_dtype must be U8 or I16, got %d", out_dtype);
+    const int64_t ch = kh / 2;
+    // rows above come from i - m + ch with m up to kh-1; rows below from m = 0
+    return pipeline_2d(x, y, dtype_size(in_dtype), os, n_img, height, width, kh - 1 - ch, ch, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t w, int64_t lx, int64_t ly, int64_t above,
+                           int64_t below, cudaStream_t s) {
+                           return firgpu_fir2d_fixed(dx, dy, in_dtype, out_dtype, 1, nr, w, lx, ly, 0, 0, hq, kh, kw,
+                                                     frac_bits, acc_bits, above, below, (void *)s);
+                       });
+}
+
+int firgpu_fir2d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t n_img, int64_t height,
+                            int64_t width, const double *h, int kh, int kw, int device)
+{
+    int rc = check_2d("firgpu_fir2d_ideal_host", x, y, in_dtype, n_img, height, width, width, width, h, kh, kw, 0, 0);
+    if (rc) return rc;
+    const int os = out_size_ideal(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir2d_ideal_host: out_dtype must be F64 or F32, got %d", out_dtype);
+    const int64_t ch = kh / 2;
+    return pipeline_2d(x, y, dtype_size(in_dtype), os, n_img, height, width, kh - 1 - ch, ch, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t w, int64_t lx, int64_t ly, int64_t above,
+                           int64_t below, cudaStream_t s) {
+                           return firgpu_fir2d_ideal(dx, dy, in_dtype, out_dtype, 1, nr, w, lx, ly, 0, 0, h, kh, kw,
+                                                     above, below, (void *)s);
+                       });
+}
+
+int firgpu_pinned_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return set_error(FIRGPU_E_NULL, "firgpu_pinned_alloc: NULL");
+    FIRGPU_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int firgpu_pinned_free(void *ptr)
+{
+    if (ptr) FIRGPU_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+int firgpu_release_cache(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto &kv : g_ctx) {
+        HostCtx *c = kv.second;
+        std::lock_guard<std::mutex> l2(c->mu);
+        cudaSetDevice(kv.first);
+        for (int s = 0; s < kSlots; ++s) {
+            if (c->d_in[s]) cudaFree(c->d_in[s]);
+            if (c->d_out[s]) cudaFree(c->d_out[s]);
+            if (c->p_in[s]) cudaFreeHost(c->p_in[s]);
+            if (c->p_out[s]) cudaFreeHost(c->p_out[s]);
+            c->d_in[s] = c->d_out[s] = c->p_in[s] = c->p_out[s] = nullptr;
+            if (c->ready) cudaStreamDestroy(c->stream[s]);
+        }
+        c->d_in_cap = c->d_out_cap = c->p_in_cap = c->p_out_cap = 0;
+        c->ready = false;
+    }
+    cudaSetDevice(prev);
+    cudaGetLastError();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+"""Shared driver of the two output-vector generators.
+
+The reference filters an image one row at a time through a Python call per
+row (fir_1d/sim/vector/gen_fixed_output.py:44-59, gen_ideal_output.py:40-49).
+Rows are independent and zero-padded separately, so here a whole image is ONE
+batched call into libfirgpu ([height, width] = rows x cols).  File discovery,
+naming and the skip-unless-overwrite rule are those of
+gen_fixed_output.py:19-31,62-107.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable
+
+import numpy as np
+
+INPUT_SUFFIX = "_x_u8.npy"
+
+
+def list_input_files(input_dir: Path) -> list[Path]:
+    found = [p for p in Path(input_dir).glob("*.npy") if p.name.endswith(INPUT_SUFFIX)]
+    found.sort(key=lambda p: p.name.lower())
+    return found
+
+
+def load_image_u8(path: Path) -> np.ndarray:
+    x = np.load(path)
+    if x.ndim != 2:
+        raise ValueError(f"{path.name}: expected 2D array, got shape={x.shape}")
+    return x if x.dtype == np.uint8 else x.astype(np.uint8)
+
+
+def case_stem(path: Path) -> str:
+    return path.name[: -len(INPUT_SUFFIX)] if path.name.endswith(INPUT_SUFFIX) else path.stem
+
+
+def generate_outputs(*, input_dir: Path, out_dir: Path, coeff_map: dict[str, list[float]], name_format: str,
+                     run_image: Callable[[np.ndarray, list[float]], np.ndarray], overwrite: bool) -> int:
+    """For every input image x every coefficient set that is missing (or all,
+    with ``overwrite``): filter, save, count.  ``name_format`` receives
+    ``stem`` and ``coeff``."""
+    inputs = list_input_files(input_dir)
+    if not inputs:
+        raise FileNotFoundError(f"No input .npy files found in {input_dir}")
+    out_dir.mkdir(parents=True, exist_ok=True)
+    written = 0
+    for path in inputs:
+        todo = []
+        for coeff_name, taps in coeff_map.items():
+            target = out_dir / name_format.format(stem=case_stem(path), coeff=coeff_name)
+            if overwrite or not target.exists():
+                todo.append((target, taps))
+        if not todo:
+            continue
+        image = load_image_u8(path)
+        for target, taps in todo:
+            np.save(target, run_image(image, taps))
+            written += 1
+    return written

@@ -1,0 +1,379 @@
+"""Array-level entry points of the B200 FIR path.
+
+Every function validates and quantises on the host exactly like the reference
+(``firgpu.quant``), then makes ONE call into ``libfirgpu.so``:
+
+* NumPy arrays / Python sequences / CPU torch tensors -> the ``*_host`` C entry
+  points (chunked H2D -> kernel -> D2H pipeline inside the library);
+* CUDA torch tensors (or anything else exposing a device pointer through
+  ``DeviceArray``) -> the stream-ordered device entry points, result stays on
+  the device.
+
+Shapes: 1-D functions filter along the last axis, every leading index is an
+independent, separately zero-padded row (reference:
+fir_1d/sim/vector/gen_fixed_output.py:44-59).  2-D functions filter the last
+two axes.  There is no CPU arithmetic path in this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib, quant
+
+_NP_CODE = {np.dtype(np.uint8): _lib.U8, np.dtype(np.int16): _lib.I16, np.dtype(np.int32): _lib.I32,
+            np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+_OUT_FIXED = {np.dtype(np.uint8): _lib.U8, np.dtype(np.int16): _lib.I16}
+_OUT_IDEAL = {np.dtype(np.float64): _lib.F64, np.dtype(np.float32): _lib.F32}
+
+
+@dataclass
+class DeviceArray:
+    """A raw device buffer for callers that do not use torch: ``ptr`` is a
+    CUDA device pointer to ``shape`` elements of ``dtype`` (C order)."""
+    ptr: int
+    shape: tuple
+    dtype: np.dtype
+    device: int = 0
+    stream: int = 0
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _np_container(x) -> np.ndarray:
+    """Any host input -> C-contiguous array in one of the five containers the
+    kernels read.  Integer types the kernels do not read are clamped here
+    (rounding is the identity on integers, fir_1d_ref.py:35-41)."""
+    a = np.asarray(x)
+    if a.dtype == object:
+        a = np.asarray(x, dtype=np.float64)
+    if a.dtype in _NP_CODE:
+        pass
+    elif a.dtype == np.bool_:
+        a = a.astype(np.uint8)
+    elif a.dtype == np.int8:
+        a = a.astype(np.int16)
+    elif a.dtype.kind in "iu":
+        a = np.clip(a, 0, 255).astype(np.uint8)
+    elif a.dtype.kind == "f":
+        a = a.astype(np.float32 if a.dtype.itemsize < 4 else np.float64)
+    else:
+        raise TypeError(f"unsupported sample dtype {a.dtype}")
+    return np.ascontiguousarray(a)
+
+
+def _torch_container(t):
+    import torch
+    if t.dtype in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64):
+        pass
+    elif t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    elif t.dtype == torch.int8:
+        t = t.to(torch.int16)
+    elif t.dtype in (torch.int64,):
+        t = t.clamp(0, 255).to(torch.uint8)
+    elif t.dtype in (torch.float16, torch.bfloat16):
+        t = t.to(torch.float32)
+    else:
+        raise TypeError(f"unsupported sample dtype {t.dtype}")
+    return t.contiguous()
+
+
+def _torch_code(t) -> int:
+    import torch
+    return {torch.uint8: _lib.U8, torch.int16: _lib.I16, torch.int32: _lib.I32,
+            torch.float32: _lib.F32, torch.float64: _lib.F64}[t.dtype]
+
+
+def _torch_dtype(np_dtype):
+    import torch
+    return {np.dtype(np.uint8): torch.uint8, np.dtype(np.int16): torch.int16,
+            np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(np_dtype)]
+
+
+def _check_finite_torch(t) -> None:
+    import torch
+    if t.is_floating_point() and t.numel():
+        ok = torch.isfinite(t)
+        if not bool(ok.all()):
+            index = int(torch.argmin(ok.reshape(-1).to(torch.uint8)))
+            raise ValueError(f"Invalid x[{index}]={float(t.reshape(-1)[index])}: x must be finite.")
+
+
+def _cuda_rows(x, allow_copy: bool):
+    """CUDA tensor -> (tensor to read, rows, cols, row pitch in elements).
+    1-D tensors and 2-D tensors whose last axis is dense are read in place,
+    pitch included (that is how a shard view of a wider buffer arrives);
+    anything else is made contiguous, which is only legal without halos."""
+    import torch
+    native = x.dtype in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64)
+    if native and x.dim() == 1 and (x.stride(0) == 1 or x.shape[0] <= 1):
+        return x, 1, int(x.shape[0]), int(x.shape[0])
+    if native and x.dim() == 2 and (x.stride(1) == 1 or x.shape[1] <= 1) and (x.stride(0) >= x.shape[1] or x.shape[0] <= 1):
+        return x, int(x.shape[0]), int(x.shape[1]), int(max(x.stride(0), x.shape[1]))
+    if native and x.is_contiguous():
+        rows, cols = _rows_cols(x.shape)
+        return x, rows, cols, cols
+    if not allow_copy:
+        raise ValueError("this tensor would need a dtype/layout copy, which is not possible for in-place shard views")
+    t = _torch_container(x)
+    rows, cols = _rows_cols(t.shape)
+    return t, rows, cols, cols
+
+
+def _rows_cols(shape) -> tuple[int, int]:
+    if len(shape) == 0:
+        raise ValueError("x must have at least one dimension")
+    cols = int(shape[-1])
+    rows = 1
+    for s in shape[:-1]:
+        rows *= int(s)
+    return rows, cols
+
+
+def _imgs(shape) -> tuple[int, int, int]:
+    if len(shape) < 2:
+        raise ValueError("2-D FIR needs an input with at least two dimensions")
+    n = 1
+    for s in shape[:-2]:
+        n *= int(s)
+    return n, int(shape[-2]), int(shape[-1])
+
+
+def _taps_ptr(arr: np.ndarray):
+    return arr.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------
+# 1-D
+# ---------------------------------------------------------------------------
+def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *,
+                dilation: int = 1, out_dtype=np.uint8, out=None, device: int = -1,
+                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True):
+    """Bit-true fixed-point FIR (fir_1d/model/python/fir_1d_fixed_ref.py:12-130)
+    along the last axis of ``x``.
+
+    ``dilation=2`` filters interleaved I/Q.  ``halo_*_valid`` say how many
+    scalars before / after every row are real neighbour samples the kernel may
+    read instead of assuming zeros (device inputs only: a shard of a longer
+    signal).  Returns uint8 (or ``out_dtype=np.int16``: same values in an int16
+    container) of the same shape, on the same side (host / device) as ``x``.
+    """
+    quant.validate_taps(h)
+    if _is_torch(x):
+        if validate:
+            _check_finite_torch(x)
+    elif not isinstance(x, DeviceArray):
+        x = _np_container(x)
+        if validate:
+            quant.check_samples_finite(x)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = quant.quantize_taps(h, frac_bits, coeff_bits)
+    return fir1d_fixed_q(x, hq, frac_bits, acc_bits, dilation=dilation, out_dtype=out_dtype, out=out,
+                         device=device, halo_left_valid=halo_left_valid, halo_right_valid=halo_right_valid)
+
+
+def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, out_dtype=np.uint8, out=None,
+                  device: int = -1, halo_left_valid: int = 0, halo_right_valid: int = 0):
+    """Same as :func:`fir1d_fixed` with already-quantised integer taps and no
+    sample validation: the thin layer over ``firgpu_fir1d_fixed[_host]``."""
+    L = _lib.lib()
+    hq = np.ascontiguousarray(hq, dtype=np.int32).reshape(-1)
+    out_code = _OUT_FIXED[np.dtype(out_dtype)]
+    if isinstance(x, DeviceArray):
+        rows, cols = _rows_cols(x.shape)
+        if out is None:
+            raise ValueError("DeviceArray inputs need an explicit out=DeviceArray")
+        _lib.check(L.firgpu_fir1d_fixed(x.ptr, out.ptr, _NP_CODE[np.dtype(x.dtype)], _OUT_FIXED[np.dtype(out.dtype)],
+                                        rows, cols, cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits,
+                                        halo_left_valid, halo_right_valid, x.stream))
+        return out
+    if _is_torch(x) and x.is_cuda:
+        import torch
+        t, rows, cols, ld = _cuda_rows(x, allow_copy=not (halo_left_valid or halo_right_valid))
+        y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
+        if (y_rows, y_cols) != (rows, cols):
+            raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir1d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
+                                            rows, cols, ld, ld_y, _taps_ptr(hq), hq.size, dilation, frac_bits,
+                                            acc_bits, halo_left_valid, halo_right_valid, stream))
+        return y
+    if halo_left_valid or halo_right_valid:
+        raise ValueError("halo_*_valid apply to device-resident shards only")
+    was_torch = _is_torch(x)
+    a = _np_container(x.numpy() if was_torch else x)
+    rows, cols = _rows_cols(a.shape)
+    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    y_np = y.numpy() if _is_torch(y) else y
+    _lib.check(L.firgpu_fir1d_fixed_host(a.ctypes.data, y_np.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
+                                         cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, device))
+    if was_torch and out is None:
+        import torch
+        return torch.from_numpy(y)
+    return y
+
+
+def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, device: int = -1,
+                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True):
+    """Ideal floating-point FIR (fir_1d/model/python/fir_1d_ref.py:43-65) along
+    the last axis.  ``out_dtype=np.float64`` is bit-identical to the reference
+    (unfused multiply and add, taps in ascending order); ``np.float32`` runs a
+    float32 datapath (|err| <= 1e-6 * 255 * sum|h|)."""
+    quant.validate_taps(h)
+    L = _lib.lib()
+    hh = np.ascontiguousarray([float(v) for v in h], dtype=np.float64)
+    out_code = _OUT_IDEAL[np.dtype(out_dtype)]
+    if _is_torch(x) and x.is_cuda:
+        import torch
+        if validate:
+            _check_finite_torch(x)
+        t, rows, cols, ld = _cuda_rows(x, allow_copy=not (halo_left_valid or halo_right_valid))
+        y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
+                                            _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid, stream))
+        return y
+    if halo_left_valid or halo_right_valid:
+        raise ValueError("halo_*_valid apply to device-resident shards only")
+    was_torch = _is_torch(x)
+    a = _np_container(x.numpy() if was_torch else x)
+    if validate:
+        quant.check_samples_finite(a)
+    rows, cols = _rows_cols(a.shape)
+    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    _lib.check(L.firgpu_fir1d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols, cols,
+                                         cols, _taps_ptr(hh), hh.size, dilation, device))
+    if was_torch and out is None:
+        import torch
+        return torch.from_numpy(y)
+    return y
+
+
+def fir1d_fixed_iq(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, **kw):
+    """Interleaved complex baseband [I0,Q0,I1,Q1,...] with real taps: Re and
+    Im are filtered independently (the only product lib/mycomplex.cpp:12-22
+    defines is complex x real).  ``z`` may also have a trailing axis of 2."""
+    shape = tuple(z.shape)
+    if len(shape) >= 2 and shape[-1] == 2:
+        flat = z.reshape(shape[:-2] + (shape[-2] * 2,))
+        return fir1d_fixed(flat, h, frac_bits, acc_bits, coeff_bits, dilation=2, **kw).reshape(shape)
+    return fir1d_fixed(z, h, frac_bits, acc_bits, coeff_bits, dilation=2, **kw)
+
+
+# ---------------------------------------------------------------------------
+# 2-D
+# ---------------------------------------------------------------------------
+def fir2d_fixed(x, h2d, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *, out_dtype=np.uint8,
+                out=None, device: int = -1, halo_top_valid: int = 0, halo_bottom_valid: int = 0,
+                validate: bool = True):
+    """2-D fixed-point FIR over the last two axes (specification: DESIGN.md,
+    "fir_2d"; the reference ships no fir_2d).  One accumulator per pixel over
+    the whole window, then the 1-D model's wrap / round / shift / saturate."""
+    hh = quant.validate_taps_2d(h2d)
+    if _is_torch(x):
+        if validate:
+            _check_finite_torch(x)
+    else:
+        x = _np_container(x)
+        if validate:
+            quant.check_samples_finite(x)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = np.ascontiguousarray(quant.quantize_taps(hh, frac_bits, coeff_bits))
+    kh, kw = hq.shape
+    L = _lib.lib()
+    out_code = _OUT_FIXED[np.dtype(out_dtype)]
+    if _is_torch(x) and x.is_cuda:
+        import torch
+        t = _torch_container(x) if not (halo_top_valid or halo_bottom_valid) else x
+        n, hgt, wid = _imgs(t.shape)
+        ld = t.stride(-2) if t.dim() >= 2 else wid
+        img_stride = t.stride(-3) if t.dim() >= 3 else hgt * ld
+        y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir2d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, wid,
+                                            img_stride, hgt * wid, _taps_ptr(hq), kh, kw, frac_bits, acc_bits,
+                                            halo_top_valid, halo_bottom_valid, stream))
+        return y
+    if halo_top_valid or halo_bottom_valid:
+        raise ValueError("halo_*_valid apply to device-resident shards only")
+    was_torch = _is_torch(x)
+    a = _np_container(x.numpy() if was_torch else x)
+    n, hgt, wid = _imgs(a.shape)
+    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    _lib.check(L.firgpu_fir2d_fixed_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, n, hgt, wid,
+                                         _taps_ptr(hq), kh, kw, frac_bits, acc_bits, device))
+    if was_torch and out is None:
+        import torch
+        return torch.from_numpy(y)
+    return y
+
+
+def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, validate: bool = True):
+    """float64 (bit-identical to the scalar specification) or float32 2-D FIR
+    over the last two axes; taps visited row-major, unfused multiply + add."""
+    hh = np.ascontiguousarray(quant.validate_taps_2d(h2d))
+    kh, kw = hh.shape
+    L = _lib.lib()
+    out_code = _OUT_IDEAL[np.dtype(out_dtype)]
+    if _is_torch(x) and x.is_cuda:
+        import torch
+        if validate:
+            _check_finite_torch(x)
+        t = _torch_container(x)
+        n, hgt, wid = _imgs(t.shape)
+        y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, wid, wid,
+                                            hgt * wid, hgt * wid, _taps_ptr(hh), kh, kw, 0, 0, stream))
+        return y
+    was_torch = _is_torch(x)
+    a = _np_container(x.numpy() if was_torch else x)
+    if validate:
+        quant.check_samples_finite(a)
+    n, hgt, wid = _imgs(a.shape)
+    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    _lib.check(L.firgpu_fir2d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, n, hgt, wid,
+                                         _taps_ptr(hh), kh, kw, device))
+    if was_torch and out is None:
+        import torch
+        return torch.from_numpy(y)
+    return y
+
+
+# ---------------------------------------------------------------------------
+# pinned host buffers without torch
+# ---------------------------------------------------------------------------
+class PinnedArray:
+    """A NumPy array over page-locked memory from ``firgpu_pinned_alloc``; the
+    ``*_host`` entry points DMA such buffers directly (no staging copy)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._ptr = C.c_void_p()
+        _lib.check(_lib.lib().firgpu_pinned_alloc(C.byref(self._ptr), nbytes))
+        buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def close(self) -> None:
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            _lib.lib().firgpu_pinned_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
