@@ -1,0 +1,285 @@
+"""GPU parity, 1-D fixed-point path, through the C ABI (ctypes) and the
+reference-shaped Python entry points.  Bit-exact against the golden vectors
+made by the unmodified reference and against the pinned oracle."""
+from __future__ import annotations
+
+import hashlib
+import re
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, fir_oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+SIMPLE_LP5 = [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16]
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import firgpu
+    from firgpu import _lib
+    assert _lib.lib().firgpu_version() >= 100
+    return firgpu
+
+
+def golden_fn():
+    from fir_1d.model.python.fir_1d_fixed_ref import fir_1d_fixed_golden
+    return fir_1d_fixed_golden
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def signal(rng, n, dtype=np.int16, wild=0.01):
+    """99 % pixels in [0,255], 1 % anywhere in the container's range
+    (exercises the input clamp) — SURVEY §8(d) input recipe."""
+    x = rng.integers(0, 256, size=n).astype(dtype)
+    if dtype != np.uint8 and wild > 0:
+        info = np.iinfo(dtype)
+        mask = rng.random(n) < wild
+        x[mask] = rng.integers(info.min, info.max, size=int(mask.sum()), endpoint=True).astype(dtype)
+    return x
+
+
+# ---- the reference's own unit tests, restated (fir_1d/sim/tests/test_1d_fixed.py) ----
+def test_reference_kats(fg):
+    f = golden_fn()
+    y = f([10, 20, 30, 40], [0.25, 0.5, 0.25])                                   # :9-16
+    assert isinstance(y, np.ndarray) and y.dtype == np.uint8 and y.tolist() == [10, 20, 30, 28]
+    assert f([-1.2, 0.5, 1.5, 254.6, 300.2], [1.0]).tolist() == [0, 1, 2, 255, 255]   # :19-24
+    assert f([255, 255], [7.999755859375]).tolist() == [255, 255]                # :27-33
+    assert f([255, 255], [-8.0]).tolist() == [0, 0]                              # :35-40
+    y = f([255, 255, 255, 255], [0.5, 0.25])                                     # :95-104
+    assert y.shape == (4,) and y.dtype == np.uint8 and y.min() >= 0 and y.max() <= 255
+
+
+@pytest.mark.parametrize("kwargs, pattern", [
+    (dict(x=[1.0, float("nan")], h=[1.0]), r"x\[1\].*finite"),
+    (dict(x=[1.0], h=[float("inf")]), r"h\[0\].*finite"),
+    (dict(x=[1.0], h=[]), r"must not be empty"),
+    (dict(x=[1.0], h=[1.0], coeff_bits=12), r"Invalid coeff_bits=12"),
+    (dict(x=[1.0], h=[1.0], frac_bits=0), r"frac_bits must be > 0"),
+    (dict(x=[1.0], h=[1.0], acc_bits=0), r"acc_bits must be > 0"),
+    (dict(x=[1.0], h=[8.0]), r"out of Q-format real range"),
+    (dict(x=[1.0], h=[1.0], frac_bits=7, coeff_bits=8), r"out of Q-format real range"),
+    (dict(x=[1.0], h=[8.0 + 1e-6]), r"\|h\| must be <="),
+])
+def test_reference_error_contract(fg, kwargs, pattern):
+    with pytest.raises(ValueError) as err:
+        golden_fn()(**kwargs)
+    assert re.search(pattern, str(err.value))
+
+
+def test_every_golden_case_bit_exact(fg, golden_cases):
+    f = golden_fn()
+    for c in golden_cases:
+        y = f(c["x"].tolist(), c["h"], frac_bits=c["frac_bits"], acc_bits=c["acc_bits"], coeff_bits=c["coeff_bits"])
+        assert y.dtype == np.uint8 and np.array_equal(y, c["y_fixed"]), c["name"]
+        y2 = f(c["x"], c["h"], frac_bits=c["frac_bits"], acc_bits=c["acc_bits"], coeff_bits=c["coeff_bits"])
+        assert np.array_equal(y2, c["y_fixed"]), c["name"] + " (ndarray input)"
+
+
+def test_reference_images_by_hash(fg, images_inputs, manifest):
+    """Config 1: the reference's own images, all 8 coefficient sets, compared
+    with the SHA-256 of the reference pipeline's output files."""
+    from fir_1d.sim.vector.gen_fixed_output import _run_fixed_rowwise
+    from firgpu import _lib
+    n = 0
+    for stem in images_inputs.keys():
+        x = images_inputs[stem]
+        for tap in ("3tap", "5tap"):
+            for name, h in manifest[f"coeff_{tap}"].items():
+                y = _run_fixed_rowwise(x, h, frac_bits=12, acc_bits=32, coeff_bits=16)
+                assert y.shape == x.shape and y.dtype == np.uint8
+                assert sha(y) == manifest["fixed"][f"{stem}__{name}_{tap}"], (stem, name, tap)
+                assert _lib.last_path() == _lib.PATH_STAGED
+                n += 1
+    assert n == 48
+
+
+def test_odd_width_image_rows(fg, image_crops, manifest):
+    stem = "case_005_img_006_4499x2999_gray"
+    x = image_crops[f"{stem}/x"]
+    for tap in ("3tap", "5tap"):
+        for name, h in manifest[f"coeff_{tap}"].items():
+            assert np.array_equal(fg.fir1d_fixed(x, h), image_crops[f"{stem}/{tap}/{name}/fixed"])
+
+
+# ---- the staged kernel against the oracle -------------------------------------------
+@pytest.mark.parametrize("in_dtype", [np.uint8, np.int16])
+@pytest.mark.parametrize("out_dtype", [np.uint8, np.int16])
+@pytest.mark.parametrize("n_taps", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_staged_all_tap_counts(fg, torch, in_dtype, out_dtype, n_taps):
+    from firgpu import _lib
+    rng = np.random.default_rng(1000 + n_taps)
+    for frac, dil in ((12, 1), (15, 1), (15, 2), (12, 2)):
+        h = rng.uniform(-0.45, 0.45, size=n_taps).tolist()
+        for n in (1, 2, 7, 64, 1000, 16384, 16385, 40000 + 2 * n_taps):
+            if dil == 2 and n % 2:
+                n += 1
+            x = signal(rng, n, in_dtype)
+            xt = torch.from_numpy(x).cuda()
+            y = fg.fir1d_fixed(xt, h, frac, 32, 16, dilation=dil, out_dtype=out_dtype)
+            assert _lib.last_path() == _lib.PATH_STAGED
+            want = c_oracle.fir1d_fixed(x, onp.quantize_taps(h, frac, 16), frac, 32, dilation=dil, out_dtype=out_dtype)
+            got = y.cpu().numpy()
+            assert got.dtype == np.dtype(out_dtype)
+            assert np.array_equal(got, want), (n_taps, frac, dil, n)
+
+
+def test_generic_kernel_serves_what_staged_declines(fg, torch):
+    """acc_bits wrap live, 32-bit taps, long filters, other containers."""
+    from firgpu import _lib
+    rng = np.random.default_rng(9)
+    x = signal(rng, 5000, np.int16)
+    xt = torch.from_numpy(x).cuda()
+    cases = [
+        (12, 16, 16, [0.9, -0.7, 0.8, 0.3, -0.2]),        # acc_bits wrap is live
+        (28, 32, 32, [7.5, -7.5, 0.001]),                 # 32-bit taps, wrap live
+        (12, 32, 16, rng.uniform(-0.2, 0.2, size=33).tolist()),   # long filter
+        (12, 20, 16, [1.0]),                              # SURVEY 8(c)5 wrap case
+        (3, 12, 8, [7.0, -6.5, 3.25, 1.0]),               # tiny frac_bits, 8-bit taps, wrap live
+        (30, 64, 32, [0.4, 0.3]),                         # frac_bits beyond the packed path
+    ]
+    for frac, acc, cb, h in cases:
+        y = fg.fir1d_fixed(xt, h, frac, acc, cb).cpu().numpy()
+        assert _lib.last_path() == _lib.PATH_GENERIC, (frac, acc, cb)
+        assert np.array_equal(y, onp.fir1d_fixed(x, h, frac, acc, cb)), (frac, acc, cb)
+    for dt in (np.int32, np.float32, np.float64):
+        xs = (rng.uniform(-20, 300, size=3001)).astype(dt)
+        y = fg.fir1d_fixed(torch.from_numpy(xs).cuda(), SIMPLE_LP5).cpu().numpy()
+        assert _lib.last_path() == _lib.PATH_GENERIC
+        assert np.array_equal(y, onp.fir1d_fixed(xs, SIMPLE_LP5))
+
+
+def test_batched_rows_pitched_and_unaligned(fg, torch):
+    """Rows x cols with pitch > cols, odd pitches (no 16-byte alignment), and
+    base pointers offset by one element: the patch path of the staged kernel."""
+    from firgpu import _lib
+    rng = np.random.default_rng(21)
+    for dtype in (np.uint8, np.int16):
+        for rows, cols, pitch in ((5, 4499, 4499), (3, 641, 650), (7, 33000, 33008), (2, 16384, 16400), (64, 64, 64)):
+            base = signal(rng, rows * pitch + 3, dtype)
+            for off in (0, 1, 3):
+                buf = torch.from_numpy(base).cuda()
+                view = buf[off:off + rows * pitch].view(rows, pitch)[:, :cols]
+                y = fg.fir1d_fixed(view, SIMPLE_LP5, 15, 32, 16)
+                assert _lib.last_path() == _lib.PATH_STAGED
+                xs = base[off:off + rows * pitch].reshape(rows, pitch)[:, :cols]
+                assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(xs, SIMPLE_LP5, 15, 32, 16)), (dtype, rows, cols, pitch, off)
+
+
+def test_segment_halos_make_seamless_shards(fg, torch):
+    """A long signal cut into segments with duplicated halos gives exactly the
+    unsharded result (config 2 / 5 sharding), for both dilations."""
+    from firgpu import shard
+    rng = np.random.default_rng(33)
+    for dil, n in ((1, 200_000), (2, 131_072 + 4096), (1, 70_001)):
+        x = signal(rng, n, np.int16)
+        want = c_oracle.fir1d_fixed(x, onp.quantize_taps(SIMPLE_LP5, 15, 16), 15, 32, dilation=dil, out_dtype=np.int16, threads=4)
+        for parts in (2, 3, 8):
+            pieces = shard.plan_segments(n, parts, 5, dil, align=4096)
+            got = np.empty(n, dtype=np.int16)
+            for p in pieces:
+                if p.size == 0:
+                    continue
+                buf, body = shard.scatter_segment(x, p, "cuda")
+                y = fg.fir1d_fixed(body, SIMPLE_LP5, 15, 32, 16, dilation=dil, out_dtype=np.int16,
+                                   halo_left_valid=p.before, halo_right_valid=p.after)
+                got[p.start:p.stop] = y.cpu().numpy()
+            assert np.array_equal(got, want), (dil, n, parts)
+
+
+def test_host_entry_point_pipeline(fg):
+    """firgpu_fir1d_fixed_host: pageable and pinned buffers, many rows, and a
+    row long enough to be cut into column segments with halos."""
+    rng = np.random.default_rng(44)
+    for shape in ((1, 40_000_000), (300, 70_001), (4096, 4096)):
+        x = signal(rng, shape[0] * shape[1], np.int16).reshape(shape)
+        want = c_oracle.fir1d_fixed(x, onp.quantize_taps(SIMPLE_LP5, 15, 16), 15, 32, out_dtype=np.int16, threads=8)
+        y = fg.fir1d_fixed(x, SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16)
+        assert np.array_equal(y, want), shape
+        pin_x, pin_y = fg.PinnedArray(shape, np.int16), fg.PinnedArray(shape, np.int16)
+        pin_x.array[...] = x
+        fg.fir1d_fixed(pin_x.array, SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16, out=pin_y.array)
+        assert np.array_equal(pin_y.array, want), shape
+        pin_x.close()
+        pin_y.close()
+
+
+def test_iq_is_two_independent_filters(fg, torch):
+    """Config 5 semantics (lib/mycomplex.cpp:12-22): interleaved I/Q with real
+    taps == the 1-D model on z[0::2] and z[1::2]."""
+    rng = np.random.default_rng(55)
+    z = signal(rng, 2 * 300_001, np.int16)
+    zt = torch.from_numpy(z).cuda()
+    y = fg.fir1d_fixed_iq(zt, SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16).cpu().numpy()
+    assert np.array_equal(y[0::2], onp.fir1d_fixed(z[0::2], SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16))
+    assert np.array_equal(y[1::2], onp.fir1d_fixed(z[1::2], SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16))
+    y2 = fg.fir1d_fixed_iq(zt.view(-1, 2), SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16)
+    assert y2.shape == (300_001, 2) and np.array_equal(y2.cpu().numpy().reshape(-1), y)
+
+
+def test_full_size_stream_properties(fg, torch):
+    """Config 2 at full size (2**28 int16 samples): windows against the
+    oracle (start, a tile seam, middle, end) + size-independent properties."""
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randint(0, 256, (n,), generator=g, device="cuda", dtype=torch.int16)
+    wild = torch.rand(n, generator=g, device="cuda") < 0.01
+    x[wild] = torch.randint(-32768, 32768, (int(wild.sum()),), generator=g, device="cuda", dtype=torch.int32).to(torch.int16)
+    del wild
+    y = fg.fir1d_fixed(x, SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16)
+    hq = onp.quantize_taps(SIMPLE_LP5, 15, 16)
+    for start in (0, 8192 - 64, (n // 2) - 5000, n - (1 << 20)):
+        stop = min(n, start + (1 << 20))
+        lo, hi = max(0, start - 2), min(n, stop + 2)
+        xs = x[lo:hi].cpu().numpy()
+        want = c_oracle.fir1d_fixed(xs, hq, 15, 32, out_dtype=np.int16, threads=8)
+        # interior of the window is independent of the window's own zero padding
+        a, b = (0 if lo == 0 else 2), (xs.size if hi == n else xs.size - 2)
+        assert np.array_equal(y[lo + a:lo + b].cpu().numpy(), want[a:b]), start
+    # range and DC-gain properties of a unity-gain low-pass over clamped pixels
+    assert int(y.min()) >= 0 and int(y.max()) <= 255
+    xc = x.clamp(0, 255)
+    # round-half-up on sixteenths biases the mean by +1/32
+    assert abs(float(y[2:-2].double().mean()) - float(xc.double().mean())) < 0.05
+    # shift invariance: filtering a shifted copy shifts the output (away from the ends)
+    y_shift = fg.fir1d_fixed(x[4096:], SIMPLE_LP5, 15, 32, 16, out_dtype=np.int16)
+    assert torch.equal(y_shift[2:1 << 22], y[4096 + 2:4096 + (1 << 22)])
+    # u8 container of the same pixels gives the same values
+    y8 = fg.fir1d_fixed(xc.to(torch.uint8), SIMPLE_LP5, 15, 32, 16)
+    assert torch.equal(y8.to(torch.int16), y)
+
+
+def test_imad_datapath_matches_dp2a(fg, torch):
+    """The alternative IMAD datapath (FIRGPU_MAC=1, kept for A/B evidence) is
+    bit-identical."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        import firgpu
+        from oracle import fir_oracle_np as onp
+        rng = np.random.default_rng(3)
+        x = rng.integers(-400, 700, size=100003).astype(np.int16)
+        h = [1/16, 4/16, 6/16, 4/16, 1/16]
+        for frac in (12, 15):
+            y = firgpu.fir1d_fixed(torch.from_numpy(x).cuda(), h, frac, 32, 16).cpu().numpy()
+            assert np.array_equal(y, onp.fir1d_fixed(x, h, frac, 32, 16))
+        print("ok")
+    """) % (str(__import__("pathlib").Path(__file__).resolve().parents[1]),
+            str(__import__("pathlib").Path(__file__).resolve().parents[1] / "warmup-fir-filter_b200"))
+    env = dict(os.environ, FIRGPU_MAC="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -1,0 +1,81 @@
+"""world_size-2 (and 3) runs of the multi-GPU host logic on CPU with gloo:
+partition, shard-time halo exchange, per-rank filtering and gathering.  The
+per-rank compute is the oracle standing in for the CUDA kernel — what is under
+test is the sharding code path of firgpu.shard, which is identical on GPUs."""
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, dilation: int, n: int, out_dir: str) -> None:
+    for p in (str(ROOT), str(ROOT / "warmup-fir-filter_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from firgpu import shard
+    from oracle import fir_oracle_np as onp
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h = [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16]
+        pieces = shard.plan_segments(n, world, len(h), dilation, align=64)
+        me = pieces[rank]
+        # every rank owns only its body (same global stream: seeded by global index)
+        full = np.random.default_rng(99).integers(-200, 500, size=n).astype(np.int16)
+        lead = shard.aligned_lead(me.before, 2)
+        buf = torch.zeros(lead + me.size + me.after, dtype=torch.int16)
+        buf[lead:lead + me.size] = torch.from_numpy(full[me.start:me.stop])
+        shard.exchange_halos(buf, lead, pieces, rank, dist)
+        window = buf[lead - me.before:lead + me.size + me.after].numpy()
+        assert np.array_equal(window, full[me.lo:me.hi]), "halo exchange delivered the wrong samples"
+        local = onp.fir1d_fixed(window, h, 15, 32, 16, dilation=dilation)[me.before:me.before + me.size]
+        # gather on rank 0 (optional, outside the hot path) and compare with the unsharded result
+        sizes = [p.size for p in pieces]
+        padded = torch.zeros(max(sizes), dtype=torch.uint8)
+        padded[:me.size] = torch.from_numpy(local)
+        got = [torch.zeros(max(sizes), dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, got, dst=0)
+        if rank == 0:
+            whole = np.concatenate([g[:s].numpy() for g, s in zip(got, sizes)])
+            want = onp.fir1d_fixed(full, h, 15, 32, 16, dilation=dilation)
+            assert np.array_equal(whole, want), "sharded result differs from the whole-signal result"
+        # the timing reduction the bench uses: max over ranks
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == float(world)
+        Path(out_dir, f"ok_{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world, dilation, n", [(2, 1, 10_000), (2, 2, 8_192), (3, 1, 5_001)])
+def test_segment_sharding_over_gloo(tmp_path, world, dilation, n):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, dilation, n, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(p.name for p in tmp_path.glob("ok_*")) == [f"ok_{r}" for r in range(world)]
+
+
+def test_row_and_band_plans_partition_exactly():
+    from firgpu import shard
+    for rows, parts in ((8192, 8), (7, 2), (3, 4)):
+        pieces = shard.plan_rows(rows, parts)
+        assert sum(p.size for p in pieces) == rows and all(p.before == p.after == 0 for p in pieces)
+    bands = shard.plan_bands(1000, 3, 3)
+    assert [(b.start, b.stop, b.before, b.after) for b in bands] == [(0, 334, 0, 1), (334, 667, 1, 1), (667, 1000, 1, 0)]

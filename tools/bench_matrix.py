@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Kernel-level sweep over the shapes BASELINE.json names (not the contract
+bench: see bench.py).  Device-resident inputs, CUDA events, one line per case:
+
+    python tools/bench_matrix.py [--cases stream,u8,iq,batched,taps,images,ideal,2d] [--reps 20]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+for p in (str(ROOT), str(ROOT / "warmup-fir-filter_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+import firgpu  # noqa: E402
+from firgpu import _lib  # noqa: E402
+
+LP5 = [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16]
+LP3 = [0.25, 0.5, 0.25]
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def report(name, seconds, samples, bytes_per_sample):
+    gbs = samples * bytes_per_sample / seconds / 1e9
+    path = {1: "generic", 2: "staged", 3: "empty"}.get(_lib.last_path(), "?")
+    print(json.dumps({"case": name, "ms": round(seconds * 1e3, 4), "gsamples_s": round(samples / seconds / 1e9, 1),
+                      "gb_s": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 3), "path": path}), flush=True)
+
+
+def rand_i16(n, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randint(-64, 320, (n,), generator=g, device="cuda", dtype=torch.int16)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="stream,u8,iq,taps,batched,images,ideal,2d")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    cases = args.cases.split(",")
+    n = 1 << 28
+    if "stream" in cases:
+        x = rand_i16(n)
+        y = torch.empty_like(x)
+        for frac, tag in ((15, "q1.15 (hi16 post)"), (12, "q4.12 (shift post)")):
+            s = timed(lambda: firgpu.fir1d_fixed(x, LP5, frac, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^28 i16->i16 5tap {tag}", s, n, 4)
+        y8 = torch.empty(n, dtype=torch.uint8, device="cuda")
+        s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out=y8, validate=False), args.reps)
+        report("stream 2^28 i16->u8 5tap q1.15", s, n, 3)
+        del x, y, y8
+    if "u8" in cases:
+        x = rand_i16(n).clamp(0, 255).to(torch.uint8)
+        y = torch.empty_like(x)
+        for h, tag in ((LP5, "5tap"), (LP3, "3tap")):
+            s = timed(lambda: firgpu.fir1d_fixed(x, h, 12, 32, 16, out=y, validate=False), args.reps)
+            report(f"stream 2^28 u8->u8 {tag} q4.12", s, n, 2)
+        s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out=y, validate=False), args.reps)
+        report("stream 2^28 u8->u8 5tap q1.15", s, n, 2)
+        del x, y
+    if "iq" in cases:
+        z = rand_i16(n)                      # 2^27 complex samples interleaved
+        y = torch.empty_like(z)
+        s = timed(lambda: firgpu.fir1d_fixed(z, LP5, 15, 32, 16, dilation=2, out_dtype=np.int16, out=y, validate=False), args.reps)
+        report("iq 2^27 complex i16 5tap q1.15", s, n, 4)
+        del z, y
+    if "taps" in cases:
+        x = rand_i16(n)
+        y = torch.empty_like(x)
+        for L in (1, 2, 3, 4, 5, 7, 9):
+            h = (np.ones(L) / (2 * L)).tolist()
+            s = timed(lambda: firgpu.fir1d_fixed(x, h, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^28 i16->i16 {L}tap q1.15", s, n, 4)
+        h33 = (np.ones(33) / 66).tolist()
+        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], h33, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 26], validate=False), 5)
+        report("stream 2^26 i16->i16 33tap (generic kernel)", s, 1 << 26, 4)
+        del x, y
+    if "batched" in cases:
+        for rows, cols in ((8192, 1 << 20), (8192, 1_000_000), (1 << 16, 4096), (1 << 20, 256)):
+            x = rand_i16(rows * cols).view(rows, cols)
+            y = torch.empty_like(x)
+            s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), max(3, args.reps // 4))
+            report(f"batched {rows}x{cols} i16->i16 5tap q1.15", s, rows * cols, 4)
+            del x, y
+    if "images" in cases:
+        for hgt, wid in ((853, 1280), (2999, 4499), (64, 64)):
+            x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
+            y = torch.empty_like(x)
+            s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 12, 32, 16, out=y, validate=False), args.reps)
+            report(f"image rows {hgt}x{wid} u8->u8 5tap q4.12", s, hgt * wid, 2)
+    if "ideal" in cases:
+        x = rand_i16(1 << 26).clamp(0, 255).to(torch.uint8)
+        y = torch.empty(1 << 26, dtype=torch.float64, device="cuda")
+        s = timed(lambda: firgpu.fir1d_ideal(x, LP5, out=y, validate=False), 5)
+        report("ideal 2^26 u8->f64 5tap", s, 1 << 26, 9)
+        y32 = torch.empty(1 << 26, dtype=torch.float32, device="cuda")
+        s = timed(lambda: firgpu.fir1d_ideal(x, LP5, out_dtype=np.float32, out=y32, validate=False), 5)
+        report("ideal 2^26 u8->f32 5tap", s, 1 << 26, 5)
+        del x, y, y32
+    if "2d" in cases:
+        img = rand_i16(16384 * 16384).view(1, 16384, 16384)
+        out = torch.empty_like(img)
+        k3 = [[1 / 9] * 3] * 3
+        k5 = np.outer(LP5, LP5).tolist()
+        for k, tag in ((k3, "3x3 box"), (k5, "5x5 lp")):
+            s = timed(lambda: firgpu.fir2d_fixed(img, k, 12, 32, 16, out_dtype=np.int16, out=out, validate=False), 3, warm=1)
+            report(f"2d 16384^2 i16->i16 {tag} q4.12", s, 16384 * 16384, 4)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,3 +116,26 @@ def scatter_band(full, piece: Piece, device):
     src = torch.as_tensor(full)
     buf = src[..., piece.lo:piece.hi, :].to(device).contiguous()
     return buf, buf[..., piece.before:piece.before + piece.size, :]
+
+
+def exchange_halos(buf, lead: int, pieces: list[Piece], rank: int, dist) -> None:
+    """Shard-time halo fill for data that is already distributed: ``buf`` is
+    this rank's ``[lead pad | halo before | body | halo after]`` buffer with
+    the body in place; the halo slots receive the neighbours' edge samples by
+    point-to-point send/recv (NCCL on GPUs, gloo in the CPU tests).  This is
+    the only inter-rank traffic the path ever needs, and it happens once,
+    outside the filtering loop."""
+    me = pieces[rank]
+    body = buf[lead:lead + me.size]
+    ops = []
+    if me.after:
+        ops.append(dist.P2POp(dist.irecv, buf[lead + me.size:lead + me.size + me.after], rank + 1))
+    if me.before:
+        ops.append(dist.P2POp(dist.irecv, buf[lead - me.before:lead], rank - 1))
+    if rank + 1 < len(pieces) and pieces[rank + 1].before:
+        ops.append(dist.P2POp(dist.isend, body[me.size - pieces[rank + 1].before:].clone(), rank + 1))
+    if rank > 0 and pieces[rank - 1].after:
+        ops.append(dist.P2POp(dist.isend, body[:pieces[rank - 1].after].clone(), rank - 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
