@@ -285,26 +285,28 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     value = world * piece.size * args.steps / (ms_total * 1e-3) / 1e9
 
     # ---- end to end through the public API with host buffers -----------------
-    e2e_steps = max(3, min(args.steps, 8))
+    e2e_value, e2e_ok, e2e_steps = None, None, 0
     n_host = piece.before + piece.size + piece.after
-    x_host = torch.empty(n_host, dtype=torch.int16).pin_memory()
-    y_host = torch.empty(n_host, dtype=torch.int16).pin_memory()
-    x_host.copy_(buf[lead - piece.before:lead + piece.size + piece.after])
-    x_np, y_np = x_host.numpy(), y_host.numpy()
-    for _ in range(2):
-        firgpu.fir1d_fixed(x_np, TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16, out=y_np, device=local_rank)
-    barrier()
-    clocks.region(True)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        firgpu.fir1d_fixed(x_np, TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16, out=y_np, device=local_rank)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-    clocks.region(False)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * piece.size * e2e_steps / float(e2e_s.item()) / 1e9
-    e2e_ok = bool(torch.equal(y_host[piece.before:piece.before + piece.size], y.cpu())) if rank == 0 else None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 8))
+        x_host = torch.empty(n_host, dtype=torch.int16).pin_memory()
+        y_host = torch.empty(n_host, dtype=torch.int16).pin_memory()
+        x_host.copy_(buf[lead - piece.before:lead + piece.size + piece.after])
+        x_np, y_np = x_host.numpy(), y_host.numpy()
+        for _ in range(2):
+            firgpu.fir1d_fixed(x_np, TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16, out=y_np, device=local_rank)
+        barrier()
+        clocks.region(True)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            firgpu.fir1d_fixed(x_np, TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16, out=y_np, device=local_rank)
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        clocks.region(False)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = world * piece.size * e2e_steps / float(e2e_s.item()) / 1e9
+        e2e_ok = bool(torch.equal(y_host[piece.before:piece.before + piece.size], y.cpu())) if rank == 0 else None
 
     clock_summary = clocks.summary()
     if rank == 0:
@@ -350,6 +352,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

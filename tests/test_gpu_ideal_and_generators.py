@@ -1,0 +1,164 @@
+"""GPU parity: the ideal (floating-point) model, and the reference-shaped
+row-wise generators / pipeline driver with their file contract
+(fir_1d/sim/tests/test_1d_ideal.py, test_fixed_output.py, test_ideal_ output.py
+restated against the GPU-backed drop-in)."""
+from __future__ import annotations
+
+import hashlib
+import re
+
+import numpy as np
+import pytest
+
+from oracle import fir_oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ideal_fn():
+    from fir_1d.model.python.fir_1d_ref import fir_1d_ideal
+    return fir_1d_ideal
+
+
+# ---- fir_1d/sim/tests/test_1d_ideal.py ---------------------------------------------
+def test_reference_ideal_kats():
+    f = ideal_fn()
+    y = f([10, 20, 30, 40], [0.25, 0.5, 0.25])                                     # :8-16
+    assert isinstance(y, list) and y == pytest.approx([10.0, 20.0, 30.0, 27.5], abs=1e-12)
+    assert len(f([1, 2, 3, 4, 5], [0.1, 0.2, 0.3, 0.4])) == 5                       # :19-24
+    assert f([-1.2, 0.49, 0.5, 1.5, 254.6, 300.2], [1.0]) == [0.0, 0.0, 1.0, 2.0, 255.0, 255.0]   # :27-34
+    assert f([255, 255], [5.0]) == [1275.0, 1275.0]                                 # :37-42 not clamped
+    assert f([1.0], [8.0]) == [8.0] and f([1.0], [-8.0]) == [-8.0]                  # :67-69
+
+
+@pytest.mark.parametrize("kwargs, pattern", [
+    (dict(x=[1.0, float("inf")], h=[1.0]), r"x\[1\].*finite"),
+    (dict(x=[1.0], h=[float("nan")]), r"h\[0\].*finite"),
+    (dict(x=[1.0], h=[]), r"must not be empty"),
+    (dict(x=[1.0], h=[8.0 + 1e-6]), r"\|h\| must be <="),
+])
+def test_reference_ideal_errors(kwargs, pattern):
+    with pytest.raises(ValueError) as err:
+        ideal_fn()(**kwargs)
+    assert re.search(pattern, str(err.value))
+
+
+def test_ideal_f64_is_bit_identical_on_every_golden_case(golden_cases):
+    f = ideal_fn()
+    for c in golden_cases:
+        y = np.array(f(c["x"].tolist(), c["h"]), dtype=np.float64)
+        assert np.array_equal(y, c["y_ideal"]), c["name"]
+
+
+def test_ideal_images_by_hash(images_inputs, manifest):
+    from fir_1d.sim.vector.gen_ideal_output import _run_ideal_rowwise
+    for stem in ("case_003_img_004_64x64_gray", "case_004_img_005_64x64_noise_gray", "case_001_img_002_640x762_gray"):
+        x = images_inputs[stem]
+        for tap in ("3tap", "5tap"):
+            for name, h in manifest[f"coeff_{tap}"].items():
+                y = _run_ideal_rowwise(x, h)
+                assert y.dtype == np.float64 and y.shape == x.shape
+                assert sha(y) == manifest["ideal"][f"{stem}__{name}_{tap}"], (stem, name, tap)
+
+
+def test_ideal_f32_within_stated_tolerance():
+    """float32 datapath: |err| <= 1e-6 * 255 * sum|h| (relative 1e-6 of the
+    output's full scale), the tolerance BASELINE.json's north star names."""
+    import torch
+    import firgpu
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 256, size=(7, 50_001)).astype(np.uint8)
+    for h in ([1 / 3] * 3, [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16], [-1 / 16, -4 / 16, 26 / 16, -4 / 16, -1 / 16], [7.3, -2.1]):
+        want = onp.fir1d_ideal(x, h)
+        got = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h, out_dtype=np.float32).cpu().numpy()
+        assert got.dtype == np.float32
+        tol = 1e-6 * 255 * float(np.sum(np.abs(h)))
+        assert np.max(np.abs(got.astype(np.float64) - want)) <= tol
+        got64 = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h).cpu().numpy()
+        assert np.array_equal(got64, want)
+        host = firgpu.fir1d_ideal(x, h)
+        assert np.array_equal(host, want)
+
+
+def test_fixed_tracks_ideal_within_one_lsb_when_unsaturated():
+    """Cross-check of the two models on the GPU (what the reference's compare
+    reports measure): a unity-gain low-pass never saturates, so the fixed
+    output is the rounded ideal output up to coefficient quantisation."""
+    import torch
+    import firgpu
+    rng = np.random.default_rng(6)
+    x = torch.from_numpy(rng.integers(0, 256, size=1 << 20).astype(np.uint8)).cuda()
+    h = [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16]
+    fixed = firgpu.fir1d_fixed(x, h).double()
+    ideal = firgpu.fir1d_ideal(x, h)
+    assert float((fixed - ideal).abs().max()) <= 0.5 + 1e-9
+
+
+# ---- generators (fir_1d/sim/tests/test_fixed_output.py, "test_ideal_ output.py") ----
+SMALL = np.array([[10, 20, 30, 40, 50, 60, 70, 80],
+                  [80, 70, 60, 50, 40, 30, 20, 10],
+                  [0, 10, 0, 10, 0, 10, 0, 10],
+                  [255, 200, 150, 100, 50, 0, 25, 75]], dtype=np.uint8)      # output_test_common.py:12-25
+
+
+def test_generators_file_contract_and_values(tmp_path):
+    from fir_1d.model.python.fir_1d_fixed_ref import fir_1d_fixed_golden
+    from fir_1d.model.python.fir_1d_ref import fir_1d_ideal
+    from fir_1d.sim.vector import gen_fixed_output as gf, gen_ideal_output as gi
+    from fir_1d.sim.vector.h_coeff import h_coeff_3tap_map, h_coeff_5tap_map
+    inp, out = tmp_path / "input", tmp_path / "output"
+    inp.mkdir()
+    np.save(inp / "case_000_small_x_u8.npy", SMALL)
+    assert gf.generate_fixed_3tap_output_vector(input_dir=inp, output_dir=out) == len(h_coeff_3tap_map)
+    assert gf.generate_fixed_5tap_output_vector(input_dir=inp, output_dir=out) == len(h_coeff_5tap_map)
+    assert gi.generate_ideal_3tap_output_vector(input_dir=inp, output_dir=out) == 4
+    assert gi.generate_ideal_5tap_output_vector(input_dir=inp, output_dir=out) == 4
+    for sub, suffix, dtype in (("fixed_3tap", "_fixed_3tap_y_u8.npy", np.uint8), ("fixed_5tap", "_fixed_5tap_y_u8.npy", np.uint8),
+                               ("ideal_3tap", "_ideal_3tap_y_f64.npy", np.float64), ("ideal_5tap", "_ideal_5tap_y_f64.npy", np.float64)):
+        files = sorted((out / sub).glob("*.npy"))
+        assert len(files) == 4 and all("__" in f.name and f.name.endswith(suffix) for f in files)
+        for f in files:
+            y = np.load(f)
+            assert y.shape == SMALL.shape and y.dtype == dtype
+    # rows are independent calls of the 1-D model (test_fixed_output.py:81-96)
+    y = np.load(out / "fixed_3tap" / "case_000_small__simple_lp_fixed_3tap_y_u8.npy")
+    for r in (0, 2):
+        assert np.array_equal(y[r], fir_1d_fixed_golden(SMALL[r].tolist(), h_coeff_3tap_map["simple_lp"]))
+        assert np.array_equal(y[r], onp.fir1d_fixed(SMALL[r], h_coeff_3tap_map["simple_lp"]))
+    yi = np.load(out / "ideal_5tap" / "case_000_small__sharpen_ideal_5tap_y_f64.npy")
+    for r in (1, 3):
+        assert np.allclose(yi[r], fir_1d_ideal(SMALL[r].tolist(), h_coeff_5tap_map["sharpen"]))
+    # idempotent skip unless overwrite (gen_fixed_output.py:95-96)
+    assert gf.generate_fixed_3tap_output_vector(input_dir=inp, output_dir=out) == 0
+    assert gf.generate_fixed_3tap_output_vector(input_dir=inp, output_dir=out, overwrite=True) == 4
+    # keyword plumbing of the bit widths
+    out2 = tmp_path / "q115"
+    assert gf.generate_fixed_5tap_output_vector(input_dir=inp, output_dir=out2, frac_bits=12, acc_bits=16, coeff_bits=16) == 4
+    y16 = np.load(out2 / "fixed_5tap" / "case_000_small__sharpen_fixed_5tap_y_u8.npy")
+    assert np.array_equal(y16, onp.fir1d_fixed(SMALL, h_coeff_5tap_map["sharpen"], 12, 16, 16))
+
+
+def test_pipeline_driver_model_stages(tmp_path, monkeypatch):
+    import pipeline_fir_1d as pipe
+    from fir_1d.sim.vector import gen_fixed_output as gf, gen_ideal_output as gi
+    inp, out = tmp_path / "input", tmp_path / "output"
+    inp.mkdir()
+    np.save(inp / "case_000_small_x_u8.npy", SMALL)
+    for mod in (gf, gi):
+        for name in dir(mod):
+            fn = getattr(mod, name)
+            if name.startswith("generate_") and callable(fn):
+                monkeypatch.setattr(mod, name, (lambda f: lambda **kw: f(input_dir=inp, output_dir=out, **kw))(fn))
+    res = pipe.run_pipeline(tap="all", overwrite_vectors=True, skip_input=True, skip_ideal=False, skip_fixed=False,
+                            skip_report=True, skip_restore=True, restore_kind="all", ideal_policy="clip",
+                            overwrite_images=False, strict_report=False, strict_restore=False, top_k=5)
+    assert res == {"selected_taps": ["3", "5"], "ideal_counts": {"ideal_3tap": 4, "ideal_5tap": 4},
+                   "fixed_counts": {"fixed_3tap": 4, "fixed_5tap": 4}}
+    with pytest.raises(ImportError, match="FIR_REFERENCE_ROOT"):
+        pipe.run_pipeline(tap="3", overwrite_vectors=False, skip_input=False, skip_ideal=True, skip_fixed=True,
+                          skip_report=True, skip_restore=True, restore_kind="all", ideal_policy="clip",
+                          overwrite_images=False, strict_report=False, strict_restore=False, top_k=5)

@@ -1,456 +1,14 @@
-// Staged 1-D fixed-point FIR for sm_100a: the fast path behind
-// firgpu_fir1d_fixed (reference arithmetic:
-// fir_1d/model/python/fir_1d_fixed_ref.py:95-128, batched as
-// fir_1d/sim/vector/gen_fixed_output.py:44-59).
-//
-// Design (see DESIGN.md "fir1d_staged"):
-//   * persistent CTAs, each walking a strided list of 16 KiB input tiles;
-//   * every tile is staged into shared memory together with a 16-byte halo on
-//     both sides by ONE 1-D bulk copy (cp.async.bulk -> UBLKCP, the TMA
-//     engine) that completes on an mbarrier; kStages tiles are in flight per
-//     CTA, so HBM latency is covered without holding registers;
-//   * only the bytes a bulk copy cannot express (row ends that need zero
-//     padding, rows whose base is not 16-byte aligned) are patched by the
-//     threads with guarded loads;
-//   * each thread owns 16 contiguous input bytes per sub-step: one LDS.128 plus
-//     two small halo loads, one coalesced 128-bit store;
-//   * arithmetic is packed: int16 containers are clamped two at a time
-//     (vimin_s16x2_relu), samples travel as four bytes per register, and the
-//     multiply-accumulate is dp2a (two signed 16-bit taps x two unsigned 8-bit
-//     samples per instruction) into an int32 accumulator that starts at the
-//     rounding bias.  When the taps can be pre-scaled so that the shift is 16
-//     bits, the shift + pack of two outputs is a single byte-permute of the
-//     accumulators' upper halves; saturation to [0,255] is again packed.
-//   * the host proves, from the actual taps, that neither the reference's
-//     acc_bits wrap nor int32 can overflow; otherwise the call is served by
-//     the generic int64 kernel (fir1d_generic.cu).
-//   * dilation 2 = interleaved I/Q: the byte-permutes de-interleave into an I
-//     stream and a Q stream, the same MAC runs on each, and the final permute
-//     re-interleaves for free.
-// Tensor cores are deliberately not used: 3/5 taps is not a contraction.
-#include "common.cuh"
+// Host side of the staged 1-D fixed-point FIR (kernels: fir1d_staged.cuh):
+// proves from the actual taps that the packed int32 datapath is exact, builds
+// the dp2a tap pairs, and dispatches to the instantiation for the containers.
+#include "fir1d_staged.cuh"
+#include "fastplan.h"
 
 #include <cstdlib>
-#include <mutex>
 
 namespace firgpu {
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kChunk = 16;                                 // input bytes per thread per sub-step
-constexpr int kSub = 4;                                    // sub-steps per tile
-constexpr int kTileBytes = kThreads * kChunk * kSub;       // 16 KiB
-constexpr int kPad = 16;                                   // halo bytes staged on each side
-constexpr int kStageBytes = ((kTileBytes + 2 * kPad + 127) / 128) * 128;
-constexpr int kStages = 3;
-constexpr int kSmemBytes = kStages * kStageBytes + kStages * 8;
-constexpr int kMaxFastTaps = 9;
-constexpr int kMaxPairs = 5;
-
-struct StagedParams {
-    const unsigned char *x;
-    unsigned char *y;
-    long long rows, cols, ld_x, ld_y;          // cols / ld in scalars of the container type
-    long long halo_left, halo_right;           // readable neighbour scalars (shard seams)
-    long long tiles_per_row, total_tiles;
-    int shift;                                 // SHIFT post mode: frac_bits
-    int bias;                                  // accumulator start value
-    int x_bulk_ok;                             // base and row pitch are 16-byte aligned
-    int y_vec_ok;
-    uint32_t cp_even[kMaxPairs];               // dp2a tap pairs, window starting on an even sample
-    uint32_t cp_odd[kMaxPairs];                // ... on an odd sample
-    int32_t hq[kMaxFastTaps];                  // IMAD mode taps
-};
-
-// ---- PTX wrappers -----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "FIRGPU_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra FIRGPU_DONE_%=;\n"
-        "bra FIRGPU_WAIT_%=;\n"
-        "FIRGPU_DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared through the TMA engine; size and both
-// addresses are multiples of 16 bytes.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ int dp2a_lo(uint32_t taps, uint32_t bytes, int acc)
-{
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(bytes), "r"(acc));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi(uint32_t taps, uint32_t bytes, int acc)
-{
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(bytes), "r"(acc));
-    return d;
-}
-template <int N> __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t *dst);
-template <> __device__ __forceinline__ void lds_words<0>(uint32_t, uint32_t *) {}
-template <> __device__ __forceinline__ void lds_words<1>(uint32_t addr, uint32_t *dst)
-{
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dst[0]) : "r"(addr));
-}
-template <> __device__ __forceinline__ void lds_words<2>(uint32_t addr, uint32_t *dst)
-{
-    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(dst[0]), "=r"(dst[1]) : "r"(addr));
-}
-template <> __device__ __forceinline__ void lds_words<4>(uint32_t addr, uint32_t *dst)
-{
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]) : "r"(addr));
-}
-
-__host__ __device__ constexpr long long floor_div(long long a, long long b)
-{
-    return a >= 0 ? a / b : -((-a + b - 1) / b);
-}
-
-// ---- compile-time geometry of one (taps, dilation, container) combination ----
-template <typename InT, int L, int DIL> struct Geo {
-    static constexpr int ES = sizeof(InT);
-    static constexpr int hi = L / 2;              // taps reaching towards higher indices
-    static constexpr int lo = L - 1 - hi;         // ... lower indices
-    static constexpr int HL4 = (lo + 3) / 4 * 4;  // stream halo, whole byte-quads
-    static constexpr int HR4 = (hi + 3) / 4 * 4;
-    static constexpr int SC = kChunk / ES;        // scalars per chunk
-    static constexpr int S = SC / DIL;            // samples per stream per chunk
-    static constexpr int HLB = HL4 * DIL * ES;    // halo bytes actually loaded
-    static constexpr int HRB = HR4 * DIL * ES;
-    static constexpr int NR = (HLB + kChunk + HRB) / 4;   // raw 32-bit words per chunk
-    static constexpr int NB = (HL4 + S + HR4) / 4;        // byte-quads per stream
-    static constexpr int NPE = (L + 1) / 2;
-    static constexpr int NPO = L / 2 + 1;
-    static constexpr int TS = kTileBytes / ES;    // scalars per tile
-    static constexpr int PADS = kPad / ES;        // scalars per staged pad
-    static_assert(HLB <= kPad && HRB <= kPad, "halo exceeds the staged pad");
-    static_assert(L >= 1 && L <= kMaxFastTaps, "tap count outside the staged kernel's range");
-};
-
-struct TilePlan {
-    long long row, col0;            // tile origin (scalars)
-    long long bulk_lo, bulk_hi;     // scalar range moved by the bulk copy (global columns)
-    long long need_hi;              // staged data is consumed up to this column
-};
-
-template <typename G>
-__device__ __forceinline__ TilePlan plan_tile(const StagedParams &p, long long tile)
-{
-    TilePlan t;
-    t.row = tile / p.tiles_per_row;
-    t.col0 = (tile - t.row * p.tiles_per_row) * G::TS;
-    const long long g0 = t.col0 - G::PADS, g1 = t.col0 + G::TS + G::PADS;
-    const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
-    long long in_tile = p.cols - t.col0;
-    if (in_tile > G::TS) in_tile = G::TS;
-    t.need_hi = t.col0 + (in_tile + G::SC - 1) / G::SC * G::SC + G::PADS;
-    if (t.need_hi > g1) t.need_hi = g1;
-    constexpr int Q = 16 / G::ES;                 // scalars per 16 bytes
-    long long lo = floor_div(vlo + Q - 1, Q) * Q, hi = floor_div(vhi, Q) * Q;
-    if (lo < g0) lo = g0;
-    if (hi > t.need_hi) hi = t.need_hi;
-    if (!p.x_bulk_ok || hi <= lo) lo = hi = g0;
-    t.bulk_lo = lo;
-    t.bulk_hi = hi;
-    return t;
-}
-
-// One stream of byte-packed samples -> S accumulators.
-template <typename G, int L, int MAC>
-__device__ __forceinline__ void mac_stream(const StagedParams &p, const uint32_t (&B)[G::NB], int (&acc)[G::S])
-{
-#pragma unroll
-    for (int i = 0; i < G::S; ++i) {
-        int a = p.bias;
-        if constexpr (MAC == 0) {
-            const int s0 = G::HL4 + i - G::lo;
-            if ((s0 & 1) == 0) {
-#pragma unroll
-                for (int k = 0; k < G::NPE; ++k) {
-                    const int q = s0 / 2 + k;
-                    if ((q >> 1) < G::NB)
-                        a = (q & 1) ? dp2a_hi(p.cp_even[k], B[q >> 1], a) : dp2a_lo(p.cp_even[k], B[q >> 1], a);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < G::NPO; ++k) {
-                    const int q = (s0 - 1) / 2 + k;
-                    if ((q >> 1) < G::NB)
-                        a = (q & 1) ? dp2a_hi(p.cp_odd[k], B[q >> 1], a) : dp2a_lo(p.cp_odd[k], B[q >> 1], a);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int d = -G::lo; d <= G::hi; ++d) {
-                const int s = G::HL4 + i + d;
-                const int v = (int)__byte_perm(B[s >> 2], 0u, 0x4440u | (unsigned)(s & 3));
-                a += p.hq[G::hi - d] * v;
-            }
-        }
-        acc[i] = a;
-    }
-}
-
-// Two accumulators -> two saturated outputs in 16-bit lanes.
-template <bool HI16>
-__device__ __forceinline__ uint32_t post_pair(int a0, int a1, int shift)
-{
-    uint32_t v;
-    if constexpr (HI16) {
-        v = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x7632u);
-    } else {
-        v = __byte_perm((uint32_t)(a0 >> shift), (uint32_t)(a1 >> shift), 0x5410u);
-    }
-    return __vimin_s16x2_relu(v, 0x00ff00ffu);
-}
-
-template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
-__global__ void __launch_bounds__(kThreads, 3)
-fir1d_staged_kernel(const __grid_constant__ StagedParams p)
-{
-    using G = Geo<InT, L, DIL>;
-    constexpr int ES = G::ES;
-    constexpr int OS = sizeof(OutT);
-    constexpr int NOUT = G::SC * OS / 4;          // output words per chunk
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;
-    const int tid = threadIdx.x;
-
-    long long n_my = 0;
-    if ((long long)blockIdx.x < p.total_tiles)
-        n_my = (p.total_tiles - 1 - blockIdx.x) / gridDim.x + 1;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](long long i) {
-        const TilePlan t = plan_tile<G>(p, (long long)blockIdx.x + i * gridDim.x);
-        if (t.bulk_hi > t.bulk_lo) {
-            const int stage = (int)(i % kStages);
-            const uint32_t bytes = (uint32_t)(t.bulk_hi - t.bulk_lo) * ES;
-            const uint32_t dst = smem_base + stage * kStageBytes + (uint32_t)(t.bulk_lo - (t.col0 - G::PADS)) * ES;
-            const unsigned char *src = p.x + (t.row * p.ld_x + t.bulk_lo) * ES;
-            fence_proxy_async();
-            mbar_expect_tx(bar_base + 8 * stage, bytes);
-            bulk_g2s(dst, src, bytes, bar_base + 8 * stage);
-        }
-    };
-
-    if (tid == 0) {
-        for (long long i = 0; i < kStages && i < n_my; ++i) issue(i);
-    }
-
-    uint32_t phase_bits = 0;
-    for (long long i = 0; i < n_my; ++i) {
-        const int stage = (int)(i % kStages);
-        const TilePlan t = plan_tile<G>(p, (long long)blockIdx.x + i * gridDim.x);
-        const long long g0 = t.col0 - G::PADS;
-        unsigned char *st = smem + stage * kStageBytes;
-        const InT *xrow = reinterpret_cast<const InT *>(p.x) + t.row * p.ld_x;
-
-        // Patch what the bulk copy does not cover: zero padding outside the
-        // readable range, and everything when the row is not 16-byte aligned.
-        const bool has_bulk = t.bulk_hi > t.bulk_lo;
-        const long long left_end = has_bulk ? t.bulk_lo : t.need_hi;
-        const long long right_begin = has_bulk ? t.bulk_hi : t.need_hi;
-        const bool patch = left_end > g0 || t.need_hi > right_begin;
-        if (patch) {
-            const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
-            InT *sts = reinterpret_cast<InT *>(st);
-            for (long long g = g0 + tid; g < left_end; g += kThreads)
-                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
-            for (long long g = right_begin + tid; g < t.need_hi; g += kThreads)
-                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
-            __syncthreads();
-        }
-        if (has_bulk) {
-            mbar_wait(bar_base + 8 * stage, (phase_bits >> stage) & 1u);
-            phase_bits ^= 1u << stage;
-        }
-
-        // Stage -> registers for all sub-steps, then hand the stage back.
-        uint32_t raw[kSub][G::NR];
-        const uint32_t st_addr = smem_base + stage * kStageBytes + kPad + tid * kChunk;
-#pragma unroll
-        for (int u = 0; u < kSub; ++u) {
-            const uint32_t a = st_addr + u * (kThreads * kChunk);
-            lds_words<G::HLB / 4>(a - G::HLB, &raw[u][0]);
-            lds_words<4>(a, &raw[u][G::HLB / 4]);
-            lds_words<G::HRB / 4>(a + kChunk, &raw[u][G::HLB / 4 + 4]);
-        }
-        __syncthreads();
-        if (tid == 0 && i + kStages < n_my) issue(i + kStages);
-
-        OutT *yrow = reinterpret_cast<OutT *>(p.y) + t.row * p.ld_y;
-#pragma unroll
-        for (int u = 0; u < kSub; ++u) {
-            const long long n0 = t.col0 + (long long)(u * kThreads + tid) * G::SC;
-            if (n0 >= p.cols) continue;
-
-            // containers -> byte-packed streams
-            uint32_t B[DIL][G::NB];
-            if constexpr (ES == 2) {
-#pragma unroll
-                for (int j = 0; j < G::NR; ++j) raw[u][j] = __vimin_s16x2_relu(raw[u][j], 0x00ff00ffu);
-            }
-            if constexpr (ES == 1 && DIL == 1) {
-#pragma unroll
-                for (int j = 0; j < G::NB; ++j) B[0][j] = raw[u][j];
-            } else if constexpr (ES == 2 && DIL == 1) {
-#pragma unroll
-                for (int j = 0; j < G::NB; ++j) B[0][j] = __byte_perm(raw[u][2 * j], raw[u][2 * j + 1], 0x6420u);
-            } else if constexpr (ES == 1 && DIL == 2) {
-#pragma unroll
-                for (int j = 0; j < G::NB; ++j) {
-                    B[0][j] = __byte_perm(raw[u][2 * j], raw[u][2 * j + 1], 0x6420u);
-                    B[1][j] = __byte_perm(raw[u][2 * j], raw[u][2 * j + 1], 0x7531u);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < G::NB; ++j) {
-                    const uint32_t ta = __byte_perm(raw[u][4 * j], raw[u][4 * j + 1], 0x6240u);
-                    const uint32_t tb = __byte_perm(raw[u][4 * j + 2], raw[u][4 * j + 3], 0x6240u);
-                    B[0][j] = __byte_perm(ta, tb, 0x5410u);
-                    B[1][j] = __byte_perm(ta, tb, 0x7632u);
-                }
-            }
-
-            int acc[DIL][G::S];
-#pragma unroll
-            for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, B[d], acc[d]);
-
-            // accumulators -> saturated 16-bit lanes in memory order
-            uint32_t V[G::SC / 2];
-            if constexpr (DIL == 1) {
-#pragma unroll
-                for (int j = 0; j < G::S / 2; ++j) V[j] = post_pair<HI16>(acc[0][2 * j], acc[0][2 * j + 1], p.shift);
-            } else {
-#pragma unroll
-                for (int j = 0; j < G::S; ++j) V[j] = post_pair<HI16>(acc[0][j], acc[1][j], p.shift);
-            }
-            uint32_t O[NOUT];
-            if constexpr (OS == 2) {
-#pragma unroll
-                for (int j = 0; j < NOUT; ++j) O[j] = V[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < NOUT; ++j) O[j] = __byte_perm(V[2 * j], V[2 * j + 1], 0x6420u);
-            }
-
-            OutT *dst = yrow + n0;
-            if (p.y_vec_ok && n0 + G::SC <= p.cols) {
-                if constexpr (NOUT == 2) {
-                    *reinterpret_cast<uint2 *>(dst) = make_uint2(O[0], O[1]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NOUT; j += 4)
-                        *reinterpret_cast<uint4 *>(dst + j * 4 / OS) = make_uint4(O[j], O[j + 1], O[j + 2], O[j + 3]);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < G::SC; ++e) {
-                    if (n0 + e < p.cols) {
-                        if constexpr (OS == 2) dst[e] = (OutT)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
-                        else dst[e] = (OutT)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ---- host side --------------------------------------------------------------
-struct FastPlan {
-    bool ok = false;
-    bool hi16 = false;
-    int shift = 0, bias = 0;
-    int32_t taps[kMaxFastTaps] = {0};     // possibly pre-scaled
-};
-
-// Decide whether the packed int32 datapath is exact for these taps.
-FastPlan plan_fast(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int mac_mode)
-{
-    FastPlan f;
-    if (n_taps < 1 || n_taps > kMaxFastTaps || frac_bits < 1 || frac_bits > 30) return f;
-    long long sum_abs = 0;
-    for (int k = 0; k < n_taps; ++k) sum_abs += hq[k] < 0 ? -(long long)hq[k] : (long long)hq[k];
-    const long long max_acc = 255LL * sum_abs;                  // |sum| can never exceed this
-    // The reference wraps to acc_bits once per output (fir_1d_fixed_ref.py:110-115);
-    // it is the identity when the sum provably fits.
-    if (acc_bits < 63 && max_acc > (1LL << (acc_bits - 1)) - 1) return f;
-    const int tap_limit = mac_mode == 0 ? 32767 : 0x7fffffff;
-    // Try to pre-scale so that the output shift is exactly 16 bits.
-    if (frac_bits <= 16) {
-        const int up = 16 - frac_bits;
-        bool fits = (max_acc << up) + 32768 <= 0x7fffffffLL;
-        for (int k = 0; fits && k < n_taps; ++k) {
-            const long long sv = (long long)hq[k] * (1LL << up);
-            if (sv > tap_limit || sv < -(long long)tap_limit - 1) fits = false;
-        }
-        if (fits) {
-            f.ok = true;
-            f.hi16 = true;
-            f.shift = 16;
-            f.bias = 32768;
-            for (int k = 0; k < n_taps; ++k) f.taps[k] = (int32_t)((long long)hq[k] * (1LL << up));
-            return f;
-        }
-    }
-    const long long bias = 1LL << (frac_bits - 1);
-    if (max_acc + bias > 0x7fffffffLL) return f;
-    if (((max_acc + bias) >> frac_bits) > 32767) return f;     // packed 16-bit saturate stage
-    for (int k = 0; k < n_taps; ++k)
-        if (hq[k] > tap_limit || hq[k] < -tap_limit - 1) return f;
-    f.ok = true;
-    f.hi16 = false;
-    f.shift = frac_bits;
-    f.bias = (int)bias;
-    for (int k = 0; k < n_taps; ++k) f.taps[k] = hq[k];
-    return f;
-}
-
-// Coefficient for the sample at offset d from the output position:
-// y[n] += h[hi - d] * x[n + d]   (fir_1d_fixed_ref.py:98-107 with idx = n - k + L//2).
-inline int32_t tap_at(const int32_t *taps, int n_taps, int d)
-{
-    const int hi = n_taps / 2, lo = n_taps - 1 - hi;
-    return (d < -lo || d > hi) ? 0 : taps[hi - d];
-}
-inline uint32_t pack_pair(int32_t first, int32_t second)
-{
-    return ((uint32_t)first & 0xffffu) | ((uint32_t)second << 16);
-}
+using namespace staged;
 
 int g_mac_mode = -1;   // -1 = read FIRGPU_MAC once; 0 dp2a, 1 imad
 int mac_mode()
@@ -460,74 +18,6 @@ int mac_mode()
         g_mac_mode = (e && e[0] == '1') ? 1 : 0;
     }
     return g_mac_mode;
-}
-
-template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
-int launch_one(const StagedParams &p, cudaStream_t stream)
-{
-    auto kern = fir1d_staged_kernel<InT, OutT, L, DIL, HI16, MAC>;
-    static std::mutex mu;
-    static int ctas_per_sm[64] = {0};
-    int dev = 0;
-    FIRGPU_CUDA(cudaGetDevice(&dev));
-    int per_sm, sms;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (dev < 64 && ctas_per_sm[dev] == 0) {
-            FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            int n = 0;
-            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, kSmemBytes));
-            ctas_per_sm[dev] = n < 1 ? 1 : n;
-        }
-        per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
-    }
-    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long grid = (long long)sms * per_sm;
-    if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(p);
-    FIRGPU_CUDA(cudaGetLastError());
-    note_launch(FIRGPU_PATH_STAGED);
-    return 1;
-}
-
-template <typename InT, typename OutT, int L, int DIL>
-int launch_modes(const StagedParams &p, bool hi16, int mac, cudaStream_t s)
-{
-    if (mac == 0) {
-        return hi16 ? launch_one<InT, OutT, L, DIL, true, 0>(p, s) : launch_one<InT, OutT, L, DIL, false, 0>(p, s);
-    }
-    // The IMAD datapath is kept for the 5-tap headline shapes only (A/B evidence
-    // for the dp2a choice, profiles/); everything else is dp2a.
-    if constexpr (L == 5 && DIL == 1) {
-        return hi16 ? launch_one<InT, OutT, L, DIL, true, 1>(p, s) : launch_one<InT, OutT, L, DIL, false, 1>(p, s);
-    } else {
-        return 0;
-    }
-}
-
-template <typename InT, typename OutT, int DIL>
-int launch_taps(const StagedParams &p, int n_taps, bool hi16, int mac, cudaStream_t s)
-{
-    switch (n_taps) {
-    case 1: return launch_modes<InT, OutT, 1, DIL>(p, hi16, mac, s);
-    case 2: return launch_modes<InT, OutT, 2, DIL>(p, hi16, mac, s);
-    case 3: return launch_modes<InT, OutT, 3, DIL>(p, hi16, mac, s);
-    case 4: return launch_modes<InT, OutT, 4, DIL>(p, hi16, mac, s);
-    case 5: return launch_modes<InT, OutT, 5, DIL>(p, hi16, mac, s);
-    case 6: return launch_modes<InT, OutT, 6, DIL>(p, hi16, mac, s);
-    case 7: return launch_modes<InT, OutT, 7, DIL>(p, hi16, mac, s);
-    case 8: return launch_modes<InT, OutT, 8, DIL>(p, hi16, mac, s);
-    case 9: return launch_modes<InT, OutT, 9, DIL>(p, hi16, mac, s);
-    default: return 0;
-    }
-}
-
-template <typename InT, typename OutT>
-int launch_dil(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s)
-{
-    if (dilation == 1) return launch_taps<InT, OutT, 1>(p, n_taps, hi16, mac, s);
-    if (dilation == 2) return launch_taps<InT, OutT, 2>(p, n_taps, hi16, mac, s);
-    return 0;
 }
 
 }  // namespace
@@ -543,7 +33,8 @@ int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
     if (force && force[0] == '1') return 0;
     int mac = mac_mode();
     if (mac == 1 && !(a.n_taps == 5 && a.dilation == 1)) mac = 0;
-    const FastPlan f = plan_fast(hq_host, a.n_taps, a.frac_bits, a.acc_bits, mac);
+    if (a.n_taps > kMaxFastTaps) return 0;
+    const FastPlan f = plan_fast(hq_host, a.n_taps, a.frac_bits, a.acc_bits, mac == 0 ? 32767 : 0x7fffffff);
     if (!f.ok) return 0;
 
     const int es = dtype_size(a.in_dtype), os = dtype_size(a.out_dtype);
@@ -557,30 +48,23 @@ int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
     // The kernel stages at most 16 bytes of neighbours; more is never needed.
     p.halo_left = a.halo_left;
     p.halo_right = a.halo_right;
-    const long long ts = kTileBytes / es;
-    p.tiles_per_row = (a.cols + ts - 1) / ts;
-    p.total_tiles = p.tiles_per_row * a.rows;
     p.shift = f.shift;
     p.bias = f.bias;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * es) % 16 == 0);
     const int out_vec = (int)((kChunk / es) * os);           // bytes per vector store: 8, 16 or 32
     const int out_align = out_vec > 16 ? 16 : out_vec;
     p.y_vec_ok = ((uintptr_t)a.y % out_align == 0) && (a.rows == 1 || (a.ld_y * os) % out_align == 0);
-    const int hi = a.n_taps / 2, lo = a.n_taps - 1 - hi;
-    for (int k = 0; k < kMaxPairs; ++k) {
-        p.cp_even[k] = pack_pair(tap_at(f.taps, a.n_taps, -lo + 2 * k), tap_at(f.taps, a.n_taps, -lo + 2 * k + 1));
-        p.cp_odd[k] = pack_pair(tap_at(f.taps, a.n_taps, -lo - 1 + 2 * k), tap_at(f.taps, a.n_taps, -lo + 2 * k));
-    }
+    build_pairs(f.taps, a.n_taps, kMaxPairs, p.cp_even, p.cp_odd);
     for (int k = 0; k < a.n_taps; ++k) p.hq[k] = f.taps[k];
 
     if (a.in_dtype == FIRGPU_U8) {
         return a.out_dtype == FIRGPU_U8
-                   ? launch_dil<uint8_t, uint8_t>(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
-                   : launch_dil<uint8_t, int16_t>(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
+                   ? launch_staged_u8_u8(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
+                   : launch_staged_u8_i16(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
     }
     return a.out_dtype == FIRGPU_U8
-               ? launch_dil<int16_t, uint8_t>(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
-               : launch_dil<int16_t, int16_t>(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
+               ? launch_staged_i16_u8(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
+               : launch_staged_i16_i16(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
 }
 
 }  // namespace firgpu

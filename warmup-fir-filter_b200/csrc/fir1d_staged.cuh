@@ -1,0 +1,588 @@
+// Staged 1-D fixed-point FIR for sm_100a (device code and launch templates): the fast path behind
+// firgpu_fir1d_fixed (reference arithmetic:
+// fir_1d/model/python/fir_1d_fixed_ref.py:95-128, batched as
+// fir_1d/sim/vector/gen_fixed_output.py:44-59).
+//
+// Design (see DESIGN.md "fir1d_staged"):
+//   * persistent CTAs, each walking a strided list of 16 KiB input tiles;
+//   * every tile is staged into shared memory together with a 16-byte halo on
+//     both sides by ONE 1-D bulk copy (cp.async.bulk -> UBLKCP, the TMA
+//     engine) that completes on an mbarrier; kStages tiles are in flight per
+//     CTA, so HBM latency is covered without holding registers;
+//   * only the bytes a bulk copy cannot express (row ends that need zero
+//     padding, rows whose base is not 16-byte aligned) are patched by the
+//     threads with guarded loads;
+//   * each thread owns 16 contiguous input bytes per sub-step: one LDS.128 plus
+//     two small halo loads, one coalesced 128-bit store;
+//   * arithmetic is packed: int16 containers are clamped two at a time
+//     (vimin_s16x2_relu), samples travel as four bytes per register, and the
+//     multiply-accumulate is dp2a (two signed 16-bit taps x two unsigned 8-bit
+//     samples per instruction) into an int32 accumulator that starts at the
+//     rounding bias.  When the taps can be pre-scaled so that the shift is 16
+//     bits, the shift + pack of two outputs is a single byte-permute of the
+//     accumulators' upper halves; saturation to [0,255] is again packed.
+//   * the host proves, from the actual taps, that neither the reference's
+//     acc_bits wrap nor int32 can overflow; otherwise the call is served by
+//     the generic int64 kernel (fir1d_generic.cu).
+//   * dilation 2 = interleaved I/Q: the byte-permutes de-interleave into an I
+//     stream and a Q stream, the same MAC runs on each, and the final permute
+//     re-interleaves for free.
+// Tensor cores are deliberately not used: 3/5 taps is not a contraction.
+#pragma once
+#include "common.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace firgpu {
+namespace staged {
+
+constexpr int kChunk = 16;                                 // input bytes per thread per sub-step
+constexpr int kPad = 16;                                   // halo bytes staged on each side
+#ifndef FIRGPU_STORE_CS
+#define FIRGPU_STORE_CS 0
+#endif
+
+// Tunables of one kernel build.  In-flight bytes per SM (= CTAs/SM x stages x
+// tile) is what the HBM system is sensitive to: about 64 KiB per SM is the
+// measured optimum (profiles/r1_sweep_tunables.md); more outstanding bulk reads
+// lower the achieved DRAM bandwidth of a 50/50 read/write stream.
+template <int THREADS, int SUB, int STAGES, int MINBLOCKS, int CTAS_PER_SM> struct Cfg {
+    static constexpr int kThreads = THREADS;               // threads per CTA
+    static constexpr int kSub = SUB;                       // 16-byte sub-steps per thread per tile
+    static constexpr int kStages = STAGES;                 // tiles in flight per CTA
+    static constexpr int kMinBlocks = MINBLOCKS;           // __launch_bounds__ register cap
+    static constexpr int kCtasPerSm = CTAS_PER_SM;         // persistent CTAs per SM (<= occupancy)
+    static constexpr int kTileBytes = THREADS * kChunk * SUB;
+    static constexpr int kStageBytes = ((kTileBytes + 2 * kPad + 127) / 128) * 128;
+    static constexpr int kSmemBytes = STAGES * kStageBytes + STAGES * 8;
+};
+
+// Per-container choice for long rows (HBM sweep on B200, 2^28-sample stream, 5 taps;
+// profiles/r1_sweep_tunables.md): GB/s of the best configuration in the comment.
+template <typename InT, typename OutT> struct TuneFor { using type = Cfg<256, 4, 2, 2, 2>; };
+#ifdef FIRGPU_K_THREADS        // tools/sweep_staged.cu builds one explicit configuration
+template <> struct TuneFor<int16_t, int16_t> { using type = Cfg<FIRGPU_K_THREADS, FIRGPU_K_SUB, FIRGPU_K_STAGES, FIRGPU_K_MINBLOCKS, 0>; };
+template <> struct TuneFor<int16_t, uint8_t> { using type = Cfg<FIRGPU_K_THREADS, FIRGPU_K_SUB, FIRGPU_K_STAGES, FIRGPU_K_MINBLOCKS, 0>; };
+template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<FIRGPU_K_THREADS, FIRGPU_K_SUB, FIRGPU_K_STAGES, FIRGPU_K_MINBLOCKS, 0>; };
+#else
+template <> struct TuneFor<int16_t, int16_t> { using type = Cfg<256, 8, 2, 1, 1>; };   // 6592 GB/s
+template <> struct TuneFor<int16_t, uint8_t> { using type = Cfg<256, 6, 2, 1, 2>; };   // 6463 GB/s
+template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<256, 4, 2, 2, 2>; };   // 6310 GB/s
+#endif
+// Rows shorter than two long-row tiles: 8 KiB tiles, three CTAs per SM.
+using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
+
+constexpr int kMaxFastTaps = 9;
+constexpr int kMaxPairs = 5;
+
+struct StagedParams {
+    const unsigned char *x;
+    unsigned char *y;
+    long long rows, cols, ld_x, ld_y;          // cols / ld in scalars of the container type
+    long long halo_left, halo_right;           // readable neighbour scalars (shard seams)
+    long long tiles_per_row, total_tiles;
+    int shift;                                 // SHIFT post mode: frac_bits
+    int bias;                                  // accumulator start value
+    int x_bulk_ok;                             // base and row pitch are 16-byte aligned
+    int y_vec_ok;
+    uint32_t cp_even[kMaxPairs];               // dp2a tap pairs, window starting on an even sample
+    uint32_t cp_odd[kMaxPairs];                // ... on an odd sample
+    int32_t hq[kMaxFastTaps];                  // IMAD mode taps
+};
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FIRGPU_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FIRGPU_DONE_%=;\n"
+        "bra FIRGPU_WAIT_%=;\n"
+        "FIRGPU_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; size and both
+// addresses are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ int dp2a_lo(uint32_t taps, uint32_t bytes, int acc)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(bytes), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t taps, uint32_t bytes, int acc)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(taps), "r"(bytes), "r"(acc));
+    return d;
+}
+template <int N> __device__ __forceinline__ void lds_words(uint32_t addr, uint32_t *dst);
+template <> __device__ __forceinline__ void lds_words<0>(uint32_t, uint32_t *) {}
+template <> __device__ __forceinline__ void lds_words<1>(uint32_t addr, uint32_t *dst)
+{
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dst[0]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_words<2>(uint32_t addr, uint32_t *dst)
+{
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(dst[0]), "=r"(dst[1]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_words<4>(uint32_t addr, uint32_t *dst)
+{
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]) : "r"(addr));
+}
+
+__device__ __forceinline__ void store_v4(void *ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+#if FIRGPU_STORE_CS
+    asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#else
+    *reinterpret_cast<uint4 *>(ptr) = make_uint4(a, b, c, d);
+#endif
+}
+__device__ __forceinline__ void store_v2(void *ptr, uint32_t a, uint32_t b)
+{
+#if FIRGPU_STORE_CS
+    asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(ptr), "r"(a), "r"(b) : "memory");
+#else
+    *reinterpret_cast<uint2 *>(ptr) = make_uint2(a, b);
+#endif
+}
+
+__host__ __device__ constexpr long long floor_div(long long a, long long b)
+{
+    return a >= 0 ? a / b : -((-a + b - 1) / b);
+}
+
+// ---- compile-time geometry of one (taps, dilation, container) combination ----
+template <typename InT, int L, int DIL> struct Geo {
+    static constexpr int ES = sizeof(InT);
+    static constexpr int hi = L / 2;              // taps reaching towards higher indices
+    static constexpr int lo = L - 1 - hi;         // ... lower indices
+    static constexpr int HL4 = (lo + 3) / 4 * 4;  // stream halo, whole byte-quads
+    static constexpr int HR4 = (hi + 3) / 4 * 4;
+    static constexpr int SC = kChunk / ES;        // scalars per chunk
+    static constexpr int S = SC / DIL;            // samples per stream per chunk
+    static constexpr int HLB = HL4 * DIL * ES;    // halo bytes actually loaded
+    static constexpr int HRB = HR4 * DIL * ES;
+    static constexpr int NR = (HLB + kChunk + HRB) / 4;   // raw 32-bit words per chunk
+    static constexpr int NB = (HL4 + S + HR4) / 4;        // byte-quads per stream
+    static constexpr int NPE = (L + 1) / 2;
+    static constexpr int NPO = L / 2 + 1;
+    static constexpr int PADS = kPad / ES;        // scalars per staged pad
+    static_assert(HLB <= kPad && HRB <= kPad, "halo exceeds the staged pad");
+    static_assert(L >= 1 && L <= kMaxFastTaps, "tap count outside the staged kernel's range");
+};
+
+struct TilePlan {
+    long long row, col0;            // tile origin (scalars)
+    long long bulk_lo, bulk_hi;     // scalar range moved by the bulk copy (global columns)
+    long long need_hi;              // staged data is consumed up to this column
+};
+
+template <typename G, int TS>
+__device__ __forceinline__ TilePlan plan_tile(const StagedParams &p, long long row, unsigned tcol)
+{
+    TilePlan t;
+    t.row = row;
+    t.col0 = (long long)tcol * TS;
+    const long long g0 = t.col0 - G::PADS, g1 = t.col0 + TS + G::PADS;
+    const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
+    long long in_tile = p.cols - t.col0;
+    if (in_tile > TS) in_tile = TS;
+    t.need_hi = t.col0 + (in_tile + G::SC - 1) / G::SC * G::SC + G::PADS;
+    if (t.need_hi > g1) t.need_hi = g1;
+    constexpr int Q = 16 / G::ES;                 // scalars per 16 bytes
+    long long lo = floor_div(vlo + Q - 1, Q) * Q, hi = floor_div(vhi, Q) * Q;
+    if (lo < g0) lo = g0;
+    if (hi > t.need_hi) hi = t.need_hi;
+    if (!p.x_bulk_ok || hi <= lo) lo = hi = g0;
+    t.bulk_lo = lo;
+    t.bulk_hi = hi;
+    return t;
+}
+
+// Walk (row, tile-in-row) forward by `step` tiles; tiles_per_row < 2^31.
+__device__ __forceinline__ void advance_tile(long long &row, unsigned &tcol, unsigned step, unsigned tiles_per_row)
+{
+    tcol += step;
+    if (tcol >= tiles_per_row) {
+        const unsigned q = tcol / tiles_per_row;
+        row += q;
+        tcol -= q * tiles_per_row;
+    }
+}
+
+// One stream of byte-packed samples -> S accumulators.
+template <typename G, int L, int MAC>
+__device__ __forceinline__ void mac_stream(const StagedParams &p, const uint32_t (&B)[G::NB], int (&acc)[G::S])
+{
+#pragma unroll
+    for (int i = 0; i < G::S; ++i) {
+        int a = p.bias;
+        if constexpr (MAC == 0) {
+            const int s0 = G::HL4 + i - G::lo;
+            if ((s0 & 1) == 0) {
+#pragma unroll
+                for (int k = 0; k < G::NPE; ++k) {
+                    const int q = s0 / 2 + k;
+                    if ((q >> 1) < G::NB)
+                        a = (q & 1) ? dp2a_hi(p.cp_even[k], B[q >> 1], a) : dp2a_lo(p.cp_even[k], B[q >> 1], a);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < G::NPO; ++k) {
+                    const int q = (s0 - 1) / 2 + k;
+                    if ((q >> 1) < G::NB)
+                        a = (q & 1) ? dp2a_hi(p.cp_odd[k], B[q >> 1], a) : dp2a_lo(p.cp_odd[k], B[q >> 1], a);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int d = -G::lo; d <= G::hi; ++d) {
+                const int s = G::HL4 + i + d;
+                const int v = (int)__byte_perm(B[s >> 2], 0u, 0x4440u | (unsigned)(s & 3));
+                a += p.hq[G::hi - d] * v;
+            }
+        }
+        acc[i] = a;
+    }
+}
+
+// Two accumulators -> two saturated outputs in 16-bit lanes.
+template <bool HI16>
+__device__ __forceinline__ uint32_t post_pair(int a0, int a1, int shift)
+{
+    uint32_t v;
+    if constexpr (HI16) {
+        v = __byte_perm((uint32_t)a0, (uint32_t)a1, 0x7632u);
+    } else {
+        v = __byte_perm((uint32_t)(a0 >> shift), (uint32_t)(a1 >> shift), 0x5410u);
+    }
+    return __vimin_s16x2_relu(v, 0x00ff00ffu);
+}
+
+// One thread's chunk: raw staged words (left halo | 16 bytes | right halo)
+// -> output words in memory order.
+template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+__device__ __forceinline__ void filter_chunk(const StagedParams &p, uint32_t (&raw)[Geo<InT, L, DIL>::NR],
+                                             uint32_t (&O)[Geo<InT, L, DIL>::SC * sizeof(OutT) / 4])
+{
+    using G = Geo<InT, L, DIL>;
+    constexpr int ES = G::ES;
+    constexpr int OS = sizeof(OutT);
+    constexpr int NOUT = G::SC * OS / 4;
+    // containers -> byte-packed streams
+    uint32_t B[DIL][G::NB];
+    if constexpr (ES == 2) {
+#pragma unroll
+        for (int j = 0; j < G::NR; ++j) raw[j] = __vimin_s16x2_relu(raw[j], 0x00ff00ffu);
+    }
+    if constexpr (ES == 1 && DIL == 1) {
+#pragma unroll
+        for (int j = 0; j < G::NB; ++j) B[0][j] = raw[j];
+    } else if constexpr (ES == 2 && DIL == 1) {
+#pragma unroll
+        for (int j = 0; j < G::NB; ++j) B[0][j] = __byte_perm(raw[2 * j], raw[2 * j + 1], 0x6420u);
+    } else if constexpr (ES == 1 && DIL == 2) {
+#pragma unroll
+        for (int j = 0; j < G::NB; ++j) {
+            B[0][j] = __byte_perm(raw[2 * j], raw[2 * j + 1], 0x6420u);
+            B[1][j] = __byte_perm(raw[2 * j], raw[2 * j + 1], 0x7531u);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G::NB; ++j) {
+            const uint32_t ta = __byte_perm(raw[4 * j], raw[4 * j + 1], 0x6240u);
+            const uint32_t tb = __byte_perm(raw[4 * j + 2], raw[4 * j + 3], 0x6240u);
+            B[0][j] = __byte_perm(ta, tb, 0x5410u);
+            B[1][j] = __byte_perm(ta, tb, 0x7632u);
+        }
+    }
+
+    int acc[DIL][G::S];
+#pragma unroll
+    for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, B[d], acc[d]);
+
+    // accumulators -> saturated 16-bit lanes in memory order
+    uint32_t V[G::SC / 2];
+    if constexpr (DIL == 1) {
+#pragma unroll
+        for (int j = 0; j < G::S / 2; ++j) V[j] = post_pair<HI16>(acc[0][2 * j], acc[0][2 * j + 1], p.shift);
+    } else {
+#pragma unroll
+        for (int j = 0; j < G::S; ++j) V[j] = post_pair<HI16>(acc[0][j], acc[1][j], p.shift);
+    }
+    if constexpr (OS == 2) {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) O[j] = V[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) O[j] = __byte_perm(V[2 * j], V[2 * j + 1], 0x6420u);
+    }
+}
+
+template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+__global__ void __launch_bounds__(C::kThreads, C::kMinBlocks)
+fir1d_staged_kernel(const __grid_constant__ StagedParams p)
+{
+    using G = Geo<InT, L, DIL>;
+    constexpr int kThreads = C::kThreads, kSub = C::kSub, kStages = C::kStages, kStageBytes = C::kStageBytes;
+    constexpr int TS = C::kTileBytes / G::ES;      // scalars per tile
+    constexpr int ES = G::ES;
+    constexpr int OS = sizeof(OutT);
+    constexpr int NOUT = G::SC * OS / 4;          // output words per chunk
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    const int tid = threadIdx.x;
+
+    long long n_my = 0;
+    if ((long long)blockIdx.x < p.total_tiles)
+        n_my = (p.total_tiles - 1 - blockIdx.x) / gridDim.x + 1;
+    const unsigned tpr = (unsigned)p.tiles_per_row;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(bar_base + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // Producer cursor (thread 0 only): the tile whose bulk copy is issued next.
+    long long p_row = 0;
+    unsigned p_tcol = 0;
+    int p_stage = 0;
+    auto issue = [&]() {
+        const TilePlan t = plan_tile<G, TS>(p, p_row, p_tcol);
+        if (t.bulk_hi > t.bulk_lo) {
+            const uint32_t bytes = (uint32_t)(t.bulk_hi - t.bulk_lo) * ES;
+            const uint32_t dst = smem_base + p_stage * kStageBytes + (uint32_t)(t.bulk_lo - (t.col0 - G::PADS)) * ES;
+            const unsigned char *src = p.x + (t.row * p.ld_x + t.bulk_lo) * ES;
+            fence_proxy_async();
+            mbar_expect_tx(bar_base + 8 * p_stage, bytes);
+            bulk_g2s(dst, src, bytes, bar_base + 8 * p_stage);
+        }
+        advance_tile(p_row, p_tcol, gridDim.x, tpr);
+        p_stage = p_stage + 1 == kStages ? 0 : p_stage + 1;
+    };
+    if (tid == 0) {
+        advance_tile(p_row, p_tcol, blockIdx.x, tpr);
+        for (int i = 0; i < kStages && i < n_my; ++i) issue();
+    }
+
+    long long c_row = 0;
+    unsigned c_tcol = 0;
+    advance_tile(c_row, c_tcol, blockIdx.x, tpr);
+    int stage = 0;
+    uint32_t phase_bits = 0;
+    const uint32_t lane_off = kPad + tid * kChunk;
+    for (long long i = 0; i < n_my; ++i) {
+        const TilePlan t = plan_tile<G, TS>(p, c_row, c_tcol);
+        const long long g0 = t.col0 - G::PADS;
+        const uint32_t st_base = smem_base + stage * kStageBytes;
+
+        // Patch what the bulk copy does not cover: zero padding outside the
+        // readable range, and everything when the row is not 16-byte aligned.
+        const bool has_bulk = t.bulk_hi > t.bulk_lo;
+        const long long left_end = has_bulk ? t.bulk_lo : t.need_hi;
+        const long long right_begin = has_bulk ? t.bulk_hi : t.need_hi;
+        if (left_end > g0 || t.need_hi > right_begin) {
+            const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
+            const InT *xrow = reinterpret_cast<const InT *>(p.x) + t.row * p.ld_x;
+            InT *sts = reinterpret_cast<InT *>(smem + stage * kStageBytes);
+            for (long long g = g0 + tid; g < left_end; g += kThreads)
+                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
+            for (long long g = right_begin + tid; g < t.need_hi; g += kThreads)
+                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
+            __syncthreads();
+        }
+        if (has_bulk) {
+            mbar_wait(bar_base + 8 * stage, (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+        }
+
+        // Stage -> registers for all sub-steps, then hand the stage back.
+        uint32_t raw[kSub][G::NR];
+#pragma unroll
+        for (int u = 0; u < kSub; ++u) {
+            const uint32_t a = st_base + lane_off + u * (kThreads * kChunk);
+            lds_words<G::HLB / 4>(a - G::HLB, &raw[u][0]);
+            lds_words<4>(a, &raw[u][G::HLB / 4]);
+            lds_words<G::HRB / 4>(a + kChunk, &raw[u][G::HLB / 4 + 4]);
+        }
+        __syncthreads();
+        if (tid == 0 && i + kStages < n_my) issue();
+
+        OutT *ythread = reinterpret_cast<OutT *>(p.y) + t.row * p.ld_y + t.col0 + tid * G::SC;
+        if (p.y_vec_ok && t.col0 + TS <= p.cols) {
+            // whole tile inside the row: no per-chunk bounds logic at all
+#pragma unroll
+            for (int u = 0; u < kSub; ++u) {
+                uint32_t O[NOUT];
+                filter_chunk<InT, OutT, L, DIL, HI16, MAC>(p, raw[u], O);
+                OutT *dst = ythread + u * (kThreads * G::SC);
+                if constexpr (NOUT == 2) {
+                    store_v2(dst, O[0], O[1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NOUT; j += 4)
+                        store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
+                }
+            }
+        } else {
+            const long long left = p.cols - t.col0 - tid * G::SC;      // scalars from this thread's first chunk to the row end
+#pragma unroll
+            for (int u = 0; u < kSub; ++u) {
+                const long long room = left - u * (kThreads * G::SC);
+                if (room <= 0) continue;
+                uint32_t O[NOUT];
+                filter_chunk<InT, OutT, L, DIL, HI16, MAC>(p, raw[u], O);
+                OutT *dst = ythread + u * (kThreads * G::SC);
+                if (p.y_vec_ok && room >= G::SC) {
+                    if constexpr (NOUT == 2) {
+                        store_v2(dst, O[0], O[1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NOUT; j += 4)
+                            store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < G::SC; ++e) {
+                        if (e < room) {
+                            if constexpr (OS == 2) dst[e] = (OutT)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
+                            else dst[e] = (OutT)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
+                        }
+                    }
+                }
+            }
+        }
+        advance_tile(c_row, c_tcol, gridDim.x, tpr);
+        stage = stage + 1 == kStages ? 0 : stage + 1;
+    }
+}
+
+template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
+{
+    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, HI16, MAC>;
+    static std::mutex mu;
+    static int ctas_per_sm[64] = {0};
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    int per_sm, sms;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 64 && ctas_per_sm[dev] == 0) {
+            FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+            int n = 0;
+            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::kThreads, C::kSmemBytes));
+            if (C::kCtasPerSm > 0 && n > C::kCtasPerSm) n = C::kCtasPerSm;
+            ctas_per_sm[dev] = n < 1 ? 1 : n;
+        }
+        per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
+    }
+    if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {      // tuning knob for profiling runs
+        const int forced = atoi(e);
+        if (forced >= 1 && forced < per_sm) per_sm = forced;
+    }
+    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    StagedParams p = p_in;
+    const long long ts = C::kTileBytes / (int)sizeof(InT);
+    p.tiles_per_row = (p.cols + ts - 1) / ts;
+    if (p.tiles_per_row >= (1LL << 31)) return 0;
+    p.total_tiles = p.tiles_per_row * p.rows;
+    long long grid = (long long)sms * per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, stream>>>(p);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 1;
+}
+
+template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+int launch_one(const StagedParams &p, cudaStream_t stream)
+{
+    using Big = typename TuneFor<InT, OutT>::type;
+#ifndef FIRGPU_K_THREADS
+    if (p.cols * (long long)sizeof(InT) < 2LL * Big::kTileBytes)
+        return launch_cfg<SmallRowCfg, InT, OutT, L, DIL, HI16, MAC>(p, stream);
+#endif
+    return launch_cfg<Big, InT, OutT, L, DIL, HI16, MAC>(p, stream);
+}
+
+template <typename InT, typename OutT, int L, int DIL>
+int launch_modes(const StagedParams &p, bool hi16, int mac, cudaStream_t s)
+{
+    if (mac == 0) {
+        return hi16 ? launch_one<InT, OutT, L, DIL, true, 0>(p, s) : launch_one<InT, OutT, L, DIL, false, 0>(p, s);
+    }
+    // The IMAD datapath is kept for the 5-tap headline shapes only (A/B evidence
+    // for the dp2a choice, profiles/); everything else is dp2a.
+    if constexpr (L == 5 && DIL == 1) {
+        return hi16 ? launch_one<InT, OutT, L, DIL, true, 1>(p, s) : launch_one<InT, OutT, L, DIL, false, 1>(p, s);
+    } else {
+        return 0;
+    }
+}
+
+template <typename InT, typename OutT, int DIL>
+int launch_taps(const StagedParams &p, int n_taps, bool hi16, int mac, cudaStream_t s)
+{
+    switch (n_taps) {
+    case 1: return launch_modes<InT, OutT, 1, DIL>(p, hi16, mac, s);
+    case 2: return launch_modes<InT, OutT, 2, DIL>(p, hi16, mac, s);
+    case 3: return launch_modes<InT, OutT, 3, DIL>(p, hi16, mac, s);
+    case 4: return launch_modes<InT, OutT, 4, DIL>(p, hi16, mac, s);
+    case 5: return launch_modes<InT, OutT, 5, DIL>(p, hi16, mac, s);
+    case 6: return launch_modes<InT, OutT, 6, DIL>(p, hi16, mac, s);
+    case 7: return launch_modes<InT, OutT, 7, DIL>(p, hi16, mac, s);
+    case 8: return launch_modes<InT, OutT, 8, DIL>(p, hi16, mac, s);
+    case 9: return launch_modes<InT, OutT, 9, DIL>(p, hi16, mac, s);
+    default: return 0;
+    }
+}
+
+template <typename InT, typename OutT>
+int launch_dil(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s)
+{
+    if (dilation == 1) return launch_taps<InT, OutT, 1>(p, n_taps, hi16, mac, s);
+    if (dilation == 2) return launch_taps<InT, OutT, 2>(p, n_taps, hi16, mac, s);
+    return 0;
+}
+
+
+// One translation unit per (input, output) container pair instantiates these
+// (fir1d_staged_inst.cu compiled four times), which keeps the build parallel.
+int launch_staged_u8_u8(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+int launch_staged_u8_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+int launch_staged_i16_u8(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+int launch_staged_i16_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+
+}  // namespace staged
+}  // namespace firgpu

@@ -1,9 +1,154 @@
-// Tiled 2-D fixed-point FIR (placeholder until the TMA tensor-map kernel lands):
-// declines every call so that firgpu_fir2d_fixed is served by fir2d_generic.cu.
-#include "common.cuh"
+// Host side of the tiled 2-D fixed-point FIR (kernels: fir2d_tiled.cuh):
+// eligibility, exactness proof, rank-1 factorisation of the integer kernel,
+// CUtensorMap construction, work decomposition.
+#include "fir2d_tiled.cuh"
+#include "fastplan.h"
+
+#include <cstdlib>
 
 namespace firgpu {
+namespace {
+using namespace tiled;
 
-int try_launch_fir2d_fixed_tiled(const Fir2dArgs &, const int32_t *) { return 0; }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+long long gcd_ll(long long a, long long b)
+{
+    a = a < 0 ? -a : a;
+    b = b < 0 ? -b : b;
+    while (b) {
+        const long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// hq[kh][kw] == a[m] * b[n] exactly?  (integer rank-1 factorisation)
+bool factor_rank1(const int32_t *hq, int kh, int kw, long long *a, long long *b)
+{
+    int r = -1;
+    for (int m = 0; m < kh && r < 0; ++m)
+        for (int n = 0; n < kw; ++n)
+            if (hq[m * kw + n] != 0) {
+                r = m;
+                break;
+            }
+    if (r < 0) return false;                       // all-zero kernel: nothing to gain
+    long long g = 0;
+    int c = -1;
+    for (int n = 0; n < kw; ++n) {
+        g = gcd_ll(g, hq[r * kw + n]);
+        if (c < 0 && hq[r * kw + n] != 0) c = n;
+    }
+    for (int n = 0; n < kw; ++n) b[n] = hq[r * kw + n] / g;
+    for (int m = 0; m < kh; ++m) {
+        if ((long long)hq[m * kw + c] % b[c] != 0) return false;
+        a[m] = (long long)hq[m * kw + c] / b[c];
+        for (int n = 0; n < kw; ++n)
+            if (a[m] * b[n] != (long long)hq[m * kw + n]) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
+{
+    if (a.in_dtype != a.out_dtype || (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16)) return 0;
+    if (!shape_supported(a.kh, a.kw)) return 0;
+    const char *force = getenv("FIRGPU_FORCE_GENERIC");
+    if (force && force[0] == '1') return 0;
+    const int es = dtype_size(a.in_dtype);
+    // TMA needs a 16-byte aligned base and 16-byte multiples for every pitch.
+    if ((uintptr_t)a.x % 16 != 0 || (a.ld_x * es) % 16 != 0) return 0;
+    if (a.n_img > 1 && (a.img_stride_x * es) % 16 != 0) return 0;
+    if (a.width >= (1LL << 31) - 4096 || a.height + a.halo_top + a.halo_bottom >= (1LL << 31) - 64 || a.n_img >= (1LL << 31))
+        return 0;
+    EncodeTiledFn encode = encode_fn();
+    if (!encode) return 0;
+
+    const int n_taps = a.kh * a.kw;
+    TiledParams p{};
+    bool sep = false;
+    FastPlan f;
+    long long fa[kMaxKH], fb[8];
+    if (shape_has_separable(a.kh, a.kw) && !(getenv("FIRGPU_NO_SEPARABLE")) && factor_rank1(hq, a.kh, a.kw, fa, fb)) {
+        bool b_fits = true;
+        for (int n = 0; n < a.kw; ++n)
+            if (fb[n] > 32767 || fb[n] < -32768) b_fits = false;
+        if (b_fits) {
+            f = plan_fast(hq, n_taps, a.frac_bits, a.acc_bits, 0x7fffffff);
+            sep = f.ok;
+        }
+    }
+    if (!sep) {
+        f = plan_fast(hq, n_taps, a.frac_bits, a.acc_bits, 32767);
+        if (!f.ok) return 0;
+    }
+    if (sep) {
+        const long long scale = f.hi16 ? (1LL << (16 - a.frac_bits)) : 1;
+        int32_t b32[8];
+        for (int n = 0; n < a.kw; ++n) b32[n] = (int32_t)fb[n];
+        build_pairs(b32, a.kw, kMaxPairs2, p.rp_even, p.rp_odd);
+        for (int m = 0; m < a.kh; ++m) p.col_taps[m] = (int32_t)(fa[m] * scale);
+    } else {
+        for (int m = 0; m < a.kh; ++m) build_pairs(f.taps + m * a.kw, a.kw, kMaxPairs2, p.cp_even[m], p.cp_odd[m]);
+    }
+
+    const int bh = a.kh == 5 ? 10 : 9;                       // Geo2::BH
+    const int stages_per_item = 7;
+    p.band_rows = stages_per_item * bh - (a.kh - 1);
+    p.stages_per_item = stages_per_item;
+    const int outw = kStripBytes / es - 2 * (16 / es);       // Geo2::OUTW
+    p.y = (unsigned char *)a.y;
+    p.ld_y = a.ld_y;
+    p.img_stride_y = a.img_stride_y;
+    p.width = (int)a.width;
+    p.height = (int)a.height;
+    p.n_img = (int)a.n_img;
+    p.n_strips = (int)((a.width + outw - 1) / outw);
+    p.n_bands = (int)((a.height + p.band_rows - 1) / p.band_rows);
+    const long long items = (long long)p.n_img * p.n_bands * p.n_strips;
+    if (items >= (1LL << 31) - (1 << 20)) return 0;
+    p.total_items = (int)items;
+    p.halo_top = (int)a.halo_top;
+    p.shift = f.shift;
+    p.bias = f.bias;
+    p.y_vec_ok = ((uintptr_t)a.y % 16 == 0) && (a.ld_y * es) % 16 == 0 && (a.n_img == 1 || (a.img_stride_y * es) % 16 == 0);
+
+    const long long map_rows = a.halo_top + a.height + a.halo_bottom;
+    CUtensorMap map;
+    cuuint64_t dims[3] = {(cuuint64_t)a.width, (cuuint64_t)map_rows, (cuuint64_t)a.n_img};
+    cuuint64_t strides[2] = {(cuuint64_t)(a.ld_x * es),
+                             (cuuint64_t)((a.n_img > 1 ? a.img_stride_x : map_rows * a.ld_x) * es)};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxElems, (cuuint32_t)bh, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    void *base = (void *)((const unsigned char *)a.x - a.halo_top * a.ld_x * es);
+    const CUresult r = encode(&map, es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 0;                          // shape the TMA cannot describe: generic kernel
+
+    return es == 1 ? launch_tiled_u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream)
+                   : launch_tiled_i16(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
+}
 
 }  // namespace firgpu

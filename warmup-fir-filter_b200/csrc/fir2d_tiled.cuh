@@ -1,0 +1,364 @@
+// Tiled 2-D fixed-point FIR for sm_100a (device code and launch templates):
+// the fast path behind firgpu_fir2d_fixed for 3- and 5-row kernels on uint8 /
+// int16 images.  The reference has no fir_2d; arithmetic = the 1-D model's
+// pre/post-processing (fir_1d/model/python/fir_1d_fixed_ref.py:79-81,110-126)
+// around y[i,j] = sum_m sum_n hq[m][n] * xs[i-m+kh/2][j-n+kw/2].
+//
+// Design (DESIGN.md "fir2d_tiled"):
+//   * a CUtensorMap over [width, rows, images] describes the batch; TMA
+//     (cp.async.bulk.tensor.3d -> UTMALDG) stages boxes of 256 columns x BH
+//     rows; out-of-bounds box elements are ZERO-FILLED by the TMA unit, which
+//     is exactly the reference's zero padding at the four image borders — the
+//     kernel has no border code at all.  Row-band shards expose their halo
+//     rows by shifting the map's origin (halo_top_valid / halo_bottom_valid).
+//   * a CTA owns a vertical strip (2 KiB of columns) of one row band and
+//     streams down it, kStages2 TMA stages in flight; each thread owns 16
+//     bytes of columns and keeps the last KH input rows in registers as
+//     byte-packed samples, so every staged row is read from shared memory once
+//     and nothing is re-read vertically inside a band;
+//   * per output row: KH x ceil((KW+1)/2) dp2a per pixel (general kernels), or
+//     — when the integer kernel is exactly rank-1, hq = a (x) b, proved on the
+//     host — one dp2a row pass per new input row plus KH IMADs per pixel;
+//   * post stage (rounding bias, shift-by-16 as a byte permute, packed
+//     saturate) and the exactness proof are shared with the 1-D kernel.
+#pragma once
+#include "fir1d_staged.cuh"
+
+#include <cuda.h>
+
+namespace firgpu {
+namespace tiled {
+
+using staged::dp2a_hi;
+using staged::dp2a_lo;
+using staged::lds_words;
+using staged::mbar_expect_tx;
+using staged::mbar_init;
+using staged::mbar_wait;
+using staged::post_pair;
+using staged::smem_u32;
+using staged::store_v4;
+
+constexpr int kThreads2 = 128;
+constexpr int kStages2 = 3;
+constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
+constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
+constexpr int kMaxKH = 5;
+constexpr int kMaxPairs2 = 3;                    // KW <= 5
+
+struct TiledParams {
+    unsigned char *y;
+    long long ld_y, img_stride_y;                // elements
+    int width, height, n_img;
+    int n_strips, n_bands, band_rows, stages_per_item;
+    int halo_top;                                // map row of image row 0
+    int shift, bias, y_vec_ok;
+    int total_items;
+    uint32_t cp_even[kMaxKH][kMaxPairs2];        // general: dp2a tap pairs of kernel row m
+    uint32_t cp_odd[kMaxKH][kMaxPairs2];
+    uint32_t rp_even[kMaxPairs2], rp_odd[kMaxPairs2];   // separable: row-pass pairs (vector b)
+    int32_t col_taps[kMaxKH];                    // separable: column taps (vector a, pre-scaled)
+};
+
+template <typename T, int KH, int KW> struct Geo2 {
+    using G1 = staged::Geo<T, KW, 1>;            // horizontal geometry = the 1-D kernel's
+    static constexpr int ES = sizeof(T);
+    static constexpr int RPS = KH >= 4 ? 2 : (KH == 3 ? 3 : 8 / KH);
+    static constexpr int BH = KH * RPS;          // rows per TMA stage (multiple of KH)
+    static constexpr int BOXB = kBoxElems * ES;  // bytes per box row
+    static constexpr int NBX = kStripBytes / BOXB;
+    static constexpr int STAGE = BH * kStripBytes;
+    static constexpr int PADS = 16 / ES;         // columns of pad staged on each side
+    static constexpr int OUTW = kStripBytes / ES - 2 * PADS;    // output columns per strip
+    static constexpr int ACTIVE = OUTW / G1::SC; // threads that own output columns
+    static constexpr int SMEM = kStages2 * STAGE + kStages2 * 8;
+    static constexpr int UP = KH - 1 - KH / 2;   // input rows above the output row
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// Byte offset inside a stage (row 0) of logical byte b of the strip row: the
+// stage is NBX boxes, each [BH][BOXB].
+template <typename G> __device__ __forceinline__ uint32_t stage_offset(uint32_t b)
+{
+    return (b / G::BOXB) * (G::BH * G::BOXB) + (b % G::BOXB);
+}
+
+// acc[i] += taps (x) B for one row of byte-packed samples (same pairing rule
+// as staged::mac_stream).
+template <typename G1, int L>
+__device__ __forceinline__ void mac_row(const uint32_t (&cpe)[kMaxPairs2], const uint32_t (&cpo)[kMaxPairs2],
+                                        const uint32_t (&B)[G1::NB], int (&acc)[G1::S])
+{
+#pragma unroll
+    for (int i = 0; i < G1::S; ++i) {
+        int a = acc[i];
+        const int s0 = G1::HL4 + i - G1::lo;
+        if ((s0 & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < G1::NPE; ++k) {
+                const int q = s0 / 2 + k;
+                if ((q >> 1) < G1::NB) a = (q & 1) ? dp2a_hi(cpe[k], B[q >> 1], a) : dp2a_lo(cpe[k], B[q >> 1], a);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < G1::NPO; ++k) {
+                const int q = (s0 - 1) / 2 + k;
+                if ((q >> 1) < G1::NB) a = (q & 1) ? dp2a_hi(cpo[k], B[q >> 1], a) : dp2a_lo(cpo[k], B[q >> 1], a);
+            }
+        }
+        acc[i] = a;
+    }
+}
+
+template <typename T, int KH, int KW, bool HI16, bool SEP>
+__global__ void __launch_bounds__(kThreads2, 3)
+fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
+{
+    using G = Geo2<T, KH, KW>;
+    using G1 = typename G::G1;
+    constexpr int ES = G::ES;
+    constexpr int NOUT = 4;                       // 16 output bytes per thread per row
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages2 * G::STAGE;
+    const int tid = threadIdx.x;
+
+    int n_my = 0;
+    if ((int)blockIdx.x < p.total_items) n_my = (p.total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+    const int spi = p.stages_per_item;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages2; ++s) mbar_init(bar_base + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // item -> (image, band, strip); consecutive items are neighbouring strips of
+    // one band, so bands that share halo rows are processed at the same time
+    // and the shared rows are L2 hits.
+    auto decode = [&](int ordinal, int &img, int &row0, int &col0) {
+        const int item = (int)blockIdx.x + ordinal * (int)gridDim.x;
+        const int strip = item % p.n_strips;
+        const int t = item / p.n_strips;
+        const int band = t % p.n_bands;
+        img = t / p.n_bands;
+        row0 = band * p.band_rows;
+        col0 = strip * G::OUTW;
+    };
+
+    // ---- producer cursor (thread 0) ------------------------------------------------
+    int p_item = 0, p_j = 0, p_stage = 0;
+    auto issue = [&]() {
+        int img, row0, col0;
+        decode(p_item, img, row0, col0);
+        const uint32_t bar = bar_base + 8 * p_stage;
+        const uint32_t dst = smem_base + p_stage * G::STAGE;
+        mbar_expect_tx(bar, G::STAGE);
+        const int c1 = row0 - G::UP + p_j * G::BH + p.halo_top;
+#pragma unroll
+        for (int bx = 0; bx < G::NBX; ++bx)
+            tma_load_3d(dst + bx * (G::BH * G::BOXB), &tmap, col0 - G::PADS + bx * kBoxElems, c1, img, bar);
+        if (++p_j == spi) {
+            p_j = 0;
+            ++p_item;
+        }
+        p_stage = p_stage + 1 == kStages2 ? 0 : p_stage + 1;
+    };
+    const long long total_stages = (long long)n_my * spi;
+    if (tid == 0) {
+        for (int i = 0; i < kStages2 && i < total_stages; ++i) issue();
+    }
+
+    // ---- per-thread constants ---------------------------------------------------------
+    const bool active = tid < G::ACTIVE;
+    const uint32_t b_main = 16 + tid * 16;
+    const uint32_t off_m = stage_offset<G>(b_main);
+    const uint32_t off_l = stage_offset<G>(b_main - G1::HLB);
+    const uint32_t off_r = stage_offset<G>(b_main + 16);
+
+    uint32_t cpe[SEP ? 1 : KH][kMaxPairs2], cpo[SEP ? 1 : KH][kMaxPairs2];
+    if constexpr (SEP) {
+#pragma unroll
+        for (int k = 0; k < kMaxPairs2; ++k) {
+            cpe[0][k] = p.rp_even[k];
+            cpo[0][k] = p.rp_odd[k];
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < KH; ++m)
+#pragma unroll
+            for (int k = 0; k < kMaxPairs2; ++k) {
+                cpe[m][k] = p.cp_even[m][k];
+                cpo[m][k] = p.cp_odd[m][k];
+            }
+    }
+
+    // rolling window of the last KH input rows
+    uint32_t Bw[SEP ? 1 : KH][G1::NB];            // general: byte-packed samples
+    int Rw[SEP ? KH : 1][G1::S];                  // separable: horizontal sums
+
+    int stage = 0;
+    uint32_t phase_bits = 0;
+    for (int k = 0; k < n_my; ++k) {
+        int img, row0, col0;
+        decode(k, img, row0, col0);
+        const int col = col0 + tid * G1::SC;
+        int rows_here = p.height - row0;
+        if (rows_here > p.band_rows) rows_here = p.band_rows;
+        T *ycol = reinterpret_cast<T *>(p.y) + (long long)img * p.img_stride_y + (long long)row0 * p.ld_y + col;
+        const bool vec = p.y_vec_ok && col + G1::SC <= p.width;
+        const int room = p.width - col;            // columns this thread may write
+        for (int j = 0; j < spi; ++j) {
+            mbar_wait(bar_base + 8 * stage, (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+            if (active && room > 0) {
+                const uint32_t st = smem_base + stage * G::STAGE;
+#pragma unroll 1
+                for (int g = 0; g < G::RPS; ++g) {
+#pragma unroll
+                    for (int rr = 0; rr < KH; ++rr) {
+                        const int r = g * KH + rr;                    // row inside the stage
+                        const int o = j * G::BH + r - (KH - 1);       // output row inside the band
+                        uint32_t raw[G1::NR];
+                        const uint32_t ro = st + r * G::BOXB;
+                        lds_words<G1::HLB / 4>(ro + off_l, &raw[0]);
+                        lds_words<4>(ro + off_m, &raw[G1::HLB / 4]);
+                        lds_words<G1::HRB / 4>(ro + off_r, &raw[G1::HLB / 4 + 4]);
+                        if constexpr (ES == 2) {
+#pragma unroll
+                            for (int q = 0; q < G1::NR; ++q) raw[q] = __vimin_s16x2_relu(raw[q], 0x00ff00ffu);
+                        }
+                        uint32_t Bnew[G1::NB];
+#pragma unroll
+                        for (int q = 0; q < G1::NB; ++q) {
+                            if constexpr (ES == 1) Bnew[q] = raw[q];
+                            else Bnew[q] = __byte_perm(raw[2 * q], raw[2 * q + 1], 0x6420u);
+                        }
+                        if constexpr (SEP) {
+#pragma unroll
+                            for (int i = 0; i < G1::S; ++i) Rw[rr][i] = 0;
+                            mac_row<G1, KW>(cpe[0], cpo[0], Bnew, Rw[rr]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < G1::NB; ++q) Bw[rr][q] = Bnew[q];
+                        }
+                        if (o >= 0 && o < rows_here) {
+                            int acc[G1::S];
+#pragma unroll
+                            for (int i = 0; i < G1::S; ++i) acc[i] = p.bias;
+#pragma unroll
+                            for (int m = 0; m < KH; ++m) {
+                                const int slot = (rr - m + KH) % KH;   // input row (newest - m) <-> kernel row m
+                                if constexpr (SEP) {
+#pragma unroll
+                                    for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
+                                } else {
+                                    mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
+                                }
+                            }
+                            uint32_t V[G1::S / 2];
+#pragma unroll
+                            for (int q = 0; q < G1::S / 2; ++q) V[q] = post_pair<HI16>(acc[2 * q], acc[2 * q + 1], p.shift);
+                            uint32_t O[NOUT];
+                            if constexpr (ES == 2) {
+#pragma unroll
+                                for (int q = 0; q < NOUT; ++q) O[q] = V[q];
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < NOUT; ++q) O[q] = __byte_perm(V[2 * q], V[2 * q + 1], 0x6420u);
+                            }
+                            T *dst = ycol + (long long)o * p.ld_y;
+                            if (vec) {
+                                store_v4(dst, O[0], O[1], O[2], O[3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < G1::SC; ++e) {
+                                    if (e < room) {
+                                        if constexpr (ES == 2) dst[e] = (T)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
+                                        else dst[e] = (T)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                               // every thread is done with this stage
+            if (tid == 0 && (long long)k * spi + j + kStages2 < total_stages) issue();
+            stage = stage + 1 == kStages2 ? 0 : stage + 1;
+        }
+    }
+}
+
+// ---- launch helpers -------------------------------------------------------------
+template <typename T, int KH, int KW, bool HI16, bool SEP>
+int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t stream)
+{
+    using G = Geo2<T, KH, KW>;
+    auto kern = fir2d_tiled_kernel<T, KH, KW, HI16, SEP>;
+    static std::mutex mu;
+    static int ctas_per_sm[64] = {0};
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    int per_sm, sms;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 64 && ctas_per_sm[dev] == 0) {
+            FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+            int n = 0;
+            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads2, G::SMEM));
+            ctas_per_sm[dev] = n < 1 ? 1 : n;
+        }
+        per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
+    }
+    if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {
+        const int forced = atoi(e);
+        if (forced >= 1 && forced < per_sm) per_sm = forced;
+    }
+    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long grid = (long long)sms * per_sm;
+    if (grid > p.total_items) grid = p.total_items;
+    kern<<<(unsigned)grid, kThreads2, G::SMEM, stream>>>(map, p);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 1;
+}
+
+template <typename T, int KH, int KW>
+int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, bool hi16, bool sep, cudaStream_t s)
+{
+    if constexpr (KW >= 3 && !(KH == 3 && KW == 3)) {
+        if (sep)
+            return hi16 ? launch_tiled_one<T, KH, KW, true, true>(map, p, s) : launch_tiled_one<T, KH, KW, false, true>(map, p, s);
+    }
+    return hi16 ? launch_tiled_one<T, KH, KW, true, false>(map, p, s) : launch_tiled_one<T, KH, KW, false, false>(map, p, s);
+}
+
+template <typename T>
+int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
+{
+    if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1>(map, p, hi16, sep, s);
+    if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3>(map, p, hi16, sep, s);
+    if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5>(map, p, hi16, sep, s);
+    return 0;
+}
+
+// Does the (kh, kw) shape have a separable instantiation?
+inline bool shape_has_separable(int kh, int kw) { return kw >= 3 && !(kh == 3 && kw == 3); }
+inline bool shape_supported(int kh, int kw) { return (kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5); }
+int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
+int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
+
+}  // namespace tiled
+}  // namespace firgpu

@@ -1,0 +1,14 @@
+// Instantiates the tiled 2-D kernels for ONE container type
+// (-DFIRGPU_TILED_T=... -DFIRGPU_TILED_NAME=...).
+#include "fir2d_tiled.cuh"
+
+namespace firgpu {
+namespace tiled {
+
+int FIRGPU_TILED_NAME(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
+{
+    return launch_tiled_shape<FIRGPU_TILED_T>(map, p, kh, kw, hi16, sep, s);
+}
+
+}  // namespace tiled
+}  // namespace firgpu
