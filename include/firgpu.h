@@ -171,6 +171,14 @@ int firgpu_fir1d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
                             const int32_t *hq, int n_taps, int dilation,
                             int frac_bits, int acc_bits, int device);
 
+/* n_filters tap sets over one host input: y holds n_filters outputs,
+ * filter_stride_y elements apart (gen_fixed_output.py:91-104 in one call). */
+int firgpu_fir1d_fixed_multi_host(const void *x, void *y, int in_dtype, int out_dtype,
+                                  int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                                  int64_t filter_stride_y,
+                                  const int32_t *hq, int n_filters, int n_taps, int dilation,
+                                  int frac_bits, int acc_bits, int device);
+
 int firgpu_fir1d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
                             int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                             const double *h, int n_taps, int dilation, int device);

@@ -283,3 +283,33 @@ def test_imad_datapath_matches_dp2a(fg, torch):
     env = dict(os.environ, FIRGPU_MAC="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_multi_filter_reads_input_once(fg, torch, manifest):
+    """firgpu_fir1d_fixed_multi[_host]: the generators' coefficient loop as one
+    call.  Four tap sets on uint8 go through the NF=4 staged kernel; any other
+    count / container falls back to single passes — same values either way."""
+    from firgpu import _lib
+    rng = np.random.default_rng(66)
+    for tap in ("3tap", "5tap"):
+        sets = list(manifest[f"coeff_{tap}"].values())
+        for shape in ((37, 4499), (64, 64), (5, 70_000), (1, 300_001)):
+            x = rng.integers(0, 256, size=shape).astype(np.uint8)
+            want = np.stack([onp.fir1d_fixed(x, h) for h in sets])
+            before = _lib.launch_count()
+            got = fg.fir1d_fixed_multi(torch.from_numpy(x).cuda(), sets)
+            assert _lib.launch_count() - before == 1 and _lib.last_path() == _lib.PATH_STAGED
+            assert got.shape == (4,) + shape and np.array_equal(got.cpu().numpy(), want), (tap, shape)
+            assert np.array_equal(fg.fir1d_fixed_multi(x, sets), want), (tap, shape, "host")
+    x = rng.integers(-100, 400, size=(3, 10_001)).astype(np.int16)
+    for sets in ([[0.25, 0.5, 0.25]] * 3, [[0.1, 0.2, 0.3, 0.2, 0.1], [0.2] * 5, [0.5, 0, 0, 0, 0.5], [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16], [0, 0, 1, 0, 0]]):
+        want = np.stack([onp.fir1d_fixed(x, h) for h in sets])
+        assert np.array_equal(fg.fir1d_fixed_multi(torch.from_numpy(x).cuda(), sets).cpu().numpy(), want)
+        assert np.array_equal(fg.fir1d_fixed_multi(x, sets), want)
+    # mixed post modes inside one group (one tap set cannot be pre-scaled to a 16-bit shift)
+    sets = [[0.25, 0.5, 0.25], [-0.125, 1.25, -0.125], [7.5, -7.0, 0.25], [1 / 3] * 3]
+    xu = rng.integers(0, 256, size=(9, 5000)).astype(np.uint8)
+    want = np.stack([onp.fir1d_fixed(xu, h) for h in sets])
+    assert np.array_equal(fg.fir1d_fixed_multi(torch.from_numpy(xu).cuda(), sets).cpu().numpy(), want)
+    with pytest.raises(ValueError, match="same length"):
+        fg.fir1d_fixed_multi(xu, [[1.0], [0.5, 0.5]])

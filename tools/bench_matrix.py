@@ -123,9 +123,21 @@ def main():
         out = torch.empty_like(img)
         k3 = [[1 / 9] * 3] * 3
         k5 = np.outer(LP5, LP5).tolist()
-        for k, tag in ((k3, "3x3 box"), (k5, "5x5 lp")):
-            s = timed(lambda: firgpu.fir2d_fixed(img, k, 12, 32, 16, out_dtype=np.int16, out=out, validate=False), 3, warm=1)
+        from firgpu import quant
+        kr = np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist()
+        for k, tag in ((k3, "3x3 box"), (k5, "5x5 lp rank-1"), (kr, "5x5 general")):
+            hq = quant.quantize_taps(np.asarray(k), 12, 16)
+            s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out_dtype=np.int16, out=out), args.reps, warm=2)
             report(f"2d 16384^2 i16->i16 {tag} q4.12", s, 16384 * 16384, 4)
+    if "multi" in cases:
+        from fir_1d.sim.vector.h_coeff import h_coeff_5tap_map
+        sets = list(h_coeff_5tap_map.values())
+        for hgt, wid in ((2999, 4499), (8192, 16384)):
+            x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
+            s = timed(lambda: firgpu.fir1d_fixed_multi(x, sets, validate=False), args.reps)
+            report(f"multi-filter x4 {hgt}x{wid} u8 -> 4 x u8 5tap q4.12 (1 read + 4 writes)", s, hgt * wid, 5)
+            s = timed(lambda: [firgpu.fir1d_fixed(x, h, validate=False) for h in sets], args.reps)
+            report(f"4 single passes {hgt}x{wid} u8 -> u8 5tap q4.12 (same 5 B/px accounting)", s, hgt * wid, 5)
 
 
 if __name__ == "__main__":

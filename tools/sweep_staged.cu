@@ -44,7 +44,7 @@ static void run_case(const char *name, const void *x, void *y, size_t n_scalars,
 {
     using C = typename TuneFor<InT, OutT>::type;
     constexpr int kThreads = C::kThreads, kSub = C::kSub, kStages = C::kStages, kSmemBytes = C::kSmemBytes, kTileBytes = C::kTileBytes;
-    auto kern = fir1d_staged_kernel<C, InT, OutT, 5, 1, true, 0>;
+    auto kern = fir1d_staged_kernel<C, InT, OutT, 5, 1, true, 0, 1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmemBytes);
@@ -54,6 +54,7 @@ static void run_case(const char *name, const void *x, void *y, size_t n_scalars,
     p.x = (const unsigned char *)x;
     p.y = (unsigned char *)y;
     p.rows = 1;
+    p.n_filters = 1;
     p.cols = (long long)n_scalars;
     p.ld_x = p.ld_y = p.cols;
     const long long ts = kTileBytes / (int)sizeof(InT);
@@ -65,8 +66,8 @@ static void run_case(const char *name, const void *x, void *y, size_t n_scalars,
     p.y_vec_ok = 1;
     const int taps[5] = {4096, 16384, 24576, 16384, 4096};      // simple_lp Q1.15, pre-scaled by 2
     for (int k = 0; k < kMaxPairs; ++k) {
-        p.cp_even[k] = pack_pair(tap_at(taps, 5, -2 + 2 * k), tap_at(taps, 5, -2 + 2 * k + 1));
-        p.cp_odd[k] = pack_pair(tap_at(taps, 5, -3 + 2 * k), tap_at(taps, 5, -2 + 2 * k));
+        p.cp_even[0][k] = pack_pair(tap_at(taps, 5, -2 + 2 * k), tap_at(taps, 5, -2 + 2 * k + 1));
+        p.cp_odd[0][k] = pack_pair(tap_at(taps, 5, -3 + 2 * k), tap_at(taps, 5, -2 + 2 * k));
     }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);

@@ -202,11 +202,12 @@ void copy_rows_host(void *dst, size_t dpitch, const void *src, size_t spitch, si
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
-// 1-D driver.  `run(d_x, d_y, nr, nc, ldd_x, ldd_y, before, after, stream)`
+// 1-D driver (n_out outputs per input, out_stride host elements apart; a piece's
+// device outputs are ldd_y * nr elements apart).  `run(d_x, d_y, nr, nc, ldd_x, ldd_y, before, after, stream)`
 // launches the device entry point on one piece.
 template <typename Run>
 int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
-                int64_t reach_before, int64_t reach_after, int device, Run run)
+                int64_t reach_before, int64_t reach_after, int device, Run run, int n_out = 1, int64_t out_stride = 0)
 {
     if (rows == 0 || cols == 0) {
         tl_path = FIRGPU_PATH_EMPTY;
@@ -246,7 +247,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     for (const Piece &p : pieces) {
         const int64_t ldd = round_up(p.nc + round_up(p.before, q_in) + p.after, q_in);
         max_in = std::max(max_in, ldd * p.nr * es + 256);
-        max_out = std::max(max_out, round_up(p.nc, 16) * p.nr * os + 256);
+        max_out = std::max(max_out, round_up(p.nc, 16) * p.nr * os * n_out + 256);
     }
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if ((rc = ctx_reserve(c, (size_t)max_in, (size_t)max_out, !x_pinned, !y_pinned))) return rc;
@@ -261,8 +262,10 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
         FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
         if (!y_pinned) {
             const Piece &p = pending[s].p;
-            copy_rows_host((char *)y + (p.r0 * ld_y + p.c0) * os, (size_t)ld_y * os, c->p_out[s],
-                           (size_t)pending[s].ldd_y * os, (size_t)p.nc * os, (size_t)p.nr);
+            for (int f = 0; f < n_out; ++f)
+                copy_rows_host((char *)y + (f * out_stride + p.r0 * ld_y + p.c0) * os, (size_t)ld_y * os,
+                               (char *)c->p_out[s] + (size_t)f * pending[s].ldd_y * p.nr * os,
+                               (size_t)pending[s].ldd_y * os, (size_t)p.nc * os, (size_t)p.nr);
         }
         pending[s].busy = false;
         return 0;
@@ -291,11 +294,14 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
         rc = run((const char *)c->d_in[s] + lead * es, c->d_out[s], p.nr, p.nc, ldd_x, ldd_y, p.before, p.after,
                  c->stream[s]);
         if (rc) return rc;
-        char *dst = y_pinned ? (char *)y + (p.r0 * ld_y + p.c0) * os : (char *)c->p_out[s];
-        const size_t dpitch = y_pinned ? (size_t)ld_y * os : (size_t)ldd_y * os;
-        if ((rc = copy_rows_async(dst, dpitch, c->d_out[s], (size_t)ldd_y * os, (size_t)p.nc * os, (size_t)p.nr,
-                                  cudaMemcpyDeviceToHost, c->stream[s])))
-            return rc;
+        for (int f = 0; f < n_out; ++f) {
+            const size_t d_off = (size_t)f * ldd_y * p.nr * os;
+            char *dst = y_pinned ? (char *)y + (f * out_stride + p.r0 * ld_y + p.c0) * os : (char *)c->p_out[s] + d_off;
+            const size_t dpitch = y_pinned ? (size_t)ld_y * os : (size_t)ldd_y * os;
+            if ((rc = copy_rows_async(dst, dpitch, (char *)c->d_out[s] + d_off, (size_t)ldd_y * os, (size_t)p.nc * os,
+                                      (size_t)p.nr, cudaMemcpyDeviceToHost, c->stream[s])))
+                return rc;
+        }
         pending[s].busy = true;
         pending[s].p = p;
         pending[s].ldd_y = ldd_y;
@@ -436,12 +442,28 @@ int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype
     if (n_filters < 0) return set_error(FIRGPU_E_SHAPE, "firgpu_fir1d_fixed_multi: n_filters=%d", n_filters);
     const int os = out_size_fixed(out_dtype);
     if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_multi: out_dtype must be U8 or I16, got %d", out_dtype);
-    // One pass per tap set; the input stays L2-resident between passes for
-    // image-sized inputs (<= 126 MB), so HBM sees it once.
-    for (int f = 0; f < n_filters; ++f) {
-        int rc = firgpu_fir1d_fixed(x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows,
-                                    cols, ld_x, ld_y, hq + (size_t)f * n_taps, n_taps, dilation, frac_bits, acc_bits, 0, 0,
-                                    stream);
+    int rc = check_1d("firgpu_fir1d_fixed_multi", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed_multi", frac_bits, acc_bits))) return rc;
+    if (rows == 0 || cols == 0 || n_filters == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    // Groups of four tap sets are served by ONE pass of the staged kernel (the
+    // input is read from HBM once); the rest one tap set at a time.
+    int f = 0;
+    for (; f + 4 <= n_filters; f += 4) {
+        Fir1dArgs a{x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows, cols, ld_x, ld_y,
+                    n_taps, dilation, frac_bits, acc_bits, 0, 0, (cudaStream_t)stream};
+        rc = try_launch_fir1d_fixed_staged_multi(a, hq + (size_t)f * n_taps, 4, filter_stride_y);
+        if (rc == 1) continue;
+        if (rc != 0) return rc;
+        break;                                        // not eligible: fall through to single passes
+    }
+    for (; f < n_filters; ++f) {
+        rc = firgpu_fir1d_fixed(x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows,
+                                cols, ld_x, ld_y, hq + (size_t)f * n_taps, n_taps, dilation, frac_bits, acc_bits, 0, 0,
+                                stream);
         if (rc) return rc;
     }
     return 0;
@@ -520,6 +542,36 @@ int firgpu_fir1d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
                            return firgpu_fir1d_fixed(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, hq, n_taps, dilation,
                                                      frac_bits, acc_bits, before, after, (void *)s);
                        });
+}
+
+int firgpu_fir1d_fixed_multi_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols,
+                                  int64_t ld_x, int64_t ld_y, int64_t filter_stride_y, const int32_t *hq, int n_filters,
+                                  int n_taps, int dilation, int frac_bits, int acc_bits, int device)
+{
+    int rc = check_1d("firgpu_fir1d_fixed_multi_host", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed_multi_host", frac_bits, acc_bits))) return rc;
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_multi_host: out_dtype must be U8 or I16, got %d", out_dtype);
+    if (n_filters < 1 || n_filters > 64) return set_error(FIRGPU_E_SHAPE, "firgpu_fir1d_fixed_multi_host: n_filters=%d outside [1,64]", n_filters);
+    const int64_t centre = n_taps / 2;
+    return pipeline_1d(x, y, dtype_size(in_dtype), os, rows, cols, ld_x, ld_y, (n_taps - 1 - centre) * (int64_t)dilation,
+                       centre * (int64_t)dilation, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before,
+                           int64_t after, cudaStream_t s) {
+                           if (before == 0 && after == 0)
+                               return firgpu_fir1d_fixed_multi(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, ly * nr, hq,
+                                                               n_filters, n_taps, dilation, frac_bits, acc_bits, (void *)s);
+                           // column segments of one very long row carry halos: one tap set at a time
+                           for (int f = 0; f < n_filters; ++f) {
+                               int r = firgpu_fir1d_fixed(dx, (char *)dy + (size_t)f * ly * nr * os, in_dtype, out_dtype, nr, nc, lx,
+                                                          ly, hq + (size_t)f * n_taps, n_taps, dilation, frac_bits, acc_bits,
+                                                          before, after, (void *)s);
+                               if (r) return r;
+                           }
+                           return 0;
+                       },
+                       n_filters, filter_stride_y);
 }
 
 int firgpu_fir1d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,

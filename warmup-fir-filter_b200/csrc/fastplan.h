@@ -19,7 +19,7 @@ struct FastPlan {
 };
 
 // tap_limit: 32767 when taps travel as signed 16-bit dp2a operands, INT32_MAX for IMAD.
-inline FastPlan plan_fast(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int tap_limit)
+inline FastPlan plan_fast(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int tap_limit, bool allow_hi16 = true)
 {
     FastPlan f;
     if (n_taps < 1 || n_taps > kFastPlanMaxTaps || frac_bits < 1 || frac_bits > 30) return f;
@@ -29,7 +29,7 @@ inline FastPlan plan_fast(const int32_t *hq, int n_taps, int frac_bits, int acc_
     // The reference wraps to acc_bits once per output; that is the identity
     // when the sum provably fits.
     if (acc_bits < 63 && max_acc > (1LL << (acc_bits - 1)) - 1) return f;
-    if (frac_bits <= 16) {
+    if (allow_hi16 && frac_bits <= 16) {
         const int up = 16 - frac_bits;
         bool fits = (max_acc << up) + 32768 <= 0x7fffffffLL;
         for (int k = 0; fits && k < n_taps; ++k) {

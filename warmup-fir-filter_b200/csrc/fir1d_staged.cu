@@ -22,8 +22,9 @@ int mac_mode()
 
 }  // namespace
 
-int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
+int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y)
 {
+    if (n_filters != 1 && n_filters != kMaxFilters) return 0;
     if (a.dilation != 1 && a.dilation != 2) return 0;
     if (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16) return 0;
     if (a.out_dtype != FIRGPU_U8 && a.out_dtype != FIRGPU_I16) return 0;
@@ -32,10 +33,24 @@ int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
     if (force && force[0] == '1') return 0;
     int mac = mac_mode();
-    if (mac == 1 && !(a.n_taps == 5 && a.dilation == 1)) mac = 0;
+    if (mac == 1 && !(a.n_taps == 5 && a.dilation == 1 && n_filters == 1)) mac = 0;
     if (a.n_taps > kMaxFastTaps) return 0;
-    const FastPlan f = plan_fast(hq_host, a.n_taps, a.frac_bits, a.acc_bits, mac == 0 ? 32767 : 0x7fffffff);
-    if (!f.ok) return 0;
+    const int tap_limit = mac == 0 ? 32767 : 0x7fffffff;
+    // every tap set must be provably exact in int32, and all of them share one post mode
+    FastPlan plans[kMaxFilters];
+    bool all_hi16 = true;
+    for (int f = 0; f < n_filters; ++f) {
+        plans[f] = plan_fast(hq_host + (size_t)f * a.n_taps, a.n_taps, a.frac_bits, a.acc_bits, tap_limit);
+        if (!plans[f].ok) return 0;
+        all_hi16 = all_hi16 && plans[f].hi16;
+    }
+    if (!all_hi16) {
+        for (int f = 0; f < n_filters; ++f) {
+            plans[f] = plan_fast(hq_host + (size_t)f * a.n_taps, a.n_taps, a.frac_bits, a.acc_bits, tap_limit, false);
+            if (!plans[f].ok) return 0;
+        }
+    }
+    const FastPlan &f0 = plans[0];
 
     const int es = dtype_size(a.in_dtype), os = dtype_size(a.out_dtype);
     StagedParams p{};
@@ -45,26 +60,33 @@ int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
     p.cols = a.cols;
     p.ld_x = a.ld_x;
     p.ld_y = a.ld_y;
-    // The kernel stages at most 16 bytes of neighbours; more is never needed.
     p.halo_left = a.halo_left;
     p.halo_right = a.halo_right;
-    p.shift = f.shift;
-    p.bias = f.bias;
+    p.n_filters = n_filters;
+    p.filter_stride_y = filter_stride_y;
+    p.shift = f0.shift;
+    p.bias = f0.bias;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * es) % 16 == 0);
     const int out_vec = (int)((kChunk / es) * os);           // bytes per vector store: 8, 16 or 32
     const int out_align = out_vec > 16 ? 16 : out_vec;
-    p.y_vec_ok = ((uintptr_t)a.y % out_align == 0) && (a.rows == 1 || (a.ld_y * os) % out_align == 0);
-    build_pairs(f.taps, a.n_taps, kMaxPairs, p.cp_even, p.cp_odd);
-    for (int k = 0; k < a.n_taps; ++k) p.hq[k] = f.taps[k];
+    p.y_vec_ok = ((uintptr_t)a.y % out_align == 0) && (a.rows == 1 || (a.ld_y * os) % out_align == 0) &&
+                 (n_filters == 1 || (filter_stride_y * os) % out_align == 0);
+    for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, a.n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
+    for (int k = 0; k < a.n_taps; ++k) p.hq[k] = f0.taps[k];
 
     if (a.in_dtype == FIRGPU_U8) {
         return a.out_dtype == FIRGPU_U8
-                   ? launch_staged_u8_u8(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
-                   : launch_staged_u8_i16(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
+                   ? launch_staged_u8_u8(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream)
+                   : launch_staged_u8_i16(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream);
     }
     return a.out_dtype == FIRGPU_U8
-               ? launch_staged_i16_u8(p, a.n_taps, a.dilation, f.hi16, mac, a.stream)
-               : launch_staged_i16_i16(p, a.n_taps, a.dilation, f.hi16, mac, a.stream);
+               ? launch_staged_i16_u8(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream)
+               : launch_staged_i16_i16(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream);
+}
+
+int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
+{
+    return try_launch_fir1d_fixed_staged_multi(a, hq_host, 1, 0);
 }
 
 }  // namespace firgpu

@@ -75,6 +75,7 @@ using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
 
 constexpr int kMaxFastTaps = 9;
 constexpr int kMaxPairs = 5;
+constexpr int kMaxFilters = 4;                 // tap sets applied to one staged input (multi-filter mode)
 
 struct StagedParams {
     const unsigned char *x;
@@ -86,8 +87,10 @@ struct StagedParams {
     int bias;                                  // accumulator start value
     int x_bulk_ok;                             // base and row pitch are 16-byte aligned
     int y_vec_ok;
-    uint32_t cp_even[kMaxPairs];               // dp2a tap pairs, window starting on an even sample
-    uint32_t cp_odd[kMaxPairs];                // ... on an odd sample
+    int n_filters;                             // 1, or kMaxFilters in multi-filter mode
+    long long filter_stride_y;                 // elements between the outputs of consecutive tap sets
+    uint32_t cp_even[kMaxFilters][kMaxPairs];  // dp2a tap pairs, window starting on an even sample
+    uint32_t cp_odd[kMaxFilters][kMaxPairs];   // ... on an odd sample
     int32_t hq[kMaxFastTaps];                  // IMAD mode taps
 };
 
@@ -238,7 +241,7 @@ __device__ __forceinline__ void advance_tile(long long &row, unsigned &tcol, uns
 
 // One stream of byte-packed samples -> S accumulators.
 template <typename G, int L, int MAC>
-__device__ __forceinline__ void mac_stream(const StagedParams &p, const uint32_t (&B)[G::NB], int (&acc)[G::S])
+__device__ __forceinline__ void mac_stream(const StagedParams &p, const int f, const uint32_t (&B)[G::NB], int (&acc)[G::S])
 {
 #pragma unroll
     for (int i = 0; i < G::S; ++i) {
@@ -250,14 +253,14 @@ __device__ __forceinline__ void mac_stream(const StagedParams &p, const uint32_t
                 for (int k = 0; k < G::NPE; ++k) {
                     const int q = s0 / 2 + k;
                     if ((q >> 1) < G::NB)
-                        a = (q & 1) ? dp2a_hi(p.cp_even[k], B[q >> 1], a) : dp2a_lo(p.cp_even[k], B[q >> 1], a);
+                        a = (q & 1) ? dp2a_hi(p.cp_even[f][k], B[q >> 1], a) : dp2a_lo(p.cp_even[f][k], B[q >> 1], a);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < G::NPO; ++k) {
                     const int q = (s0 - 1) / 2 + k;
                     if ((q >> 1) < G::NB)
-                        a = (q & 1) ? dp2a_hi(p.cp_odd[k], B[q >> 1], a) : dp2a_lo(p.cp_odd[k], B[q >> 1], a);
+                        a = (q & 1) ? dp2a_hi(p.cp_odd[f][k], B[q >> 1], a) : dp2a_lo(p.cp_odd[f][k], B[q >> 1], a);
                 }
             }
         } else {
@@ -285,18 +288,13 @@ __device__ __forceinline__ uint32_t post_pair(int a0, int a1, int shift)
     return __vimin_s16x2_relu(v, 0x00ff00ffu);
 }
 
-// One thread's chunk: raw staged words (left halo | 16 bytes | right halo)
-// -> output words in memory order.
-template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
-__device__ __forceinline__ void filter_chunk(const StagedParams &p, uint32_t (&raw)[Geo<InT, L, DIL>::NR],
-                                             uint32_t (&O)[Geo<InT, L, DIL>::SC * sizeof(OutT) / 4])
+// One thread's chunk, step 1: raw staged words (left halo | 16 bytes | right
+// halo) -> byte-packed sample streams (one per I/Q component).
+template <typename InT, int L, int DIL>
+__device__ __forceinline__ void pack_chunk(uint32_t (&raw)[Geo<InT, L, DIL>::NR], uint32_t (&B)[DIL][Geo<InT, L, DIL>::NB])
 {
     using G = Geo<InT, L, DIL>;
     constexpr int ES = G::ES;
-    constexpr int OS = sizeof(OutT);
-    constexpr int NOUT = G::SC * OS / 4;
-    // containers -> byte-packed streams
-    uint32_t B[DIL][G::NB];
     if constexpr (ES == 2) {
 #pragma unroll
         for (int j = 0; j < G::NR; ++j) raw[j] = __vimin_s16x2_relu(raw[j], 0x00ff00ffu);
@@ -322,10 +320,19 @@ __device__ __forceinline__ void filter_chunk(const StagedParams &p, uint32_t (&r
             B[1][j] = __byte_perm(ta, tb, 0x7632u);
         }
     }
+}
 
+// Step 2: byte-packed streams x tap set f -> output words in memory order.
+template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+__device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int f, const uint32_t (&B)[DIL][Geo<InT, L, DIL>::NB],
+                                               uint32_t (&O)[Geo<InT, L, DIL>::SC * sizeof(OutT) / 4])
+{
+    using G = Geo<InT, L, DIL>;
+    constexpr int OS = sizeof(OutT);
+    constexpr int NOUT = G::SC * OS / 4;
     int acc[DIL][G::S];
 #pragma unroll
-    for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, B[d], acc[d]);
+    for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, f, B[d], acc[d]);
 
     // accumulators -> saturated 16-bit lanes in memory order
     uint32_t V[G::SC / 2];
@@ -345,7 +352,32 @@ __device__ __forceinline__ void filter_chunk(const StagedParams &p, uint32_t (&r
     }
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+// Write one chunk's output words: a vector store, or guarded scalars at ragged
+// row ends / unaligned outputs (`room` = scalars left in the row).
+template <typename OutT, int SC>
+__device__ __forceinline__ void store_chunk(OutT *dst, const uint32_t (&O)[SC * sizeof(OutT) / 4], bool vec, long long room)
+{
+    constexpr int OS = sizeof(OutT);
+    constexpr int NOUT = SC * OS / 4;
+    if (vec) {
+        if constexpr (NOUT == 2) {
+            store_v2(dst, O[0], O[1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NOUT; j += 4) store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < SC; ++e) {
+            if (e < room) {
+                if constexpr (OS == 2) dst[e] = (OutT)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
+                else dst[e] = (OutT)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
+            }
+        }
+    }
+}
+
+template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC, int NF>
 __global__ void __launch_bounds__(C::kThreads, C::kMinBlocks)
 fir1d_staged_kernel(const __grid_constant__ StagedParams p)
 {
@@ -443,15 +475,13 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             // whole tile inside the row: no per-chunk bounds logic at all
 #pragma unroll
             for (int u = 0; u < kSub; ++u) {
-                uint32_t O[NOUT];
-                filter_chunk<InT, OutT, L, DIL, HI16, MAC>(p, raw[u], O);
-                OutT *dst = ythread + u * (kThreads * G::SC);
-                if constexpr (NOUT == 2) {
-                    store_v2(dst, O[0], O[1]);
-                } else {
+                uint32_t B[DIL][G::NB];
+                pack_chunk<InT, L, DIL>(raw[u], B);
 #pragma unroll
-                    for (int j = 0; j < NOUT; j += 4)
-                        store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
+                for (int f = 0; f < NF; ++f) {
+                    uint32_t O[NOUT];
+                    mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
+                    store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O, true, G::SC);
                 }
             }
         } else {
@@ -460,25 +490,14 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             for (int u = 0; u < kSub; ++u) {
                 const long long room = left - u * (kThreads * G::SC);
                 if (room <= 0) continue;
-                uint32_t O[NOUT];
-                filter_chunk<InT, OutT, L, DIL, HI16, MAC>(p, raw[u], O);
-                OutT *dst = ythread + u * (kThreads * G::SC);
-                if (p.y_vec_ok && room >= G::SC) {
-                    if constexpr (NOUT == 2) {
-                        store_v2(dst, O[0], O[1]);
-                    } else {
+                uint32_t B[DIL][G::NB];
+                pack_chunk<InT, L, DIL>(raw[u], B);
 #pragma unroll
-                        for (int j = 0; j < NOUT; j += 4)
-                            store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < G::SC; ++e) {
-                        if (e < room) {
-                            if constexpr (OS == 2) dst[e] = (OutT)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
-                            else dst[e] = (OutT)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
-                        }
-                    }
+                for (int f = 0; f < NF; ++f) {
+                    uint32_t O[NOUT];
+                    mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
+                    store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O,
+                                             p.y_vec_ok && room >= G::SC, room);
                 }
             }
         }
@@ -487,10 +506,10 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
     }
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC, int NF = 1>
 int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
 {
-    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, HI16, MAC>;
+    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, HI16, MAC, NF>;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -528,6 +547,12 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
 template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
 int launch_one(const StagedParams &p, cudaStream_t stream)
 {
+    // four tap sets over one staged input (the generators' coefficient loop):
+    // uint8 images, 3 / 5 taps only
+    if constexpr (sizeof(InT) == 1 && sizeof(OutT) == 1 && (L == 3 || L == 5) && DIL == 1 && MAC == 0) {
+        if (p.n_filters == kMaxFilters) return launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, HI16, MAC, kMaxFilters>(p, stream);
+    }
+    if (p.n_filters != 1) return 0;
     using Big = typename TuneFor<InT, OutT>::type;
 #ifndef FIRGPU_K_THREADS
     if (p.cols * (long long)sizeof(InT) < 2LL * Big::kTileBytes)

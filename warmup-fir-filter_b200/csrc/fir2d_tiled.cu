@@ -113,8 +113,8 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
         for (int m = 0; m < a.kh; ++m) build_pairs(f.taps + m * a.kw, a.kw, kMaxPairs2, p.cp_even[m], p.cp_odd[m]);
     }
 
-    const int bh = a.kh == 5 ? 10 : 9;                       // Geo2::BH
-    const int stages_per_item = 7;
+    const int bh = rows_per_stage(a.kh);                     // Geo2::BH
+    const int stages_per_item = (kBandTarget + a.kh - 1 + bh - 1) / bh;
     p.band_rows = stages_per_item * bh - (a.kh - 1);
     p.stages_per_item = stages_per_item;
     const int outw = kStripBytes / es - 2 * (16 / es);       // Geo2::OUTW

@@ -39,8 +39,26 @@ using staged::post_pair;
 using staged::smem_u32;
 using staged::store_v4;
 
-constexpr int kThreads2 = 128;
-constexpr int kStages2 = 3;
+// Tunables (overridable only by tools/sweep_tiled.cu).
+#ifndef FIRGPU_T2_THREADS
+#define FIRGPU_T2_THREADS 128
+#endif
+#ifndef FIRGPU_T2_STAGES
+#define FIRGPU_T2_STAGES 2
+#endif
+#ifndef FIRGPU_T2_RPS5
+#define FIRGPU_T2_RPS5 2          // stage rows = KH * RPS for KH >= 4
+#endif
+#ifndef FIRGPU_T2_RPS3
+#define FIRGPU_T2_RPS3 3          // ... for KH == 3
+#endif
+#ifndef FIRGPU_T2_MINBLOCKS
+#define FIRGPU_T2_MINBLOCKS 3
+#endif
+constexpr int kThreads2 = FIRGPU_T2_THREADS;
+constexpr int kStages2 = FIRGPU_T2_STAGES;
+constexpr int kBandTarget = 64;                  // output rows per band, about
+inline constexpr int rows_per_stage(int kh) { return kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
 constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
 constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
 constexpr int kMaxKH = 5;
@@ -63,8 +81,8 @@ struct TiledParams {
 template <typename T, int KH, int KW> struct Geo2 {
     using G1 = staged::Geo<T, KW, 1>;            // horizontal geometry = the 1-D kernel's
     static constexpr int ES = sizeof(T);
-    static constexpr int RPS = KH >= 4 ? 2 : (KH == 3 ? 3 : 8 / KH);
-    static constexpr int BH = KH * RPS;          // rows per TMA stage (multiple of KH)
+    static constexpr int BH = rows_per_stage(KH);   // rows per TMA stage (multiple of KH)
+    static constexpr int RPS = BH / KH;
     static constexpr int BOXB = kBoxElems * ES;  // bytes per box row
     static constexpr int NBX = kStripBytes / BOXB;
     static constexpr int STAGE = BH * kStripBytes;
@@ -117,7 +135,7 @@ __device__ __forceinline__ void mac_row(const uint32_t (&cpe)[kMaxPairs2], const
 }
 
 template <typename T, int KH, int KW, bool HI16, bool SEP>
-__global__ void __launch_bounds__(kThreads2, 3)
+__global__ void __launch_bounds__(kThreads2, FIRGPU_T2_MINBLOCKS)
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
     using G = Geo2<T, KH, KW>;
@@ -319,6 +337,9 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
         }
         per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
     }
+    // Measured on B200 (profiles/r1_sweep_tunables.md): two stages in flight; 3-row
+    // kernels are fastest with 3 resident CTAs per SM, 5-row kernels with all that fit.
+    if (KH <= 3 && per_sm > 3) per_sm = 3;
     if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {
         const int forced = atoi(e);
         if (forced >= 1 && forced < per_sm) per_sm = forced;

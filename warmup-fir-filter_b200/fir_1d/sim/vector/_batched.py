@@ -35,10 +35,12 @@ def case_stem(path: Path) -> str:
 
 
 def generate_outputs(*, input_dir: Path, out_dir: Path, coeff_map: dict[str, list[float]], name_format: str,
-                     run_image: Callable[[np.ndarray, list[float]], np.ndarray], overwrite: bool) -> int:
+                     run_image: Callable[[np.ndarray, list[float]], np.ndarray], overwrite: bool,
+                     run_image_multi: Callable[[np.ndarray, list[list[float]]], np.ndarray] | None = None) -> int:
     """For every input image x every coefficient set that is missing (or all,
     with ``overwrite``): filter, save, count.  ``name_format`` receives
-    ``stem`` and ``coeff``."""
+    ``stem`` and ``coeff``.  With ``run_image_multi`` all missing coefficient
+    sets of an image are computed by one call (the image is read once)."""
     inputs = list_input_files(input_dir)
     if not inputs:
         raise FileNotFoundError(f"No input .npy files found in {input_dir}")
@@ -53,6 +55,12 @@ def generate_outputs(*, input_dir: Path, out_dir: Path, coeff_map: dict[str, lis
         if not todo:
             continue
         image = load_image_u8(path)
+        if run_image_multi is not None and len(todo) > 1:
+            outputs = run_image_multi(image, [taps for _, taps in todo])
+            for (target, _), y in zip(todo, outputs):
+                np.save(target, y)
+                written += 1
+            continue
         for target, taps in todo:
             np.save(target, run_image(image, taps))
             written += 1

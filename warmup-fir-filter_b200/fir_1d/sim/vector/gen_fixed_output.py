@@ -44,6 +44,7 @@ def _generate(tap_label: str, coeff_map, input_dir: Path, output_dir: Path, frac
         run_image=lambda img, taps: _run_fixed_rowwise(img, taps, frac_bits=frac_bits, acc_bits=acc_bits,
                                                        coeff_bits=coeff_bits),
         overwrite=overwrite,
+        run_image_multi=lambda img, tap_sets: _ops.fir1d_fixed_multi(img, tap_sets, frac_bits, acc_bits, coeff_bits),
     )
 
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "firgpu_fir2d_fixed": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir2d_ideal": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir1d_fixed_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci]),
+    "firgpu_fir1d_fixed_multi_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci, _ci]),
     "firgpu_fir1d_ideal_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci]),
     "firgpu_fir2d_fixed_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci]),
     "firgpu_fir2d_ideal_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _vp, _ci, _ci, _ci]),

@@ -286,7 +286,16 @@ def fir2d_fixed(x, h2d, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int
         if validate:
             quant.check_samples_finite(x)
     quant.check_bits(frac_bits, acc_bits, coeff_bits)
-    hq = np.ascontiguousarray(quant.quantize_taps(hh, frac_bits, coeff_bits))
+    hq = quant.quantize_taps(hh, frac_bits, coeff_bits)
+    return fir2d_fixed_q(x, hq, frac_bits, acc_bits, out_dtype=out_dtype, out=out, device=device,
+                         halo_top_valid=halo_top_valid, halo_bottom_valid=halo_bottom_valid)
+
+
+def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8, out=None, device: int = -1,
+                  halo_top_valid: int = 0, halo_bottom_valid: int = 0):
+    """:func:`fir2d_fixed` with already-quantised integer taps ``[kh, kw]`` and
+    no validation: the thin layer over ``firgpu_fir2d_fixed[_host]``."""
+    hq = np.ascontiguousarray(hq2d, dtype=np.int32)
     kh, kw = hq.shape
     L = _lib.lib()
     out_code = _OUT_FIXED[np.dtype(out_dtype)]
@@ -315,6 +324,55 @@ def fir2d_fixed(x, h2d, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int
         import torch
         return torch.from_numpy(y)
     return y
+
+
+def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *, out_dtype=np.uint8,
+                      device: int = -1, validate: bool = True):
+    """Several tap sets (all of one length) over ONE pass of the input — the
+    coefficient loop of the output-vector generators
+    (fir_1d/sim/vector/gen_fixed_output.py:91-104) as a single call.  Returns an
+    array of shape ``[len(h_sets)] + x.shape``; groups of four tap sets are
+    served by one kernel launch that reads ``x`` from HBM once."""
+    h_sets = [list(h) for h in h_sets]
+    for h in h_sets:
+        quant.validate_taps(h)
+    if len({len(h) for h in h_sets}) != 1:
+        raise ValueError("all tap sets of one multi-filter call must have the same length")
+    is_t = _is_torch(x)
+    if is_t:
+        if validate:
+            _check_finite_torch(x)
+    else:
+        x = _np_container(x)
+        if validate:
+            quant.check_samples_finite(x)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = np.ascontiguousarray(np.stack([quant.quantize_taps(h, frac_bits, coeff_bits) for h in h_sets]), dtype=np.int32)
+    nf, n_taps = hq.shape
+    L = _lib.lib()
+    out_code = _OUT_FIXED[np.dtype(out_dtype)]
+    if is_t and x.is_cuda:
+        import torch
+        t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
+        y = torch.empty((nf,) + tuple(x.shape), dtype=_torch_dtype(out_dtype), device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir1d_fixed_multi(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld,
+                                                  cols, rows * cols, _taps_ptr(hq), nf, n_taps, 1, frac_bits, acc_bits,
+                                                  stream))
+        return y
+    a = _np_container(x.numpy() if is_t else x)
+    rows, cols = _rows_cols(a.shape)
+    y = np.empty((nf,) + a.shape, dtype=out_dtype)
+    _lib.check(L.firgpu_fir1d_fixed_multi_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
+                                               cols, cols, rows * cols, _taps_ptr(hq), nf, n_taps, 1, frac_bits,
+                                               acc_bits, device))
+    return torch_from(y) if is_t else y
+
+
+def torch_from(a):
+    import torch
+    return torch.from_numpy(a)
 
 
 def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, validate: bool = True):
