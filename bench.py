@@ -233,6 +233,7 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():

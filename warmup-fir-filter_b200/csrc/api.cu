@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -90,8 +91,20 @@ int check_bits(const char *fn, int frac_bits, int acc_bits)
 // bounced through pinned slot buffers; pinned / registered memory is DMA'd
 // directly.
 // ---------------------------------------------------------------------------
-constexpr int kSlots = 3;
-constexpr size_t kChunkTarget = 32u << 20;   // input bytes per chunk
+constexpr int kSlots = 4;
+constexpr size_t kChunkDefault = 32u << 20;  // input bytes per chunk
+
+// FIRGPU_CHUNK_MB overrides the chunk size (tuning / tests of the segment path).
+size_t chunk_target()
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("FIRGPU_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        v = mb >= 1 && mb <= 1024 ? (size_t)mb << 20 : kChunkDefault;
+    }
+    return v;
+}
 
 struct HostCtx {
     std::mutex mu;
@@ -226,15 +239,15 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     std::vector<Piece> pieces;
     const int64_t row_bytes = cols * es;
     const int64_t q_in = 16 / es;                      // scalars per 16 bytes
-    if ((size_t)row_bytes <= kChunkTarget) {
-        int64_t per = (int64_t)(kChunkTarget / (size_t)row_bytes);
+    if ((size_t)row_bytes <= chunk_target()) {
+        int64_t per = (int64_t)(chunk_target() / (size_t)row_bytes);
         if (per < 1) per = 1;
         // keep at least kSlots pieces in flight when there is enough work
         if (rows >= 2 * kSlots && per > (rows + 2 * kSlots - 1) / (2 * kSlots) && (size_t)(row_bytes * rows) > (4u << 20))
             per = (rows + 2 * kSlots - 1) / (2 * kSlots);
         for (int64_t r = 0; r < rows; r += per) pieces.push_back({r, std::min(per, rows - r), 0, cols, 0, 0});
     } else {
-        const int64_t seg = round_up((int64_t)(kChunkTarget / es), 16384);
+        const int64_t seg = round_up((int64_t)(chunk_target() / es), 16384);
         for (int64_t r = 0; r < rows; ++r)
             for (int64_t c0 = 0; c0 < cols; c0 += seg) {
                 const int64_t nc = std::min(seg, cols - c0);
@@ -330,7 +343,7 @@ int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t h
     std::lock_guard<std::mutex> lock(c->mu);
 
     const int64_t row_bytes = width * es;
-    int64_t band = (int64_t)(kChunkTarget / (size_t)std::max<int64_t>(row_bytes, 1));
+    int64_t band = (int64_t)(chunk_target() / (size_t)std::max<int64_t>(row_bytes, 1));
     if (band < 8) band = 8;
     if (band > height) band = height;
     std::vector<Piece> pieces;     // r0 = image * height + first row

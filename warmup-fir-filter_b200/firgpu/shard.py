@@ -125,17 +125,24 @@ def exchange_halos(buf, lead: int, pieces: list[Piece], rank: int, dist) -> None
     point-to-point send/recv (NCCL on GPUs, gloo in the CPU tests).  This is
     the only inter-rank traffic the path ever needs, and it happens once,
     outside the filtering loop."""
+    import torch
     me = pieces[rank]
     body = buf[lead:lead + me.size]
-    ops = []
+
+    def raw(t):                       # NCCL has no int16: move the bytes
+        return t.contiguous().view(torch.uint8)
+
+    ops, keep = [], []
     if me.after:
-        ops.append(dist.P2POp(dist.irecv, buf[lead + me.size:lead + me.size + me.after], rank + 1))
+        ops.append(dist.P2POp(dist.irecv, raw(buf[lead + me.size:lead + me.size + me.after]), rank + 1))
     if me.before:
-        ops.append(dist.P2POp(dist.irecv, buf[lead - me.before:lead], rank - 1))
+        ops.append(dist.P2POp(dist.irecv, raw(buf[lead - me.before:lead]), rank - 1))
     if rank + 1 < len(pieces) and pieces[rank + 1].before:
-        ops.append(dist.P2POp(dist.isend, body[me.size - pieces[rank + 1].before:].clone(), rank + 1))
+        keep.append(raw(body[me.size - pieces[rank + 1].before:].clone()))
+        ops.append(dist.P2POp(dist.isend, keep[-1], rank + 1))
     if rank > 0 and pieces[rank - 1].after:
-        ops.append(dist.P2POp(dist.isend, body[:pieces[rank - 1].after].clone(), rank - 1))
+        keep.append(raw(body[:pieces[rank - 1].after].clone()))
+        ops.append(dist.P2POp(dist.isend, keep[-1], rank - 1))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
