@@ -132,6 +132,27 @@ int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype,
                        void *stream);
 
 /* ------------------------------------------------------------------------
+ * Fused fixed-vs-ideal comparison (row-batched, no outputs materialised).
+ *
+ * Stands behind _compute_metrics
+ *   fir_1d/sim/vector/gen_3tap_compare_report.py:67-112 (and the 5-tap twin),
+ * which the reference applies to a saved ideal/fixed file pair.  Here both
+ * models are evaluated per sample in one pass over x and reduced to
+ *   metrics[0] = sum |fixed - ideal|     metrics[4] = #(fixed == 0)
+ *   metrics[1] = sum (fixed - ideal)^2   metrics[5] = #(fixed == 255)
+ *   metrics[2] = sum (fixed - ideal)     metrics[6] = #(ideal < 0 or > 255)
+ *   metrics[3] = max |fixed - ideal|
+ * (float64; divide by rows*cols for the report's means).  metrics is a HOST
+ * array of 7 doubles; the call synchronises the stream.
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                         const int32_t *hq, const double *h, int n_taps,
+                         int frac_bits, int acc_bits, double *metrics, void *stream);
+int firgpu_fir1d_compare_host(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                              const int32_t *hq, const double *h, int n_taps,
+                              int frac_bits, int acc_bits, double *metrics, int device);
+
+/* ------------------------------------------------------------------------
  * 2-D fixed-point / ideal FIR over a batch of images.
  *
  * The reference has NO fir_2d implementation (fir_2d/model/cpp/CMakeLists.txt

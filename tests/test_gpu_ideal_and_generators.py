@@ -162,3 +162,63 @@ def test_pipeline_driver_model_stages(tmp_path, monkeypatch):
         pipe.run_pipeline(tap="3", overwrite_vectors=False, skip_input=False, skip_ideal=True, skip_fixed=True,
                           skip_report=True, skip_restore=True, restore_kind="all", ideal_policy="clip",
                           overwrite_images=False, strict_report=False, strict_restore=False, top_k=5)
+
+
+# ---- fused compare metrics ------------------------------------------
+def numpy_metrics(y_ideal, y_fixed):
+    """The reference's `_compute_metrics` (gen_3tap_compare_report.py:67-112) restated on arrays."""
+    diff = y_fixed.astype(np.float64) - y_ideal.astype(np.float64)
+    n = diff.size
+    return {"num_samples": n, "max_abs_err": float(np.abs(diff).max()), "mae": float(np.abs(diff).mean()),
+            "rmse": float(np.sqrt(np.mean(np.square(diff)))), "mean_err": float(diff.mean()),
+            "sat_low_ratio": float(np.mean(y_fixed == 0)), "sat_high_ratio": float(np.mean(y_fixed == 255)),
+            "sat_ratio": float(np.mean(y_fixed == 0)) + float(np.mean(y_fixed == 255)),
+            "clip_needed_ratio": float(np.mean((y_ideal < 0.0) | (y_ideal > 255.0)))}
+
+
+def test_fused_compare_matches_file_based_metrics(images_small, images_inputs, manifest):
+    """Against the reference pipeline's own saved ideal / fixed outputs for
+    the two 64x64 cases, and against oracle outputs for a larger image."""
+    import torch
+    import firgpu
+    stems = sorted({k.split("/")[0] for k in images_small.keys()})
+    for stem in stems:
+        x = images_small[f"{stem}/x"]
+        for tap in ("3tap", "5tap"):
+            for name, h in manifest[f"coeff_{tap}"].items():
+                want = numpy_metrics(images_small[f"{stem}/{tap}/{name}/ideal"], images_small[f"{stem}/{tap}/{name}/fixed"])
+                for got in (firgpu.compare_metrics(x, h), firgpu.compare_metrics(torch.from_numpy(x).cuda(), h)):
+                    assert got["num_samples"] == want["num_samples"]
+                    for key in ("sat_low_ratio", "sat_high_ratio", "clip_needed_ratio", "max_abs_err"):
+                        assert got[key] == want[key], (stem, tap, name, key)
+                    for key in ("mae", "rmse", "mean_err", "sat_ratio"):
+                        assert got[key] == pytest.approx(want[key], rel=1e-11, abs=1e-13), (stem, tap, name, key)
+    # the documented worst case: case_004 (64x64 noise) x edge  (fir_1d/docs/*_compare_analysis_v1.md)
+    noise = images_small["case_004_img_005_64x64_noise_gray/x"]
+    assert firgpu.compare_metrics(noise, manifest["coeff_3tap"]["edge"])["rmse"] == pytest.approx(36.4074, abs=5e-5)
+    assert firgpu.compare_metrics(noise, manifest["coeff_5tap"]["edge"])["rmse"] == pytest.approx(13.4034, abs=5e-5)
+    x = images_inputs["case_001_img_002_640x762_gray"]
+    for h, fb, ab in ((manifest["coeff_5tap"]["sharpen"], 12, 32), (manifest["coeff_3tap"]["edge"], 12, 16), ([0.3, 0.3], 9, 32)):
+        want = numpy_metrics(onp.fir1d_ideal(x, h), onp.fir1d_fixed(x, h, fb, ab, 16))
+        got = firgpu.compare_metrics(x, h, fb, ab, 16)
+        for key, v in want.items():
+            assert got[key] == pytest.approx(v, rel=1e-11, abs=1e-13), key
+    assert firgpu.compare_metrics(np.zeros((0, 5), np.uint8), [1.0])["num_samples"] == 0
+
+
+def test_fused_compare_rows_and_summary(tmp_path, images_small, manifest):
+    from fir_1d.sim.vector import gen_fused_compare as fused
+    for stem in sorted({k.split("/")[0] for k in images_small.keys()}):
+        np.save(tmp_path / f"{stem}_x_u8.npy", images_small[f"{stem}/x"])
+    rows = fused.fused_compare_rows(tmp_path, "5")
+    assert [r["key"] for r in rows] == sorted(r["key"] for r in rows) and len(rows) == 8
+    assert set(rows[0]) >= {"key", "case_stem", "coeff_name", "height", "width", "num_samples", "max_abs_err", "mae", "rmse",
+                            "mean_err", "sat_low_ratio", "sat_high_ratio", "sat_ratio", "clip_needed_ratio"}
+    want_rows = []
+    for r in rows:
+        want_rows.append(numpy_metrics(images_small[f"{r['case_stem']}/5tap/{r['coeff_name']}/ideal"],
+                                       images_small[f"{r['case_stem']}/5tap/{r['coeff_name']}/fixed"]))
+    summary = fused.summarize(rows)
+    assert summary["num_cases"] == 8 and summary["num_samples_total"] == 8 * 64 * 64
+    assert summary["avg_rmse"] == pytest.approx(np.mean([w["rmse"] for w in want_rows]), rel=1e-11)
+    assert summary["max_max_abs_err"] == max(w["max_abs_err"] for w in want_rows)

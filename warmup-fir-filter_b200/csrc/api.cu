@@ -638,6 +638,49 @@ int firgpu_fir2d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
                        });
 }
 
+int firgpu_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq,
+                         const double *h, int n_taps, int frac_bits, int acc_bits, double *metrics, void *stream)
+{
+    int rc = check_1d("firgpu_fir1d_compare", x, x, in_dtype, rows, cols, ld_x, ld_x, hq, n_taps, 1, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_compare", frac_bits, acc_bits))) return rc;
+    if (!h || !metrics) return set_error(FIRGPU_E_NULL, "firgpu_fir1d_compare: NULL taps / metrics pointer");
+    for (int i = 0; i < 7; ++i) metrics[i] = 0.0;
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    return launch_fir1d_compare(x, in_dtype, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, metrics, (cudaStream_t)stream);
+}
+
+int firgpu_fir1d_compare_host(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq,
+                              const double *h, int n_taps, int frac_bits, int acc_bits, double *metrics, int device)
+{
+    int rc = check_1d("firgpu_fir1d_compare_host", x, x, in_dtype, rows, cols, ld_x, ld_x, hq, n_taps, 1, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_compare_host", frac_bits, acc_bits))) return rc;
+    if (!h || !metrics) return set_error(FIRGPU_E_NULL, "firgpu_fir1d_compare_host: NULL taps / metrics pointer");
+    for (int i = 0; i < 7; ++i) metrics[i] = 0.0;
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    const int es = dtype_size(in_dtype);
+    const size_t pitch = (size_t)round_up(cols * es, 16);
+    void *d_x = nullptr;
+    FIRGPU_CUDA(cudaMalloc(&d_x, pitch * (size_t)rows));
+    cudaError_t e = cudaMemcpy2D(d_x, pitch, x, (size_t)ld_x * es, (size_t)cols * es, (size_t)rows, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_x);
+        return check_cuda(e, "cudaMemcpy2D");
+    }
+    rc = launch_fir1d_compare(d_x, in_dtype, rows, cols, (int64_t)(pitch / es), hq, h, n_taps, frac_bits, acc_bits, metrics, 0);
+    cudaFree(d_x);
+    return rc;
+}
+
 int firgpu_pinned_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) return set_error(FIRGPU_E_NULL, "firgpu_pinned_alloc: NULL");

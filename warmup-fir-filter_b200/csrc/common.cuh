@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/firgpu.h"
 
@@ -120,6 +121,9 @@ int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host);
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
 // n_filters tap sets ([n_filters][n_taps]) over one pass of the input; outputs filter_stride_y elements apart.
 int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y);
+// fir1d_compare.cu
+int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
+                         const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s);
 // fir2d.cu
 int launch_fir2d_fixed_generic(const Fir2dArgs &a, const int32_t *hq_host);
 int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);

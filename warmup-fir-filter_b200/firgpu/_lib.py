@@ -30,6 +30,8 @@ SIGNATURES = {
     "firgpu_fir1d_fixed": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir1d_fixed_multi": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci, _vp]),
     "firgpu_fir1d_ideal": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _i64, _i64, _vp]),
+    "firgpu_fir1d_compare": (_ci, [_vp, _ci, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _vp, _vp]),
+    "firgpu_fir1d_compare_host": (_ci, [_vp, _ci, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _vp, _ci]),
     "firgpu_fir2d_fixed": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir2d_ideal": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir1d_fixed_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci]),

@@ -268,6 +268,50 @@ def fir1d_fixed_iq(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: in
     return fir1d_fixed(z, h, frac_bits, acc_bits, coeff_bits, dilation=2, **kw)
 
 
+def compare_metrics(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *, device: int = -1,
+                    validate: bool = True) -> dict:
+    """Fixed-vs-ideal report metrics of one case, fused: both models are
+    evaluated per sample in one pass over ``x`` ([rows, cols] or 1-D) and only
+    seven reductions leave the GPU.  Same keys and definitions as the
+    reference's ``_compute_metrics`` (fir_1d/sim/vector/
+    gen_3tap_compare_report.py:67-112); float64 sums agree with NumPy's to about
+    1e-12 relative (different summation order), counts are exact."""
+    quant.validate_taps(h)
+    is_t = _is_torch(x)
+    if is_t:
+        if validate:
+            _check_finite_torch(x)
+    else:
+        x = _np_container(x)
+        if validate:
+            quant.check_samples_finite(x)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = np.ascontiguousarray(quant.quantize_taps(h, frac_bits, coeff_bits), dtype=np.int32)
+    hh = np.ascontiguousarray([float(v) for v in h], dtype=np.float64)
+    out = np.zeros(7, dtype=np.float64)
+    L = _lib.lib()
+    if is_t and x.is_cuda:
+        import torch
+        t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(L.firgpu_fir1d_compare(t.data_ptr(), _torch_code(t), rows, cols, ld, _taps_ptr(hq), _taps_ptr(hh),
+                                              hq.size, frac_bits, acc_bits, out.ctypes.data, stream))
+    else:
+        a = _np_container(x.numpy() if is_t else x)
+        rows, cols = _rows_cols(a.shape)
+        _lib.check(L.firgpu_fir1d_compare_host(a.ctypes.data, _NP_CODE[a.dtype], rows, cols, cols, _taps_ptr(hq),
+                                               _taps_ptr(hh), hq.size, frac_bits, acc_bits, out.ctypes.data, device))
+    n = rows * cols
+    if n == 0:
+        return {"num_samples": 0, "max_abs_err": 0.0, "mae": 0.0, "rmse": 0.0, "mean_err": 0.0, "sat_low_ratio": 0.0,
+                "sat_high_ratio": 0.0, "sat_ratio": 0.0, "clip_needed_ratio": 0.0}
+    low, high = float(out[4]) / n, float(out[5]) / n
+    return {"num_samples": int(n), "max_abs_err": float(out[3]), "mae": float(out[0]) / n,
+            "rmse": float(np.sqrt(out[1] / n)), "mean_err": float(out[2]) / n, "sat_low_ratio": low,
+            "sat_high_ratio": high, "sat_ratio": low + high, "clip_needed_ratio": float(out[6]) / n}
+
+
 # ---------------------------------------------------------------------------
 # 2-D
 # ---------------------------------------------------------------------------
