@@ -132,6 +132,47 @@ int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype,
                        void *stream);
 
 /* ------------------------------------------------------------------------
+ * Extended 1-D entry points: the reference model with its fixed choices made
+ * parameters.  (centre = n_taps/2, in [0,255], out [0,255], raw = 0) IS the
+ * reference model and is served by the same kernels as the plain calls; any
+ * other setting runs on the generic int64 / fp64 kernels.
+ *
+ *   centre   taps ahead of the output position: y[n] = sum_k h[k] x[n-(k-centre)*dilation].
+ *            centre = 0 is the causal form of Fir1D::process_sample / fir_1d_idel
+ *            (fir_1d/model/cpp/fir_1d_ref.cpp:16-63); with halo_left_valid =
+ *            (n_taps-1)*dilation carried samples in front of x it is chunked
+ *            streaming with state.
+ *   in_lo/in_hi, out_lo/out_hi   sample clamp and output saturation ranges:
+ *            (-32768, 32767) twice with out_dtype I16 is the signed int16
+ *            output path the reference lists as future work
+ *            (fir_1d/docs/fir_1d_3tap_compare_analysis_v1.md:185).
+ *   raw      ideal model only: filter the samples as given, no round / clamp
+ *            (the C++ Fir1D model takes raw doubles).
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_fixed_ex(const void *x, void *y, int in_dtype, int out_dtype,
+                          int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                          const int32_t *hq, int n_taps, int dilation,
+                          int frac_bits, int acc_bits,
+                          int64_t halo_left_valid, int64_t halo_right_valid,
+                          int centre, int in_lo, int in_hi, int out_lo, int out_hi,
+                          void *stream);
+int firgpu_fir1d_ideal_ex(const void *x, void *y, int in_dtype, int out_dtype,
+                          int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                          const double *h, int n_taps, int dilation,
+                          int64_t halo_left_valid, int64_t halo_right_valid,
+                          int centre, int in_lo, int in_hi, int raw, void *stream);
+int firgpu_fir1d_fixed_ex_host(const void *x, void *y, int in_dtype, int out_dtype,
+                               int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                               const int32_t *hq, int n_taps, int dilation,
+                               int frac_bits, int acc_bits,
+                               int centre, int in_lo, int in_hi, int out_lo, int out_hi,
+                               int device);
+int firgpu_fir1d_ideal_ex_host(const void *x, void *y, int in_dtype, int out_dtype,
+                               int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                               const double *h, int n_taps, int dilation,
+                               int centre, int in_lo, int in_hi, int raw, int device);
+
+/* ------------------------------------------------------------------------
  * Fused fixed-vs-ideal comparison (row-batched, no outputs materialised).
  *
  * Stands behind _compute_metrics

@@ -19,17 +19,19 @@ MAX_TAPS = 1024
 PIXEL_LO, PIXEL_HI = 0, 255          # fir_1d_fixed_ref.py:50-51
 
 
-def prep_samples(x) -> np.ndarray:
-    """round-half-up (floor(x + 0.5) in float64) then clamp to [0, 255]
-    (fir_1d/model/python/fir_1d_ref.py:35-41).  Integer inputs skip the
-    rounding, which is the identity on them."""
+def prep_samples(x, lo: int = PIXEL_LO, hi: int = PIXEL_HI) -> np.ndarray:
+    """round-half-up (floor(x + 0.5) in float64) then clamp to [lo, hi]
+    (fir_1d/model/python/fir_1d_ref.py:35-41; the reference's range is
+    [0, 255]).  Integer inputs skip the rounding, which is the identity on
+    them.  Returns uint8 for the reference range, int64 otherwise."""
     a = np.asarray(x)
-    if a.dtype == np.uint8:
+    out_t = np.uint8 if (lo, hi) == (PIXEL_LO, PIXEL_HI) else np.int64
+    if a.dtype == np.uint8 and out_t == np.uint8:
         return a
     if a.dtype.kind in "iub":
-        return np.clip(a, PIXEL_LO, PIXEL_HI).astype(np.uint8)
+        return np.clip(a.astype(np.int64), lo, hi).astype(out_t)
     r = np.floor(a.astype(np.float64) + 0.5)
-    return np.clip(r, PIXEL_LO, PIXEL_HI).astype(np.uint8)
+    return np.clip(r, lo, hi).astype(out_t)
 
 
 def quantize_taps(h, frac_bits: int, coeff_bits: int) -> np.ndarray:
@@ -60,10 +62,12 @@ def post_accumulate(acc: np.ndarray, frac_bits: int, acc_bits: int,
     return acc
 
 
-def _shifted_views(xs: np.ndarray, n_taps: int, dilation: int):
-    """Yield (k, view) where view[..., n] == xs[..., n - (k - L//2)*dilation]
-    with zeros outside (fir_1d_fixed_ref.py:86,99-104)."""
-    centre = n_taps // 2
+def _shifted_views(xs: np.ndarray, n_taps: int, dilation: int, centre: int | None = None):
+    """Yield (k, view) where view[..., n] == xs[..., n - (k - centre)*dilation]
+    with zeros outside; centre = L//2 is the reference's alignment
+    (fir_1d_fixed_ref.py:86,99-104), centre = 0 the causal form of the C++
+    Fir1D (fir_1d/model/cpp/fir_1d_ref.cpp:16-33)."""
+    centre = n_taps // 2 if centre is None else centre
     n = xs.shape[-1]
     left = (n_taps - 1 - centre) * dilation      # reach towards lower indices
     right = centre * dilation                    # reach towards higher indices
@@ -76,31 +80,47 @@ def _shifted_views(xs: np.ndarray, n_taps: int, dilation: int):
 
 def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16,
                 *, dilation: int = 1, taps_are_quantized: bool = False,
-                out_dtype=np.uint8) -> np.ndarray:
+                out_dtype=np.uint8, centre: int | None = None,
+                in_range=(PIXEL_LO, PIXEL_HI), out_range=(PIXEL_LO, PIXEL_HI)) -> np.ndarray:
     """Fixed-point FIR along the last axis; every leading index is an
-    independent, separately zero-padded row (gen_fixed_output.py:44-59)."""
-    xs = prep_samples(x)
+    independent, separately zero-padded row (gen_fixed_output.py:44-59).
+    ``centre`` / ``in_range`` / ``out_range`` turn the reference's fixed
+    choices (L//2, [0,255], [0,255]) into parameters (extended entry points;
+    any non-default value is OUR specification, not reference-pinned)."""
+    xs = prep_samples(x, *in_range)
     hq = np.asarray(h, dtype=np.int64) if taps_are_quantized else quantize_taps(h, frac_bits, coeff_bits)
     assert 1 <= hq.size <= MAX_TAPS
     acc = np.zeros(xs.shape, dtype=np.int64)
     xi = xs.astype(np.int64)
-    for k, view in _shifted_views(xi, hq.size, dilation):
+    for k, view in _shifted_views(xi, hq.size, dilation, centre):
         if hq[k] != 0:
             acc += view * hq[k]
-    return post_accumulate(acc, frac_bits, acc_bits).astype(out_dtype)
+    return post_accumulate(acc, frac_bits, acc_bits, *out_range).astype(out_dtype)
 
 
-def fir1d_ideal(x, h, *, dilation: int = 1, dtype=np.float64) -> np.ndarray:
+def fir1d_ideal(x, h, *, dilation: int = 1, dtype=np.float64, centre: int | None = None, raw: bool = False,
+                in_range=(PIXEL_LO, PIXEL_HI)) -> np.ndarray:
     """float64 model along the last axis: acc = acc + h[k] * xs[...] in
     ascending k, separate multiply and add (fir_1d_ref.py:55-63).  The padded
     zeros contribute +-0.0, which never changes a non-negative-zero sum, so
     including them is bit-identical to the reference's skip."""
-    xs = prep_samples(x).astype(dtype)
+    xs = np.asarray(x, dtype=dtype) if raw else prep_samples(x, *in_range).astype(dtype)
     hh = np.asarray(h, dtype=dtype)
     acc = np.zeros(xs.shape, dtype=dtype)
-    for k, view in _shifted_views(xs, hh.size, dilation):
+    for k, view in _shifted_views(xs, hh.size, dilation, centre):
         acc = acc + hh[k] * view
     return acc
+
+
+def fir1d_full_causal(x, h) -> np.ndarray:
+    """Fir1D::fir_1d_idel (fir_1d/model/cpp/fir_1d_ref.cpp:37-63): raw float64
+    samples, causal alignment, all N + L - 1 outputs = the causal model on the
+    signal extended by L - 1 zeros."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.size == 0 or len(h) == 0:
+        return np.zeros(0)
+    ext = np.concatenate([x, np.zeros(len(h) - 1)])
+    return fir1d_ideal(ext, h, centre=0, raw=True)
 
 
 def fir1d_fixed_iq(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16,

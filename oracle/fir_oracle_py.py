@@ -34,7 +34,7 @@ PIXEL_HI = 255    # fir_1d/model/python/fir_1d_fixed_ref.py:50
 # --------------------------------------------------------------------------
 # shared stages
 # --------------------------------------------------------------------------
-def prep_sample(sample) -> int:
+def prep_sample(sample, lo: int = PIXEL_LO, hi: int = PIXEL_HI) -> int:
     """One input sample -> integer pixel.
 
     Round half up as floor(s + 0.5) evaluated in float64
@@ -42,10 +42,10 @@ def prep_sample(sample) -> int:
     (fir_1d_ref.py:40-41).
     """
     rounded = math.floor(sample + 0.5)
-    if rounded < PIXEL_LO:
-        return PIXEL_LO
-    if rounded > PIXEL_HI:
-        return PIXEL_HI
+    if rounded < lo:
+        return lo
+    if rounded > hi:
+        return hi
     return rounded
 
 
@@ -88,35 +88,37 @@ def post_accumulate(acc: int, frac_bits: int, acc_bits: int,
 # --------------------------------------------------------------------------
 def fir1d_fixed(x: Sequence, h: Sequence[float], frac_bits: int = 12,
                 acc_bits: int = 32, coeff_bits: int = 16, *,
-                dilation: int = 1) -> np.ndarray:
+                dilation: int = 1, centre: int | None = None,
+                in_range=(PIXEL_LO, PIXEL_HI), out_range=(PIXEL_LO, PIXEL_HI)) -> np.ndarray:
     """Same-mode, centre-aligned, zero-padded fixed-point FIR of one signal.
 
     y[n] = post( sum_k hq[k] * xs[n - (k - L//2) * dilation] ), xs = 0 outside
     [0, N)  (fir_1d_fixed_ref.py:83-107; dilation == 1 is the reference, other
     values are the interleaved-channel generalisation used for I/Q).
     """
-    xs = [prep_sample(s) for s in x]
+    xs = [prep_sample(s, *in_range) for s in x]
     hq = quantize_taps(h, frac_bits, coeff_bits)
     n_samples, n_taps = len(xs), len(hq)
-    centre = n_taps // 2
-    out = np.empty(n_samples, dtype=np.uint8)
+    centre = n_taps // 2 if centre is None else centre
+    out = np.empty(n_samples, dtype=np.uint8 if tuple(out_range) == (PIXEL_LO, PIXEL_HI) else np.int64)
     for n in range(n_samples):
         acc = 0
         for k in range(n_taps):
             src = n - (k - centre) * dilation
             if 0 <= src < n_samples:
                 acc += xs[src] * hq[k]
-        out[n] = post_accumulate(acc, frac_bits, acc_bits)
+        out[n] = post_accumulate(acc, frac_bits, acc_bits, *out_range)
     return out
 
 
-def fir1d_ideal(x: Sequence, h: Sequence[float], *, dilation: int = 1) -> list[float]:
+def fir1d_ideal(x: Sequence, h: Sequence[float], *, dilation: int = 1, centre: int | None = None,
+                raw: bool = False) -> list[float]:
     """float64 model: same indexing, taps visited in ascending k, one multiply
     then one add per visited tap, out-of-range taps skipped, no output clamp
     (fir_1d/model/python/fir_1d_ref.py:43-65)."""
-    xs = [prep_sample(s) for s in x]
+    xs = [float(s) for s in x] if raw else [prep_sample(s) for s in x]
     n_samples, n_taps = len(xs), len(h)
-    centre = n_taps // 2
+    centre = n_taps // 2 if centre is None else centre
     out = [0.0] * n_samples
     for n in range(n_samples):
         acc = 0.0

@@ -222,3 +222,67 @@ def test_fused_compare_rows_and_summary(tmp_path, images_small, manifest):
     assert summary["num_cases"] == 8 and summary["num_samples_total"] == 8 * 64 * 64
     assert summary["avg_rmse"] == pytest.approx(np.mean([w["rmse"] for w in want_rows]), rel=1e-11)
     assert summary["max_max_abs_err"] == max(w["max_abs_err"] for w in want_rows)
+
+
+# ---- extended entry points: causal / streaming (C++ Fir1D) and signed int16 ---------
+def test_fir1d_class_matches_reference_cpp_vectors():
+    """fir_1d.model.python.fir_1d_stream.Fir1D against vectors produced by the
+    reference's own C++ Fir1D (tests/golden/cpp_fir1d_cases.npz): bit-identical,
+    whole-signal, sample-by-sample and in ragged chunks."""
+    import torch
+    import firgpu
+    from conftest import GOLDEN
+    from fir_1d.model.python.fir_1d_stream import Fir1D
+    blob = np.load(GOLDEN / "cpp_fir1d_cases.npz")
+    rng = np.random.default_rng(0)
+    for i, name in enumerate(blob["names"]):
+        x, h = blob[f"{name}/x"], blob[f"{name}/h"]
+        assert np.array_equal(Fir1D.fir_1d_idel(x, h), blob[f"{name}/full"]), name
+        f = Fir1D(h)
+        assert f.taps() == h.tolist()
+        cuts = np.sort(rng.integers(0, x.size + 1, size=3))
+        chunks = np.split(x, cuts)
+        y = np.concatenate([f.process_block(c) for c in chunks])
+        assert np.array_equal(y, blob[f"{name}/stream"]), name
+        if i < 3:
+            f.reset()
+            assert [f.process_sample(v) for v in x[:20]] == blob[f"{name}/stream"][:20].tolist()
+        # device tensors, with the history exposed as real neighbour samples
+        if x.size > len(h):
+            xt = torch.from_numpy(x).cuda()
+            k = len(h) - 1
+            y_tail = firgpu.fir1d_ideal(xt[k:], h.tolist(), centre=0, raw=True, halo_left_valid=k)
+            assert np.array_equal(y_tail.cpu().numpy(), blob[f"{name}/stream"][k:]), name
+    assert Fir1D().process_sample(3.0) == 0.0 and Fir1D.fir_1d_idel([], [1.0]).size == 0
+
+
+def test_signed_int16_and_alignment_modes_against_oracle():
+    """in/out ranges and the tap alignment as parameters:
+    our specification, equal to the reference model at the defaults."""
+    import torch
+    import firgpu
+    from firgpu import _lib
+    rng = np.random.default_rng(12)
+    x = rng.integers(-32768, 32768, size=(3, 20_001)).astype(np.int16)
+    xt = torch.from_numpy(x).cuda()
+    h = [0.4, -0.3, 0.2, 0.1, -0.05]
+    full = (-32768, 32767)
+    for centre in (None, 0, 1, 4):
+        for in_r, out_r in ((full, full), ((0, 255), full), ((-100, 100), (-7, 300)), ((0, 255), (0, 255))):
+            for frac, acc in ((12, 32), (15, 48), (12, 24)):
+                want = onp.fir1d_fixed(x, h, frac, acc, 16, centre=centre, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                got = firgpu.fir1d_fixed(xt, h, frac, acc, 16, centre=centre, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                assert np.array_equal(got.cpu().numpy(), want), (centre, in_r, out_r, frac, acc)
+                host = firgpu.fir1d_fixed(x, h, frac, acc, 16, centre=centre, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                assert np.array_equal(host, want), (centre, in_r, out_r, frac, acc, "host")
+    # defaults through the _ex entry point are the reference model on the fast kernel
+    y = firgpu.fir1d_fixed(xt, h, 12, 32, 16, centre=2, in_range=(0, 255), out_range=(0, 255))
+    assert _lib.last_path() == _lib.PATH_STAGED and np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h))
+    assert firgpu.fir1d_fixed(xt, h, in_range=full, out_range=full).dtype == torch.int16
+    # ideal model with alignment / clamp range
+    for centre in (0, 3):
+        want = onp.fir1d_ideal(x, h, centre=centre, in_range=(-50, 900))
+        assert np.array_equal(firgpu.fir1d_ideal(xt, h, centre=centre, in_range=(-50, 900)).cpu().numpy(), want)
+        assert np.array_equal(firgpu.fir1d_ideal(x, h, centre=centre, in_range=(-50, 900)), want)
+    with pytest.raises(firgpu._lib.FirGpuError):
+        firgpu.fir1d_fixed(xt, h, centre=5)

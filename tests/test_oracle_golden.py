@@ -155,3 +155,33 @@ def test_numpy_and_c_oracle_fuzz_against_scalar(acc_bits):
             assert np.array_equal(onp.fir1d_fixed(x, h, fb, acc_bits, cb, dilation=dil), want)
             hq = onp.quantize_taps(h, fb, cb)
             assert np.array_equal(c_oracle.fir1d_fixed(x, hq, fb, acc_bits, dilation=dil), want)
+
+
+def test_causal_raw_model_matches_reference_cpp_vectors():
+    """tests/golden/cpp_fir1d_cases.npz = Fir1D::fir_1d_idel / process_sample of
+    the reference's own C++ (compiled by oracle/Makefile, make_golden_cpp.py):
+    the oracle's causal raw-sample model must be bit-identical."""
+    from conftest import GOLDEN
+    blob = np.load(GOLDEN / "cpp_fir1d_cases.npz")
+    assert len(blob["names"]) == 61
+    assert np.allclose(blob["pdf_p13/full"], [1 / 3, 1, 2, 3, 4, 3, 5 / 3])      # course PDF p.13 example
+    for name in blob["names"]:
+        x, h = blob[f"{name}/x"], blob[f"{name}/h"].tolist()
+        assert np.array_equal(onp.fir1d_full_causal(x, h), blob[f"{name}/full"]), name
+        assert np.array_equal(onp.fir1d_ideal(x, h, centre=0, raw=True), blob[f"{name}/stream"]), name
+        assert np.array_equal(np.array(opy.fir1d_ideal(x.tolist(), h, centre=0, raw=True)), blob[f"{name}/stream"]), name
+
+
+def test_parametrised_oracle_reduces_to_reference_at_defaults(golden_cases):
+    for c in golden_cases[:80]:
+        y = onp.fir1d_fixed(c["x"], c["h"], c["frac_bits"], c["acc_bits"], c["coeff_bits"], centre=len(c["h"]) // 2,
+                            in_range=(0, 255), out_range=(0, 255))
+        assert np.array_equal(y, c["y_fixed"]), c["name"]
+    rng = np.random.default_rng(1)
+    x = rng.integers(-40000, 40000, size=300)
+    h = [0.4, -0.3, 0.2, 0.1]
+    for centre in range(4):
+        for rng_in, rng_out in (((0, 255), (0, 255)), ((-32768, 32767), (-32768, 32767)), ((-100, 100), (-5, 300))):
+            a = opy.fir1d_fixed(x.tolist(), h, 12, 32, 16, centre=centre, in_range=rng_in, out_range=rng_out)
+            b = onp.fir1d_fixed(x, h, 12, 32, 16, centre=centre, in_range=rng_in, out_range=rng_out, out_dtype=np.int64)
+            assert np.array_equal(np.asarray(a, dtype=np.int64), b), (centre, rng_in, rng_out)

@@ -681,6 +681,109 @@ int firgpu_fir1d_compare_host(const void *x, int in_dtype, int64_t rows, int64_t
     return rc;
 }
 
+// ---- extended entry points: alignment, clamp / saturation bounds, raw samples ----
+namespace {
+int check_ex(const char *fn, int n_taps, int centre, int in_lo, int in_hi, int out_lo, int out_hi)
+{
+    if (centre < 0 || centre >= n_taps) return set_error(FIRGPU_E_TAPS, "%s: centre=%d outside [0,%d)", fn, centre, n_taps);
+    if (in_lo > in_hi || out_lo > out_hi) return set_error(FIRGPU_E_BITS, "%s: empty clamp range", fn);
+    if (in_lo < -32768 || in_hi > 32767) return set_error(FIRGPU_E_BITS, "%s: sample range must fit int16", fn);
+    return 0;
+}
+}  // namespace
+
+int firgpu_fir1d_fixed_ex(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                          int64_t ld_y, const int32_t *hq, int n_taps, int dilation, int frac_bits, int acc_bits,
+                          int64_t halo_left_valid, int64_t halo_right_valid, int centre, int in_lo, int in_hi, int out_lo,
+                          int out_hi, void *stream)
+{
+    int rc = check_1d("firgpu_fir1d_fixed_ex", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation,
+                      halo_left_valid, halo_right_valid);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed_ex", frac_bits, acc_bits))) return rc;
+    if ((rc = check_ex("firgpu_fir1d_fixed_ex", n_taps, centre, in_lo, in_hi, out_lo, out_hi))) return rc;
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_ex: out_dtype must be U8 or I16, got %d", out_dtype);
+    if ((out_dtype == FIRGPU_U8 && (out_lo < 0 || out_hi > 255)) || out_lo < -32768 || out_hi > 32767)
+        return set_error(FIRGPU_E_BITS, "firgpu_fir1d_fixed_ex: output range [%d,%d] does not fit the output container", out_lo, out_hi);
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, frac_bits, acc_bits,
+                halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    a.centre = centre;
+    a.in_lo = in_lo;
+    a.in_hi = in_hi;
+    a.out_lo = out_lo;
+    a.out_hi = out_hi;
+    if (a.is_reference_model()) {           // the reference's own parameters: the fast kernels apply
+        rc = try_launch_fir1d_fixed_staged(a, hq);
+        if (rc == 1) return 0;
+        if (rc != 0) return rc;
+    }
+    return launch_fir1d_fixed_generic(a, hq);
+}
+
+int firgpu_fir1d_ideal_ex(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                          int64_t ld_y, const double *h, int n_taps, int dilation, int64_t halo_left_valid,
+                          int64_t halo_right_valid, int centre, int in_lo, int in_hi, int raw, void *stream)
+{
+    int rc = check_1d("firgpu_fir1d_ideal_ex", x, y, in_dtype, rows, cols, ld_x, ld_y, h, n_taps, dilation, halo_left_valid,
+                      halo_right_valid);
+    if (rc) return rc;
+    if ((rc = check_ex("firgpu_fir1d_ideal_ex", n_taps, centre, in_lo, in_hi, 0, 0))) return rc;
+    if (!out_size_ideal(out_dtype)) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_ideal_ex: out_dtype must be F64 or F32, got %d", out_dtype);
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, 0, 0,
+                halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    a.centre = centre;
+    a.in_lo = in_lo;
+    a.in_hi = in_hi;
+    a.raw = raw ? 1 : 0;
+    return launch_fir1d_ideal(a, h);
+}
+
+int firgpu_fir1d_fixed_ex_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols,
+                               int64_t ld_x, int64_t ld_y, const int32_t *hq, int n_taps, int dilation, int frac_bits,
+                               int acc_bits, int centre, int in_lo, int in_hi, int out_lo, int out_hi, int device)
+{
+    int rc = check_1d("firgpu_fir1d_fixed_ex_host", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_ex("firgpu_fir1d_fixed_ex_host", n_taps, centre, in_lo, in_hi, out_lo, out_hi))) return rc;
+    const int os = out_size_fixed(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_ex_host: out_dtype must be U8 or I16, got %d", out_dtype);
+    return pipeline_1d(x, y, dtype_size(in_dtype), os, rows, cols, ld_x, ld_y, (n_taps - 1 - centre) * (int64_t)dilation,
+                       centre * (int64_t)dilation, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before,
+                           int64_t after, cudaStream_t s) {
+                           return firgpu_fir1d_fixed_ex(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, hq, n_taps, dilation,
+                                                        frac_bits, acc_bits, before, after, centre, in_lo, in_hi, out_lo,
+                                                        out_hi, (void *)s);
+                       });
+}
+
+int firgpu_fir1d_ideal_ex_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols,
+                               int64_t ld_x, int64_t ld_y, const double *h, int n_taps, int dilation, int centre,
+                               int in_lo, int in_hi, int raw, int device)
+{
+    int rc = check_1d("firgpu_fir1d_ideal_ex_host", x, y, in_dtype, rows, cols, ld_x, ld_y, h, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_ex("firgpu_fir1d_ideal_ex_host", n_taps, centre, in_lo, in_hi, 0, 0))) return rc;
+    const int os = out_size_ideal(out_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_ideal_ex_host: out_dtype must be F64 or F32, got %d", out_dtype);
+    return pipeline_1d(x, y, dtype_size(in_dtype), os, rows, cols, ld_x, ld_y, (n_taps - 1 - centre) * (int64_t)dilation,
+                       centre * (int64_t)dilation, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before,
+                           int64_t after, cudaStream_t s) {
+                           return firgpu_fir1d_ideal_ex(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, h, n_taps, dilation,
+                                                        before, after, centre, in_lo, in_hi, raw, (void *)s);
+                       });
+}
+
 int firgpu_pinned_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) return set_error(FIRGPU_E_NULL, "firgpu_pinned_alloc: NULL");

@@ -65,10 +65,23 @@ __device__ __forceinline__ int prep_sample(double v)
 }
 __device__ __forceinline__ int prep_sample(float v) { return prep_sample((double)v); }
 
+// Parametrised forms (extended entry points): sample clamp range [lo, hi] and
+// a raw mode for the floating-point model; (0, 255) reproduces the reference.
+__device__ __forceinline__ int prep_sample_range(uint8_t v, int lo, int hi) { return min(max((int)v, lo), hi); }
+__device__ __forceinline__ int prep_sample_range(int16_t v, int lo, int hi) { return min(max((int)v, lo), hi); }
+__device__ __forceinline__ int prep_sample_range(int32_t v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int prep_sample_range(double v, int lo, int hi)
+{
+    double r = floor(__dadd_rn(v, 0.5));
+    r = fmin(fmax(r, (double)lo), (double)hi);
+    return (int)r;
+}
+__device__ __forceinline__ int prep_sample_range(float v, int lo, int hi) { return prep_sample_range((double)v, lo, hi); }
+
 // wrap -> bias -> shift -> saturate on a 64-bit accumulator.  |acc| < 2^50 for
 // every supported tap count, so int64 itself never overflows and the only
 // wrap is the explicit one the reference performs.
-__device__ __forceinline__ int post_accumulate(long long acc, int frac_bits, int acc_bits)
+__device__ __forceinline__ int post_accumulate(long long acc, int frac_bits, int acc_bits, int out_lo = 0, int out_hi = kPixelMax)
 {
     if (acc_bits < 64) {
         unsigned long long m = (unsigned long long)acc & ((1ULL << acc_bits) - 1ULL);
@@ -82,7 +95,7 @@ __device__ __forceinline__ int post_accumulate(long long acc, int frac_bits, int
         acc += 1LL << (frac_bits - 1);
         v = acc >> frac_bits;
     }
-    return (int)(v < 0 ? 0 : (v > kPixelMax ? kPixelMax : v));
+    return (int)(v < out_lo ? out_lo : (v > out_hi ? out_hi : v));
 }
 
 template <typename T> struct DtypeOf;
@@ -101,6 +114,15 @@ struct Fir1dArgs {
     int n_taps, dilation, frac_bits, acc_bits;
     int64_t halo_left, halo_right;
     cudaStream_t stream;
+    // extended entry points (defaults = the reference model)
+    int centre = -1;                 // taps ahead of the output position; -1 = n_taps / 2
+    int in_lo = 0, in_hi = 255;      // sample clamp range
+    int out_lo = 0, out_hi = 255;    // output saturation range
+    int raw = 0;                     // ideal model only: use samples as they are (no round / clamp)
+    bool is_reference_model() const
+    {
+        return (centre < 0 || centre == n_taps / 2) && in_lo == 0 && in_hi == 255 && out_lo == 0 && out_hi == 255 && !raw;
+    }
 };
 
 struct Fir2dArgs {

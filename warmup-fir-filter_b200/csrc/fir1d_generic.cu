@@ -21,9 +21,8 @@ fir1d_fixed_generic_kernel(const InT *__restrict__ x, OutT *__restrict__ y,
                            int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                            InlineTaps inline_taps, const int32_t *__restrict__ long_taps,
                            int n_taps, int dilation, int frac_bits, int acc_bits,
-                           int64_t halo_left, int64_t halo_right)
+                           int64_t halo_left, int64_t halo_right, int centre, int in_lo, int in_hi, int out_lo, int out_hi)
 {
-    const int centre = n_taps / 2;
     const int64_t lo = -halo_left, hi = cols + halo_right;   // readable index range of a row
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
         const InT *xr = x + r * ld_x;
@@ -35,10 +34,10 @@ fir1d_fixed_generic_kernel(const InT *__restrict__ x, OutT *__restrict__ y,
                 const int64_t src = n - (int64_t)(k - centre) * dilation;
                 if (src >= lo && src < hi) {
                     const int32_t tap = long_taps ? long_taps[k] : inline_taps.v[k];
-                    acc += (long long)prep_sample(xr[src]) * (long long)tap;
+                    acc += (long long)prep_sample_range(xr[src], in_lo, in_hi) * (long long)tap;
                 }
             }
-            yr[n] = (OutT)post_accumulate(acc, frac_bits, acc_bits);
+            yr[n] = (OutT)post_accumulate(acc, frac_bits, acc_bits, out_lo, out_hi);
         }
     }
 }
@@ -49,9 +48,8 @@ __global__ void __launch_bounds__(kBlock)
 fir1d_ideal_kernel(const InT *__restrict__ x, OutT *__restrict__ y,
                    int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                    InlineTapsF64 inline_taps, const double *__restrict__ long_taps,
-                   int n_taps, int dilation, int64_t halo_left, int64_t halo_right)
+                   int n_taps, int dilation, int64_t halo_left, int64_t halo_right, int centre, int in_lo, int in_hi, int raw)
 {
-    const int centre = n_taps / 2;
     const int64_t lo = -halo_left, hi = cols + halo_right;
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
         const InT *xr = x + r * ld_x;
@@ -63,9 +61,10 @@ fir1d_ideal_kernel(const InT *__restrict__ x, OutT *__restrict__ y,
                 const int64_t src = n - (int64_t)(k - centre) * dilation;
                 if (src >= lo && src < hi) {
                     const double tap = long_taps ? long_taps[k] : inline_taps.v[k];
-                    const int s = prep_sample(xr[src]);
+                    // raw: the C++ Fir1D model filters the samples as given (fir_1d/model/cpp/fir_1d_ref.cpp:37-63)
+                    const double s = raw ? (double)xr[src] : (double)prep_sample_range(xr[src], in_lo, in_hi);
                     if constexpr (sizeof(OutT) == 8) {
-                        acc = __dadd_rn(acc, __dmul_rn(tap, (double)s));
+                        acc = __dadd_rn(acc, __dmul_rn(tap, s));
                     } else {
                         acc = fmaf((float)tap, (float)s, acc);
                     }
@@ -101,7 +100,8 @@ int run_fixed(const Fir1dArgs &a, const int32_t *hq_host)
     }
     fir1d_fixed_generic_kernel<InT, OutT><<<grid_for(a.rows, a.cols), kBlock, 0, a.stream>>>(
         (const InT *)a.x, (OutT *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, it, dev_taps, a.n_taps,
-        a.dilation, a.frac_bits, a.acc_bits, a.halo_left, a.halo_right);
+        a.dilation, a.frac_bits, a.acc_bits, a.halo_left, a.halo_right, a.centre < 0 ? a.n_taps / 2 : a.centre, a.in_lo, a.in_hi,
+        a.out_lo, a.out_hi);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_GENERIC);
     if (dev_taps) FIRGPU_CUDA(cudaFreeAsync(dev_taps, a.stream));
@@ -121,7 +121,7 @@ int run_ideal(const Fir1dArgs &a, const double *h_host)
     }
     fir1d_ideal_kernel<InT, OutT><<<grid_for(a.rows, a.cols), kBlock, 0, a.stream>>>(
         (const InT *)a.x, (OutT *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, it, dev_taps, a.n_taps,
-        a.dilation, a.halo_left, a.halo_right);
+        a.dilation, a.halo_left, a.halo_right, a.centre < 0 ? a.n_taps / 2 : a.centre, a.in_lo, a.in_hi, a.raw);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_GENERIC);
     if (dev_taps) FIRGPU_CUDA(cudaFreeAsync(dev_taps, a.stream));

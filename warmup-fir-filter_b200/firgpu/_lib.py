@@ -30,6 +30,10 @@ SIGNATURES = {
     "firgpu_fir1d_fixed": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _vp]),
     "firgpu_fir1d_fixed_multi": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci, _vp]),
     "firgpu_fir1d_ideal": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _i64, _i64, _vp]),
+    "firgpu_fir1d_fixed_ex": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _ci, _ci, _ci, _ci, _ci, _vp]),
+    "firgpu_fir1d_ideal_ex": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _i64, _i64, _ci, _ci, _ci, _ci, _vp]),
+    "firgpu_fir1d_fixed_ex_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci]),
+    "firgpu_fir1d_ideal_ex_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci]),
     "firgpu_fir1d_compare": (_ci, [_vp, _ci, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _vp, _vp]),
     "firgpu_fir1d_compare_host": (_ci, [_vp, _ci, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _vp, _ci]),
     "firgpu_fir2d_fixed": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _i64, _i64, _vp]),

@@ -44,10 +44,11 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
-def _np_container(x) -> np.ndarray:
+def _np_container(x, lo: int = 0, hi: int = 255) -> np.ndarray:
     """Any host input -> C-contiguous array in one of the five containers the
-    kernels read.  Integer types the kernels do not read are clamped here
-    (rounding is the identity on integers, fir_1d_ref.py:35-41)."""
+    kernels read.  Integer types the kernels do not read are clamped here to
+    the sample range [lo, hi] (rounding is the identity on integers,
+    fir_1d_ref.py:35-41)."""
     a = np.asarray(x)
     if a.dtype == object:
         a = np.asarray(x, dtype=np.float64)
@@ -58,7 +59,7 @@ def _np_container(x) -> np.ndarray:
     elif a.dtype == np.int8:
         a = a.astype(np.int16)
     elif a.dtype.kind in "iu":
-        a = np.clip(a, 0, 255).astype(np.uint8)
+        a = np.clip(a, lo, hi).astype(np.uint8 if (lo >= 0 and hi <= 255) else np.int16)
     elif a.dtype.kind == "f":
         a = a.astype(np.float32 if a.dtype.itemsize < 4 else np.float64)
     else:
@@ -152,8 +153,9 @@ def _taps_ptr(arr: np.ndarray):
 # 1-D
 # ---------------------------------------------------------------------------
 def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *,
-                dilation: int = 1, out_dtype=np.uint8, out=None, device: int = -1,
-                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True):
+                dilation: int = 1, out_dtype=None, out=None, device: int = -1,
+                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True,
+                centre=None, in_range=(0, 255), out_range=(0, 255)):
     """Bit-true fixed-point FIR (fir_1d/model/python/fir_1d_fixed_ref.py:12-130)
     along the last axis of ``x``.
 
@@ -162,25 +164,38 @@ def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int =
     read instead of assuming zeros (device inputs only: a shard of a longer
     signal).  Returns uint8 (or ``out_dtype=np.int16``: same values in an int16
     container) of the same shape, on the same side (host / device) as ``x``.
+
+    ``centre`` (taps ahead of the output; default ``len(h) // 2``), ``in_range``
+    and ``out_range`` turn the reference's fixed choices into parameters (the
+    extended C entry points): ``centre=0`` is the causal alignment,
+    ``in_range = out_range = (-32768, 32767)`` the signed int16 path.  The
+    defaults ARE the reference model.
     """
     quant.validate_taps(h)
+    in_range, out_range = (int(in_range[0]), int(in_range[1])), (int(out_range[0]), int(out_range[1]))
+    if out_dtype is None:
+        out_dtype = np.uint8 if (out_range[0] >= 0 and out_range[1] <= 255) else np.int16
     if _is_torch(x):
         if validate:
             _check_finite_torch(x)
     elif not isinstance(x, DeviceArray):
-        x = _np_container(x)
+        x = _np_container(x, *in_range)
         if validate:
             quant.check_samples_finite(x)
     quant.check_bits(frac_bits, acc_bits, coeff_bits)
     hq = quant.quantize_taps(h, frac_bits, coeff_bits)
+    ex = None
+    if (centre is not None and centre != len(hq) // 2) or in_range != (0, 255) or out_range != (0, 255):
+        ex = (len(hq) // 2 if centre is None else int(centre),) + in_range + out_range
     return fir1d_fixed_q(x, hq, frac_bits, acc_bits, dilation=dilation, out_dtype=out_dtype, out=out,
-                         device=device, halo_left_valid=halo_left_valid, halo_right_valid=halo_right_valid)
+                         device=device, halo_left_valid=halo_left_valid, halo_right_valid=halo_right_valid, ex=ex)
 
 
 def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, out_dtype=np.uint8, out=None,
-                  device: int = -1, halo_left_valid: int = 0, halo_right_valid: int = 0):
+                  device: int = -1, halo_left_valid: int = 0, halo_right_valid: int = 0, ex=None):
     """Same as :func:`fir1d_fixed` with already-quantised integer taps and no
-    sample validation: the thin layer over ``firgpu_fir1d_fixed[_host]``."""
+    sample validation: the thin layer over ``firgpu_fir1d_fixed[_host]``
+    (``ex = (centre, in_lo, in_hi, out_lo, out_hi)`` selects the ``_ex`` forms)."""
     L = _lib.lib()
     hq = np.ascontiguousarray(hq, dtype=np.int32).reshape(-1)
     out_code = _OUT_FIXED[np.dtype(out_dtype)]
@@ -201,19 +216,29 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(L.firgpu_fir1d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
-                                            rows, cols, ld, ld_y, _taps_ptr(hq), hq.size, dilation, frac_bits,
-                                            acc_bits, halo_left_valid, halo_right_valid, stream))
+            if ex is None:
+                _lib.check(L.firgpu_fir1d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
+                                                rows, cols, ld, ld_y, _taps_ptr(hq), hq.size, dilation, frac_bits,
+                                                acc_bits, halo_left_valid, halo_right_valid, stream))
+            else:
+                _lib.check(L.firgpu_fir1d_fixed_ex(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
+                                                   rows, cols, ld, ld_y, _taps_ptr(hq), hq.size, dilation, frac_bits,
+                                                   acc_bits, halo_left_valid, halo_right_valid, *ex, stream))
         return y
     if halo_left_valid or halo_right_valid:
         raise ValueError("halo_*_valid apply to device-resident shards only")
     was_torch = _is_torch(x)
-    a = _np_container(x.numpy() if was_torch else x)
+    a = _np_container(x.numpy() if was_torch else x, *((ex[1], ex[2]) if ex else (0, 255)))
     rows, cols = _rows_cols(a.shape)
     y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
     y_np = y.numpy() if _is_torch(y) else y
-    _lib.check(L.firgpu_fir1d_fixed_host(a.ctypes.data, y_np.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
-                                         cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, device))
+    if ex is None:
+        _lib.check(L.firgpu_fir1d_fixed_host(a.ctypes.data, y_np.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
+                                             cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, device))
+    else:
+        _lib.check(L.firgpu_fir1d_fixed_ex_host(a.ctypes.data, y_np.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
+                                                cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, *ex,
+                                                device))
     if was_torch and out is None:
         import torch
         return torch.from_numpy(y)
@@ -221,15 +246,22 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
 
 
 def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, device: int = -1,
-                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True):
+                halo_left_valid: int = 0, halo_right_valid: int = 0, validate: bool = True,
+                centre=None, raw: bool = False, in_range=(0, 255)):
     """Ideal floating-point FIR (fir_1d/model/python/fir_1d_ref.py:43-65) along
     the last axis.  ``out_dtype=np.float64`` is bit-identical to the reference
     (unfused multiply and add, taps in ascending order); ``np.float32`` runs a
-    float32 datapath (|err| <= 1e-6 * 255 * sum|h|)."""
+    float32 datapath (|err| <= 1e-6 * 255 * sum|h|).  ``centre=0`` is the
+    causal alignment and ``raw=True`` filters the samples as given (no round /
+    clamp): together the C++ ``Fir1D`` model (fir_1d/model/cpp/fir_1d_ref.cpp)."""
     quant.validate_taps(h)
     L = _lib.lib()
     hh = np.ascontiguousarray([float(v) for v in h], dtype=np.float64)
     out_code = _OUT_IDEAL[np.dtype(out_dtype)]
+    in_range = (int(in_range[0]), int(in_range[1]))
+    ex = None
+    if (centre is not None and centre != hh.size // 2) or raw or in_range != (0, 255):
+        ex = (hh.size // 2 if centre is None else int(centre),) + in_range + (1 if raw else 0,)
     if _is_torch(x) and x.is_cuda:
         import torch
         if validate:
@@ -238,19 +270,28 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
         y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
-                                            _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid, stream))
+            if ex is None:
+                _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
+                                                _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid, stream))
+            else:
+                _lib.check(L.firgpu_fir1d_ideal_ex(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
+                                                   _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid,
+                                                   *ex, stream))
         return y
     if halo_left_valid or halo_right_valid:
         raise ValueError("halo_*_valid apply to device-resident shards only")
     was_torch = _is_torch(x)
-    a = _np_container(x.numpy() if was_torch else x)
+    a = _np_container(x.numpy() if was_torch else x, *in_range)
     if validate:
         quant.check_samples_finite(a)
     rows, cols = _rows_cols(a.shape)
     y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
-    _lib.check(L.firgpu_fir1d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols, cols,
-                                         cols, _taps_ptr(hh), hh.size, dilation, device))
+    if ex is None:
+        _lib.check(L.firgpu_fir1d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols, cols,
+                                             cols, _taps_ptr(hh), hh.size, dilation, device))
+    else:
+        _lib.check(L.firgpu_fir1d_ideal_ex_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols, cols,
+                                                cols, _taps_ptr(hh), hh.size, dilation, *ex, device))
     if was_torch and out is None:
         import torch
         return torch.from_numpy(y)
