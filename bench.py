@@ -233,7 +233,8 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL logs (its version banner included) go to stdout by default: stdout carries ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():

@@ -286,3 +286,31 @@ def test_signed_int16_and_alignment_modes_against_oracle():
         assert np.array_equal(firgpu.fir1d_ideal(x, h, centre=centre, in_range=(-50, 900)), want)
     with pytest.raises(firgpu._lib.FirGpuError):
         firgpu.fir1d_fixed(xt, h, centre=5)
+
+
+def test_ideal_fast_kernel_bit_identical():
+    """fir1d_ideal_fast_kernel (uint8 / int16 -> float64): every tap count,
+    ragged lengths, several rows, shard halos — bit-identical to the oracle
+    (and therefore to the reference's float64 model)."""
+    import torch
+    import firgpu
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(31)
+    for dtype in (np.uint8, np.int16):
+        for n_taps in range(1, 10):
+            h = rng.uniform(-8, 8, size=n_taps).tolist()
+            for shape in ((1, 1), (1, 7), (3, 2048), (2, 2050), (5, 4098), (1, 100_003)):
+                x = rng.integers(0, 256, size=shape).astype(dtype)
+                if dtype == np.int16:
+                    x[rng.random(shape) < 0.05] = -999
+                    x[rng.random(shape) < 0.05] = 12345
+                got = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h)
+                assert _lib.last_path() == _lib.PATH_STAGED, (dtype, n_taps, shape)
+                assert np.array_equal(got.cpu().numpy(), onp.fir1d_ideal(x, h)), (dtype, n_taps, shape)
+    x = rng.integers(-300, 600, size=50_000).astype(np.int16)
+    h = [0.1, -0.2, 0.3, 0.4, 0.05]
+    want = onp.fir1d_ideal(x, h)
+    for p in shard.plan_segments(x.size, 3, 5, 1, align=64):
+        buf, body = shard.scatter_segment(x, p, "cuda")
+        y = firgpu.fir1d_ideal(body, h, halo_left_valid=p.before, halo_right_valid=p.after)
+        assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])

@@ -67,9 +67,9 @@ int main(int argc, char **argv)
             float ms;
             cudaEventElapsedTime(&ms, e0, e1);
             ms /= reps;
-            printf("{\"case\": \"%s\", \"threads\": %d, \"stages\": %d, \"rps5\": %d, \"rps3\": %d, \"minblocks\": %d, \"ctas_per_sm_cap\": %d, "
+            printf("{\"case\": \"%s\", \"threads\": %d, \"stages\": %d, \"rps5\": %d, \"rps3\": %d, \"minblocks\": %d, \"warpspec\": %d, \"ctas_per_sm_cap\": %d, "
                    "\"rc\": %d, \"ms\": %.4f, \"gb_s\": %.1f, \"err\": \"%s\"}\n",
-                   c.name, FIRGPU_T2_THREADS, FIRGPU_T2_STAGES, FIRGPU_T2_RPS5, FIRGPU_T2_RPS3, FIRGPU_T2_MINBLOCKS, ctas, rc, ms,
+                   c.name, FIRGPU_T2_THREADS, FIRGPU_T2_STAGES, FIRGPU_T2_RPS5, FIRGPU_T2_RPS3, FIRGPU_T2_MINBLOCKS, FIRGPU_T2_WARPSPEC, ctas, rc, ms,
                    n * n * 4.0 / (ms * 1e-3) / 1e9, cudaGetErrorString(err));
             fflush(stdout);
         }

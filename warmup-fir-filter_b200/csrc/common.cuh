@@ -138,6 +138,8 @@ struct Fir2dArgs {
 // fir1d_generic.cu
 int launch_fir1d_fixed_generic(const Fir1dArgs &a, const int32_t *hq_host);
 int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host);
+// fir1d_ideal_fast.cu — 1 = served, 0 = not eligible
+int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
 // taps are outside the staged kernel's domain (caller falls to generic), <0 / >0 on error.
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);

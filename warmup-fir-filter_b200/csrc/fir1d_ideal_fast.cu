@@ -1,0 +1,132 @@
+// Fast path of the ideal (floating-point) 1-D model for uint8 / int16 inputs and
+// float64 output: fir_1d/model/python/fir_1d_ref.py:43-65, batched as
+// fir_1d/sim/vector/gen_ideal_output.py:37-50.
+//
+// Bound: HBM, 9-10 bytes per sample (1-2 in, 8 out) — the output dominates.
+// A CTA converts one tile of samples to float64 ONCE into shared memory
+// (round/clamp is the identity on integers, so conversion = clamp + cast),
+// then every thread produces pairs of adjacent outputs from 128-bit shared
+// loads and writes them with one 16-byte store, so a warp writes 512
+// contiguous bytes.  Arithmetic is the reference's: taps in ascending k,
+// __dmul_rn then __dadd_rn (no FMA contraction), accumulator starting at +0.0
+// — bit-identical to the Python model.  Zero padding outside the row is
+// stored as +0.0 samples, which adds +-0.0 to a +0.0-started sum and never
+// changes it (same argument as oracle/fir_oracle_np.py::fir1d_ideal).
+#include "common.cuh"
+
+#include <cstdlib>
+
+namespace firgpu {
+namespace {
+
+constexpr int kThreadsI = 256;
+constexpr int kPairs = 4;                               // output pairs per thread
+constexpr int kTileI = kThreadsI * 2 * kPairs;          // 2048 outputs per CTA
+constexpr int kMaxFastIdealTaps = 9;
+
+template <int L> struct TapsF64 {
+    double v[L];
+};
+
+template <typename InT, int L>
+__global__ void __launch_bounds__(kThreadsI)
+fir1d_ideal_fast_kernel(const InT *__restrict__ x, double *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
+                        int64_t ld_y, int64_t tiles_per_row, TapsF64<L> h, int64_t halo_left, int64_t halo_right)
+{
+    constexpr int hi = L / 2, lo = L - 1 - hi;
+    constexpr int LEAD = lo + (lo & 1);                  // even, so that window starts stay 16-byte aligned
+    constexpr int WIN = (LEAD + 2 + hi + 1) / 2 * 2;     // doubles read per output pair
+    constexpr int SPAN = kTileI + LEAD + ((hi + 1) / 2) * 2;
+    __shared__ __align__(16) double xs[SPAN];
+
+    const int64_t tile = blockIdx.x;
+    const int64_t row = tile / tiles_per_row;
+    const int64_t col0 = (tile - row * tiles_per_row) * kTileI;
+    const InT *xr = x + row * ld_x;
+    const int64_t vlo = -halo_left, vhi = cols + halo_right;
+
+    // samples [col0 - LEAD, col0 - LEAD + SPAN) -> float64 in shared memory
+    for (int i = threadIdx.x; i < SPAN; i += kThreadsI) {
+        const int64_t g = col0 - LEAD + i;
+        xs[i] = (g >= vlo && g < vhi) ? (double)prep_sample(xr[g]) : 0.0;
+    }
+    __syncthreads();
+
+    double *yr = y + row * ld_y;
+    const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & 15) == 0);
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+        const int o = j * (2 * kThreadsI) + 2 * threadIdx.x;      // first output of the pair, inside the tile
+        const int64_t n = col0 + o;
+        if (n >= cols) break;
+        double w[WIN];
+#pragma unroll
+        for (int q = 0; q < WIN; q += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(&xs[o + q]);
+            w[q] = v.x;
+            w[q + 1] = v.y;
+        }
+        // output n reads samples n + hi ... n - lo  <->  w[LEAD + hi - k], k = 0..L-1
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
+            a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
+        }
+        if (n + 1 < cols && y_vec) {
+            *reinterpret_cast<double2 *>(yr + n) = make_double2(a0, a1);
+        } else {
+            yr[n] = a0;
+            if (n + 1 < cols) yr[n + 1] = a1;
+        }
+    }
+}
+
+template <typename InT, int L>
+int run(const Fir1dArgs &a, const double *h_host)
+{
+    TapsF64<L> h;
+    for (int k = 0; k < L; ++k) h.v[k] = h_host[k];
+    const int64_t tiles_per_row = (a.cols + kTileI - 1) / kTileI;
+    const int64_t total = tiles_per_row * a.rows;
+    if (total > 0x7fffffffLL) return 0;
+    fir1d_ideal_fast_kernel<InT, L><<<(unsigned)total, kThreadsI, 0, a.stream>>>(
+        (const InT *)a.x, (double *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, h, a.halo_left, a.halo_right);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 1;
+}
+
+template <typename InT>
+int by_taps(const Fir1dArgs &a, const double *h)
+{
+    switch (a.n_taps) {
+    case 1: return run<InT, 1>(a, h);
+    case 2: return run<InT, 2>(a, h);
+    case 3: return run<InT, 3>(a, h);
+    case 4: return run<InT, 4>(a, h);
+    case 5: return run<InT, 5>(a, h);
+    case 6: return run<InT, 6>(a, h);
+    case 7: return run<InT, 7>(a, h);
+    case 8: return run<InT, 8>(a, h);
+    case 9: return run<InT, 9>(a, h);
+    default: return 0;
+    }
+}
+
+}  // namespace
+
+// 1 = served, 0 = not eligible (caller uses the generic kernel), else error.
+int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
+{
+    if (a.out_dtype != FIRGPU_F64 || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
+    if (!a.is_reference_model()) return 0;
+    if ((a.ld_y & 1) && a.rows > 1) return 0;            // keeps every row's pair stores 16-byte aligned or uniformly scalar
+    const char *force = getenv("FIRGPU_FORCE_GENERIC");
+    if (force && force[0] == '1') return 0;
+    if (a.in_dtype == FIRGPU_U8) return by_taps<uint8_t>(a, h_host);
+    if (a.in_dtype == FIRGPU_I16) return by_taps<int16_t>(a, h_host);
+    return 0;
+}
+
+}  // namespace firgpu

@@ -55,8 +55,12 @@ using staged::store_v4;
 #ifndef FIRGPU_T2_MINBLOCKS
 #define FIRGPU_T2_MINBLOCKS 3
 #endif
+#ifndef FIRGPU_T2_WARPSPEC
+#define FIRGPU_T2_WARPSPEC 1      // 1: dedicated TMA producer warp + per-stage empty barriers; 0: __syncthreads per stage
+#endif
 constexpr int kThreads2 = FIRGPU_T2_THREADS;
 constexpr int kStages2 = FIRGPU_T2_STAGES;
+constexpr int kBlock2 = kThreads2 + (FIRGPU_T2_WARPSPEC ? 32 : 0);   // consumer threads (+ one producer warp)
 constexpr int kBandTarget = 64;                  // output rows per band, about
 inline constexpr int rows_per_stage(int kh) { return kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
 constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
@@ -89,7 +93,7 @@ template <typename T, int KH, int KW> struct Geo2 {
     static constexpr int PADS = 16 / ES;         // columns of pad staged on each side
     static constexpr int OUTW = kStripBytes / ES - 2 * PADS;    // output columns per strip
     static constexpr int ACTIVE = OUTW / G1::SC; // threads that own output columns
-    static constexpr int SMEM = kStages2 * STAGE + kStages2 * 8;
+    static constexpr int SMEM = kStages2 * STAGE + 2 * kStages2 * 8;
     static constexpr int UP = KH - 1 - KH / 2;   // input rows above the output row
 };
 
@@ -135,7 +139,7 @@ __device__ __forceinline__ void mac_row(const uint32_t (&cpe)[kMaxPairs2], const
 }
 
 template <typename T, int KH, int KW, bool HI16, bool SEP>
-__global__ void __launch_bounds__(kThreads2, FIRGPU_T2_MINBLOCKS)
+__global__ void __launch_bounds__(kBlock2, FIRGPU_T2_MINBLOCKS)
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
     using G = Geo2<T, KH, KW>;
@@ -152,9 +156,13 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if ((int)blockIdx.x < p.total_items) n_my = (p.total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
     const int spi = p.stages_per_item;
 
+    const uint32_t empty_base = bar_base + 8 * kStages2;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages2; ++s) mbar_init(bar_base + 8 * s, 1);
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(bar_base + 8 * s, 1);                   // "full": TMA transaction barrier
+            mbar_init(empty_base + 8 * s, kThreads2 / 32);    // "empty": one arrival per consumer warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -191,9 +199,27 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         p_stage = p_stage + 1 == kStages2 ? 0 : p_stage + 1;
     };
     const long long total_stages = (long long)n_my * spi;
+#if FIRGPU_T2_WARPSPEC
+    if (tid >= kThreads2) {
+        // Producer warp: one lane walks the whole stage sequence, refilling a
+        // stage as soon as every consumer warp has released it.
+        if (tid == kThreads2) {
+            uint32_t empty_phase = 0;
+            for (long long q = 0; q < total_stages; ++q) {
+                if (q >= kStages2) {
+                    mbar_wait(empty_base + 8 * p_stage, (empty_phase >> p_stage) & 1u);
+                    empty_phase ^= 1u << p_stage;
+                }
+                issue();
+            }
+        }
+        return;
+    }
+#else
     if (tid == 0) {
         for (int i = 0; i < kStages2 && i < total_stages; ++i) issue();
     }
+#endif
 
     // ---- per-thread constants ---------------------------------------------------------
     const bool active = tid < G::ACTIVE;
@@ -309,8 +335,13 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     }
                 }
             }
+#if FIRGPU_T2_WARPSPEC
+            __syncwarp();                                  // this warp is done with the stage
+            if ((tid & 31) == 0) staged::mbar_arrive(empty_base + 8 * stage);
+#else
             __syncthreads();                               // every thread is done with this stage
             if (tid == 0 && (long long)k * spi + j + kStages2 < total_stages) issue();
+#endif
             stage = stage + 1 == kStages2 ? 0 : stage + 1;
         }
     }
@@ -332,7 +363,7 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
         if (dev < 64 && ctas_per_sm[dev] == 0) {
             FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
             int n = 0;
-            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads2, G::SMEM));
+            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kBlock2, G::SMEM));
             ctas_per_sm[dev] = n < 1 ? 1 : n;
         }
         per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
@@ -347,7 +378,7 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long grid = (long long)sms * per_sm;
     if (grid > p.total_items) grid = p.total_items;
-    kern<<<(unsigned)grid, kThreads2, G::SMEM, stream>>>(map, p);
+    kern<<<(unsigned)grid, kBlock2, G::SMEM, stream>>>(map, p);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
