@@ -442,6 +442,18 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     }
     Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, frac_bits, acc_bits,
                 halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    // Many short rows (images, short channels): the row-streaming tensor-map
+    // kernel keeps whole CTAs busy where the 1-D tile kernel would stage one
+    // mostly empty tile per row.  Its TMA out-of-bounds zero fill is the
+    // per-row zero padding.
+    if (rows >= 16 && cols * dtype_size(in_dtype) <= 8192 && dilation == 1 && halo_left_valid == 0 && halo_right_valid == 0 &&
+        in_dtype == out_dtype) {
+        Fir2dArgs b{x, y, in_dtype, out_dtype, 1, rows, cols, ld_x, ld_y, 0, 0, 1, n_taps, frac_bits, acc_bits, 0, 0,
+                    (cudaStream_t)stream};
+        rc = try_launch_fir2d_fixed_tiled(b, hq);
+        if (rc == 1) return 0;
+        if (rc != 0) return rc;
+    }
     rc = try_launch_fir1d_fixed_staged(a, hq);
     if (rc == 1) return 0;
     if (rc != 0) return rc;

@@ -62,7 +62,7 @@ constexpr int kThreads2 = FIRGPU_T2_THREADS;
 constexpr int kStages2 = FIRGPU_T2_STAGES;
 constexpr int kBlock2 = kThreads2 + (FIRGPU_T2_WARPSPEC ? 32 : 0);   // consumer threads (+ one producer warp)
 constexpr int kBandTarget = 64;                  // output rows per band, about
-inline constexpr int rows_per_stage(int kh) { return kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
+inline constexpr int rows_per_stage(int kh) { return kh == 1 ? 8 : kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
 constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
 constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
 constexpr int kMaxKH = 5;
@@ -387,7 +387,7 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
 template <typename T, int KH, int KW>
 int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, bool hi16, bool sep, cudaStream_t s)
 {
-    if constexpr (KW >= 3 && !(KH == 3 && KW == 3)) {
+    if constexpr (KH > 1 && KW >= 3 && !(KH == 3 && KW == 3)) {
         if (sep)
             return hi16 ? launch_tiled_one<T, KH, KW, true, true>(map, p, s) : launch_tiled_one<T, KH, KW, false, true>(map, p, s);
     }
@@ -397,6 +397,8 @@ int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, bool hi16, 
 template <typename T>
 int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
 {
+    if (kh == 1 && kw == 3) return launch_tiled_modes<T, 1, 3>(map, p, hi16, sep, s);   // short-row batches of the 1-D filter
+    if (kh == 1 && kw == 5) return launch_tiled_modes<T, 1, 5>(map, p, hi16, sep, s);
     if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1>(map, p, hi16, sep, s);
     if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3>(map, p, hi16, sep, s);
     if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5>(map, p, hi16, sep, s);
@@ -407,8 +409,11 @@ int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int
 }
 
 // Does the (kh, kw) shape have a separable instantiation?
-inline bool shape_has_separable(int kh, int kw) { return kw >= 3 && !(kh == 3 && kw == 3); }
-inline bool shape_supported(int kh, int kw) { return (kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5); }
+inline bool shape_has_separable(int kh, int kw) { return kh > 1 && kw >= 3 && !(kh == 3 && kw == 3); }
+inline bool shape_supported(int kh, int kw)
+{
+    return ((kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5)) || (kh == 1 && (kw == 3 || kw == 5));
+}
 int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
 int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
 
