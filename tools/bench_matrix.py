@@ -129,6 +129,18 @@ def main():
             hq = quant.quantize_taps(np.asarray(k), 12, 16)
             s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out_dtype=np.int16, out=out), args.reps, warm=2)
             report(f"2d 16384^2 i16->i16 {tag} q4.12", s, 16384 * 16384, 4)
+        img8 = rand_i16(16384 * 16384).clamp(0, 255).to(torch.uint8).view(1, 16384, 16384)
+        out8 = torch.empty_like(img8)
+        for k, tag in ((k3, "3x3 box"), (k5, "5x5 lp rank-1"), (kr, "5x5 general")):
+            hq = quant.quantize_taps(np.asarray(k), 12, 16)
+            s = timed(lambda: firgpu.fir2d_fixed_q(img8, hq, 12, 32, out=out8), args.reps, warm=2)
+            report(f"2d 16384^2 u8->u8 {tag} q4.12", s, 16384 * 16384, 2)
+        del img, out, img8, out8
+        batch = rand_i16(4 * 8192 * 8192).view(4, 8192, 8192)
+        outb = torch.empty_like(batch)
+        hq = quant.quantize_taps(np.asarray(k3), 12, 16)
+        s = timed(lambda: firgpu.fir2d_fixed_q(batch, hq, 12, 32, out_dtype=np.int16, out=outb), args.reps, warm=2)
+        report("2d batch 4 x 8192^2 i16->i16 3x3 box q4.12", s, 4 * 8192 * 8192, 4)
     if "multi" in cases:
         from fir_1d.sim.vector.h_coeff import h_coeff_5tap_map
         sets = list(h_coeff_5tap_map.values())

@@ -11,7 +11,8 @@
 // __dmul_rn then __dadd_rn (no FMA contraction), accumulator starting at +0.0
 // — bit-identical to the Python model.  Zero padding outside the row is
 // stored as +0.0 samples, which adds +-0.0 to a +0.0-started sum and never
-// changes it (same argument as oracle/fir_oracle_np.py::fir1d_ideal).
+// changes it (x + (+-0.0) == x for every x, and +0.0 + (-0.0) == +0.0), so the
+// padded form is bit-identical to the reference's "skip taps outside the row".
 #include "common.cuh"
 
 #include <cstdlib>

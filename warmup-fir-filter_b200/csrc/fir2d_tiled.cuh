@@ -65,6 +65,8 @@ constexpr int kBandTarget = 64;                  // output rows per band, about
 inline constexpr int rows_per_stage(int kh) { return kh == 1 ? 8 : kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
 constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
 constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
+constexpr int kMapElemBytes = 2;                 // the tensor map always describes 16-bit elements: int16 pixels, or PAIRS of
+                                                 // uint8 pixels (even widths), so that a box row is 512 bytes for both
 constexpr int kMaxKH = 5;
 constexpr int kMaxPairs2 = 3;                    // KW <= 5
 
@@ -87,7 +89,7 @@ template <typename T, int KH, int KW> struct Geo2 {
     static constexpr int ES = sizeof(T);
     static constexpr int BH = rows_per_stage(KH);   // rows per TMA stage (multiple of KH)
     static constexpr int RPS = BH / KH;
-    static constexpr int BOXB = kBoxElems * ES;  // bytes per box row
+    static constexpr int BOXB = kBoxElems * kMapElemBytes;   // bytes per box row
     static constexpr int NBX = kStripBytes / BOXB;
     static constexpr int STAGE = BH * kStripBytes;
     static constexpr int PADS = 16 / ES;         // columns of pad staged on each side
@@ -191,7 +193,7 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int c1 = row0 - G::UP + p_j * G::BH + p.halo_top;
 #pragma unroll
         for (int bx = 0; bx < G::NBX; ++bx)
-            tma_load_3d(dst + bx * (G::BH * G::BOXB), &tmap, col0 - G::PADS + bx * kBoxElems, c1, img, bar);
+            tma_load_3d(dst + bx * (G::BH * G::BOXB), &tmap, (col0 - G::PADS) * ES / kMapElemBytes + bx * kBoxElems, c1, img, bar);
         if (++p_j == spi) {
             p_j = 0;
             ++p_item;
@@ -369,8 +371,9 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
         per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
     }
     // Measured on B200 (profiles/r1_sweep_tunables.md): two stages in flight; 3-row
-    // kernels are fastest with 3 resident CTAs per SM, 5-row kernels with all that fit.
-    if (KH <= 3 && per_sm > 3) per_sm = 3;
+    // int16 kernels are fastest with 3 resident CTAs per SM; 5-row and all uint8 kernels
+    // (twice the arithmetic per byte) with all that fit.
+    if (KH <= 3 && sizeof(T) == 2 && per_sm > 3) per_sm = 3;
     if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {
         const int forced = atoi(e);
         if (forced >= 1 && forced < per_sm) per_sm = forced;

@@ -40,6 +40,44 @@ class DeviceArray:
     stream: int = 0
 
 
+_TAP_CACHE: dict = {}
+
+
+def _tap_key(h, frac_bits: int, acc_bits: int, coeff_bits: int):
+    """Cache key of an already validated + quantised tap set, or None when the
+    taps are not plain Python numbers (arrays, exotic scalars: never cached)."""
+    try:
+        key = (tuple(h), frac_bits, acc_bits, coeff_bits)
+        hash(key)
+    except TypeError:
+        return None
+    return key if all(type(v) in (int, float) for v in key[0]) else None
+
+
+def _remember_taps(key, hq: np.ndarray) -> None:
+    if key is not None:
+        if len(_TAP_CACHE) > 256:
+            _TAP_CACHE.clear()
+        hq.setflags(write=False)
+        _TAP_CACHE[key] = hq
+
+
+class _on_device:
+    """`with torch.cuda.device(d)` only when d is not already current (the
+    context manager costs more than a small launch)."""
+
+    def __init__(self, torch, device):
+        self.cm = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.cm is not None:
+            self.cm.__enter__()
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
@@ -171,7 +209,12 @@ def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int =
     ``in_range = out_range = (-32768, 32767)`` the signed int16 path.  The
     defaults ARE the reference model.
     """
-    quant.validate_taps(h)
+    # A cache hit means this exact tap set already passed every coefficient-side
+    # check; the reference's order (taps, samples, bit widths, Q range) is kept.
+    key = _tap_key(h, frac_bits, acc_bits, coeff_bits)
+    hq = _TAP_CACHE.get(key) if key is not None else None
+    if hq is None:
+        quant.validate_taps(h)
     in_range, out_range = (int(in_range[0]), int(in_range[1])), (int(out_range[0]), int(out_range[1]))
     if out_dtype is None:
         out_dtype = np.uint8 if (out_range[0] >= 0 and out_range[1] <= 255) else np.int16
@@ -182,8 +225,10 @@ def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int =
         x = _np_container(x, *in_range)
         if validate:
             quant.check_samples_finite(x)
-    quant.check_bits(frac_bits, acc_bits, coeff_bits)
-    hq = quant.quantize_taps(h, frac_bits, coeff_bits)
+    if hq is None:
+        quant.check_bits(frac_bits, acc_bits, coeff_bits)
+        hq = quant.quantize_taps(h, frac_bits, coeff_bits)
+        _remember_taps(key, hq)
     ex = None
     if (centre is not None and centre != len(hq) // 2) or in_range != (0, 255) or out_range != (0, 255):
         ex = (len(hq) // 2 if centre is None else int(centre),) + in_range + out_range
@@ -214,7 +259,7 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
         _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
         if (y_rows, y_cols) != (rows, cols):
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             if ex is None:
                 _lib.check(L.firgpu_fir1d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
@@ -268,7 +313,7 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
             _check_finite_torch(x)
         t, rows, cols, ld = _cuda_rows(x, allow_copy=not (halo_left_valid or halo_right_valid))
         y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             if ex is None:
                 _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
@@ -334,7 +379,7 @@ def compare_metrics(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: i
     if is_t and x.is_cuda:
         import torch
         t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir1d_compare(t.data_ptr(), _torch_code(t), rows, cols, ld, _taps_ptr(hq), _taps_ptr(hh),
                                               hq.size, frac_bits, acc_bits, out.ctypes.data, stream))
@@ -391,7 +436,7 @@ def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8,
         ld = t.stride(-2) if t.dim() >= 2 else wid
         img_stride = t.stride(-3) if t.dim() >= 3 else hgt * ld
         y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir2d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, wid,
                                             img_stride, hgt * wid, _taps_ptr(hq), kh, kw, frac_bits, acc_bits,
@@ -440,7 +485,7 @@ def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_
         import torch
         t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
         y = torch.empty((nf,) + tuple(x.shape), dtype=_torch_dtype(out_dtype), device=x.device)
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir1d_fixed_multi(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld,
                                                   cols, rows * cols, _taps_ptr(hq), nf, n_taps, 1, frac_bits, acc_bits,
@@ -474,7 +519,7 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
         t = _torch_container(x)
         n, hgt, wid = _imgs(t.shape)
         y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
-        with torch.cuda.device(x.device):
+        with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, wid, wid,
                                             hgt * wid, hgt * wid, _taps_ptr(hh), kh, kw, 0, 0, stream))
