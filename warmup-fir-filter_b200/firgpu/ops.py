@@ -497,12 +497,10 @@ def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_
     _lib.check(L.firgpu_fir1d_fixed_multi_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
                                                cols, cols, rows * cols, _taps_ptr(hq), nf, n_taps, 1, frac_bits,
                                                acc_bits, device))
-    return torch_from(y) if is_t else y
-
-
-def torch_from(a):
-    import torch
-    return torch.from_numpy(a)
+    if is_t:
+        import torch
+        return torch.from_numpy(y)
+    return y
 
 
 def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, validate: bool = True):
