@@ -313,3 +313,44 @@ def test_multi_filter_reads_input_once(fg, torch, manifest):
     assert np.array_equal(fg.fir1d_fixed_multi(torch.from_numpy(xu).cuda(), sets).cpu().numpy(), want)
     with pytest.raises(ValueError, match="same length"):
         fg.fir1d_fixed_multi(xu, [[1.0], [0.5, 0.5]])
+
+
+def test_wide_signed_int16_fast_path(fg, torch):
+    """Extended entry point on int16 containers with non-reference clamp ranges:
+    served by the wide datapath of the staged kernel (IMAD on full-width
+    samples, saturating pack) whenever int32 provably suffices — bit-exact
+    against the parametrised oracle, tile edges, ragged tails, shard halos and
+    interleaved I/Q included."""
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(77)
+    full = (-32768, 32767)
+    for n_taps in (1, 2, 3, 5, 8, 9):
+        h = rng.uniform(-0.2, 0.2, size=n_taps).tolist()            # sum|h| < 2: int32 is provably enough in Q1.15
+        for dil, n in ((1, 1), (1, 9), (1, 16384), (1, 70_003), (2, 66_002), (1, 300_001)):
+            x = rng.integers(-32768, 32768, size=n).astype(np.int16)
+            xt = torch.from_numpy(x).cuda()
+            for in_r, out_r in ((full, full), ((-1000, 2000), (-300, 300)), ((0, 255), full)):
+                got = fg.fir1d_fixed(xt, h, 15, 32, 16, dilation=dil, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, dil, n, in_r, out_r)
+                want = onp.fir1d_fixed(x, h, 15, 32, 16, dilation=dil, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                assert np.array_equal(got.cpu().numpy(), want), (n_taps, dil, n, in_r, out_r)
+    # rows with pitch, and segments with halos
+    x = rng.integers(-32768, 32768, size=(5, 33_000)).astype(np.int16)
+    h = [0.1, -0.2, 0.4, -0.2, 0.1]
+    view = torch.from_numpy(x).cuda()[:, :32_999]
+    got = fg.fir1d_fixed(view, h, 15, 32, 16, in_range=full, out_range=full)
+    assert _lib.last_path() == _lib.PATH_STAGED
+    assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x[:, :32_999], h, 15, 32, 16, in_range=full, out_range=full, out_dtype=np.int16))
+    sig = rng.integers(-32768, 32768, size=200_000).astype(np.int16)
+    want = onp.fir1d_fixed(sig, h, 15, 32, 16, in_range=full, out_range=full, out_dtype=np.int16)
+    for p in shard.plan_segments(sig.size, 3, 5, 1, align=4096):
+        buf, body = shard.scatter_segment(sig, p, "cuda")
+        y = fg.fir1d_fixed(body, h, 15, 32, 16, in_range=full, out_range=full, halo_left_valid=p.before, halo_right_valid=p.after)
+        assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])
+    # saturation really happens, and the int32 proof sends big taps to the generic kernel
+    loud = np.full(4096, 32767, np.int16)
+    y = fg.fir1d_fixed(torch.from_numpy(loud).cuda(), [0.9, 0.9], 15, 32, 16, in_range=full, out_range=full)
+    assert _lib.last_path() == _lib.PATH_STAGED and int(y[10]) == 32767
+    y = fg.fir1d_fixed(torch.from_numpy(loud).cuda(), [0.999, 0.999, 0.999], 15, 32, 16, in_range=full, out_range=full)
+    assert _lib.last_path() == _lib.PATH_GENERIC            # 32767 * 3 * 32735 > 2^31: wrap is live, int64 kernel
+    assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(loud, [0.999, 0.999, 0.999], 15, 32, 16, in_range=full, out_range=full, out_dtype=np.int16))

@@ -55,7 +55,7 @@ def rand_i16(n, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="stream,u8,iq,taps,batched,images,ideal,2d")
+    ap.add_argument("--cases", default="stream,signed,u8,iq,taps,batched,images,ideal,2d")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     cases = args.cases.split(",")
@@ -70,6 +70,18 @@ def main():
         s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out=y8, validate=False), args.reps)
         report("stream 2^28 i16->u8 5tap q1.15", s, n, 3)
         del x, y, y8
+    if "signed" in cases:
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randint(-32768, 32768, (n,), generator=g, device="cuda", dtype=torch.int32).to(torch.int16)
+        y = torch.empty_like(x)
+        full = (-32768, 32767)
+        s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, in_range=full, out_range=full, out=y, validate=False), args.reps)
+        report("signed int16 stream 2^28 i16->i16 5tap q1.15 (wide datapath)", s, n, 4)
+        s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, dilation=2, in_range=full, out_range=full, out=y, validate=False), args.reps)
+        report("signed int16 I/Q 2^27 complex 5tap q1.15 (wide datapath)", s, n, 4)
+        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], LP5, 15, 48, 16, centre=0, in_range=full, out_range=full, out=y[: 1 << 26], validate=False), 5)
+        report("signed int16 causal 2^26 (generic kernel)", s, 1 << 26, 4)
+        del x, y
     if "u8" in cases:
         x = rand_i16(n).clamp(0, 255).to(torch.uint8)
         y = torch.empty_like(x)

@@ -27,6 +27,25 @@ __global__ void fill_kernel(int16_t *x, size_t n)
         x[i] = (int16_t)((i * 2654435761u >> 7) % 300 - 20);
 }
 
+__global__ void store_kernel(uint4 *__restrict__ b, size_t n)
+{
+    const uint4 v = make_uint4(1u, 2u, 3u, 4u);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = v;
+}
+
+__global__ void load_kernel(const uint4 *__restrict__ a, uint4 *__restrict__ sink, size_t n)
+{
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = a[i];
+        acc.x ^= v.x;
+        acc.y ^= v.y;
+        acc.z ^= v.z;
+        acc.w ^= v.w;
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[0] = acc;      // never true in practice; keeps the loads alive
+}
+
 __global__ void copy_kernel(const uint4 *__restrict__ a, uint4 *__restrict__ b, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
@@ -117,6 +136,23 @@ int main(int argc, char **argv)
             cudaEventElapsedTime(&ms, e0, e1);
             ms /= reps;
             printf("{\"case\": \"copy_kernel uint4 grid-stride\", \"grid\": %d, \"ms\": %.4f, \"gb_s\": %.1f}\n", g, ms, n * 4.0 / (ms * 1e-3) / 1e9);
+        }
+        for (int g : {sms * 8, sms * 32}) {
+            cudaEventRecord(e0);
+            for (int r = 0; r < reps; ++r) store_kernel<<<g, 256>>>((uint4 *)y, n / 8);
+            cudaEventRecord(e1);
+            cudaDeviceSynchronize();
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms /= reps;
+            printf("{\"case\": \"store-only kernel uint4\", \"grid\": %d, \"ms\": %.4f, \"gb_s\": %.1f}\n", g, ms, n * 2.0 / (ms * 1e-3) / 1e9);
+            cudaEventRecord(e0);
+            for (int r = 0; r < reps; ++r) load_kernel<<<g, 256>>>((const uint4 *)x, (uint4 *)y, n / 8);
+            cudaEventRecord(e1);
+            cudaDeviceSynchronize();
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms /= reps;
+            printf("{\"case\": \"load-only kernel uint4\", \"grid\": %d, \"ms\": %.4f, \"gb_s\": %.1f}\n", g, ms, n * 2.0 / (ms * 1e-3) / 1e9);
         }
         cudaEventRecord(e0);
         for (int r = 0; r < reps; ++r) cudaMemcpyAsync(y, x, n * 2, cudaMemcpyDeviceToDevice);

@@ -731,9 +731,11 @@ int firgpu_fir1d_fixed_ex(const void *x, void *y, int in_dtype, int out_dtype, i
     a.out_hi = out_hi;
     if (a.is_reference_model()) {           // the reference's own parameters: the fast kernels apply
         rc = try_launch_fir1d_fixed_staged(a, hq);
-        if (rc == 1) return 0;
-        if (rc != 0) return rc;
+    } else {                                // other clamp ranges on int16 containers: wide datapath
+        rc = try_launch_fir1d_fixed_staged_wide(a, hq);
     }
+    if (rc == 1) return 0;
+    if (rc != 0) return rc;
     return launch_fir1d_fixed_generic(a, hq);
 }
 

@@ -143,6 +143,8 @@ int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
 // taps are outside the staged kernel's domain (caller falls to generic), <0 / >0 on error.
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
+// wide datapath of the extended entry point (signed int16 ranges); 1 = served, 0 = not eligible
+int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_host);
 // n_filters tap sets ([n_filters][n_taps]) over one pass of the input; outputs filter_stride_y elements apart.
 int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y);
 // fir1d_compare.cu

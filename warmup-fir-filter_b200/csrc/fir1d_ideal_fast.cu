@@ -47,9 +47,31 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, double *__restrict__ y, int64
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
 
     // samples [col0 - LEAD, col0 - LEAD + SPAN) -> float64 in shared memory
-    for (int i = threadIdx.x; i < SPAN; i += kThreadsI) {
-        const int64_t g = col0 - LEAD + i;
-        xs[i] = (g >= vlo && g < vhi) ? (double)prep_sample(xr[g]) : 0.0;
+    constexpr int PER = kTileI / kThreadsI;               // 8 body samples per thread
+    const bool interior = col0 - LEAD >= vlo && col0 - LEAD + SPAN <= vhi &&
+                          ((reinterpret_cast<uintptr_t>(xr + col0) & (PER * sizeof(InT) - 1)) == 0);
+    if (interior) {
+        // one vector load of 8 samples per thread, converted in registers
+        const InT *src = xr + col0 + threadIdx.x * PER;
+        InT v[PER];
+        if constexpr (sizeof(InT) == 1) {
+            *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(src);
+        } else {
+            *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(src);
+        }
+        double *dst = &xs[LEAD + threadIdx.x * PER];
+#pragma unroll
+        for (int q = 0; q < PER; q += 2)
+            *reinterpret_cast<double2 *>(dst + q) = make_double2((double)prep_sample(v[q]), (double)prep_sample(v[q + 1]));
+        // the few samples on either side of the body
+        if (threadIdx.x < LEAD) xs[threadIdx.x] = (double)prep_sample(xr[col0 - LEAD + threadIdx.x]);
+        if (threadIdx.x < SPAN - LEAD - kTileI)
+            xs[LEAD + kTileI + threadIdx.x] = (double)prep_sample(xr[col0 + kTileI + threadIdx.x]);
+    } else {
+        for (int i = threadIdx.x; i < SPAN; i += kThreadsI) {
+            const int64_t g = col0 - LEAD + i;
+            xs[i] = (g >= vlo && g < vhi) ? (double)prep_sample(xr[g]) : 0.0;
+        }
     }
     __syncthreads();
 

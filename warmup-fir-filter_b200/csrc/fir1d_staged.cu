@@ -4,6 +4,7 @@
 #include "fir1d_staged.cuh"
 #include "fastplan.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace firgpu {
@@ -87,6 +88,52 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
 {
     return try_launch_fir1d_fixed_staged_multi(a, hq_host, 1, 0);
+}
+
+// Wide datapath: int16 samples used at full width with caller-given clamp
+// ranges (extended entry point).  Exactness proof: |sample| <= M and
+// M * sum|hq| + bias < 2^31 and below the acc_bits wrap point.
+int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_host)
+{
+    if (a.in_dtype != FIRGPU_I16 || a.out_dtype != FIRGPU_I16) return 0;
+    if (a.dilation != 1 && a.dilation != 2) return 0;
+    if (a.dilation == 2 && ((a.cols | a.halo_left | a.halo_right) & 1)) return 0;
+    if (a.n_taps > kMaxFastTaps || (a.centre >= 0 && a.centre != a.n_taps / 2)) return 0;
+    if (a.frac_bits < 1 || a.frac_bits > 30) return 0;
+    if (a.in_lo < -32768 || a.in_hi > 32767 || a.out_lo < -32768 || a.out_hi > 32767) return 0;
+    const char *force = getenv("FIRGPU_FORCE_GENERIC");
+    if (force && force[0] == '1') return 0;
+    long long sum_abs = 0;
+    for (int k = 0; k < a.n_taps; ++k) sum_abs += hq_host[k] < 0 ? -(long long)hq_host[k] : (long long)hq_host[k];
+    const long long m = std::max<long long>(a.in_lo < 0 ? -(long long)a.in_lo : a.in_lo, a.in_hi < 0 ? -(long long)a.in_hi : a.in_hi);
+    const long long bias = 1LL << (a.frac_bits - 1);
+    if (sum_abs > (1LL << 40)) return 0;
+    const long long max_acc = m * sum_abs;
+    if (max_acc + bias > 0x7fffffffLL) return 0;
+    if (a.acc_bits < 63 && max_acc > (1LL << (a.acc_bits - 1)) - 1) return 0;
+
+    StagedParams p{};
+    p.x = (const unsigned char *)a.x;
+    p.y = (unsigned char *)a.y;
+    p.rows = a.rows;
+    p.cols = a.cols;
+    p.ld_x = a.ld_x;
+    p.ld_y = a.ld_y;
+    p.halo_left = a.halo_left;
+    p.halo_right = a.halo_right;
+    p.n_filters = 1;
+    p.shift = a.frac_bits;
+    p.bias = (int)bias;
+    p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * 2) % 16 == 0);
+    p.y_vec_ok = ((uintptr_t)a.y % 16 == 0) && (a.rows == 1 || (a.ld_y * 2) % 16 == 0);
+    for (int k = 0; k < a.n_taps; ++k) p.hq[k] = hq_host[k];
+    auto dup = [](int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); };
+    p.in_lo2 = dup(a.in_lo);
+    p.in_hi2 = dup(a.in_hi);
+    p.out_lo2 = dup(a.out_lo);
+    p.out_hi2 = dup(a.out_hi);
+    const bool clamp = !(a.in_lo == -32768 && a.in_hi == 32767 && a.out_lo == -32768 && a.out_hi == 32767);
+    return launch_staged_wide(p, a.n_taps, a.dilation, clamp, a.stream);
 }
 
 }  // namespace firgpu

@@ -91,7 +91,8 @@ struct StagedParams {
     long long filter_stride_y;                 // elements between the outputs of consecutive tap sets
     uint32_t cp_even[kMaxFilters][kMaxPairs];  // dp2a tap pairs, window starting on an even sample
     uint32_t cp_odd[kMaxFilters][kMaxPairs];   // ... on an odd sample
-    int32_t hq[kMaxFastTaps];                  // IMAD mode taps
+    int32_t hq[kMaxFastTaps];                  // IMAD / wide mode taps
+    uint32_t in_lo2, in_hi2, out_lo2, out_hi2; // wide mode: clamp bounds, each duplicated into both 16-bit lanes
 };
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -356,6 +357,45 @@ __device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int 
     }
 }
 
+// Wide datapath (MAC == 2): int16 samples used at full width — the signed int16
+// path of the extended entry points.  Each staged pair is clamped to the
+// caller's sample range (packed, skipped for the full int16 range), unpacked
+// to int32, accumulated with IMAD (taps are constant-bank operands), shifted,
+// and packed back with saturation (cvt.pack.sat.s16.s32 = two outputs per
+// instruction), then clamped to the output range.  dilation needs no
+// de-interleave here: every scalar has its own register.
+template <int L, int DIL, bool CLAMP>
+__device__ __forceinline__ void wide_chunk(const StagedParams &p, const uint32_t (&raw)[Geo<int16_t, L, DIL>::NR], uint32_t (&O)[4])
+{
+    using G = Geo<int16_t, L, DIL>;
+    constexpr int HLS = G::HLB / 2;                // halo scalars in front of the chunk
+    int X[G::NR * 2];
+#pragma unroll
+    for (int j = 0; j < G::NR; ++j) {
+        uint32_t w = raw[j];
+        if constexpr (CLAMP) w = __vmaxs2(__vmins2(w, p.in_hi2), p.in_lo2);
+        // sign-extend the low half: prmt selector 9 = byte 1 with sign replication (the
+        // __byte_perm intrinsic masks that bit off, so the instruction is written out)
+        asm("prmt.b32 %0, %1, %1, 0x9910;" : "=r"(X[2 * j]) : "r"(w));
+        X[2 * j + 1] = (int)w >> 16;
+    }
+    int v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int a = p.bias;
+#pragma unroll
+        for (int k = 0; k < L; ++k) a += p.hq[k] * X[HLS + e + (G::hi - k) * DIL];
+        v[e] = a >> p.shift;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t o;
+        asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o) : "r"(v[2 * j + 1]), "r"(v[2 * j]));
+        if constexpr (CLAMP) o = __vmaxs2(__vmins2(o, p.out_hi2), p.out_lo2);
+        O[j] = o;
+    }
+}
+
 // Write one chunk's output words: a vector store, or guarded scalars at ragged
 // row ends / unaligned outputs (`room` = scalars left in the row).
 template <typename OutT, int SC>
@@ -479,13 +519,19 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             // whole tile inside the row: no per-chunk bounds logic at all
 #pragma unroll
             for (int u = 0; u < kSub; ++u) {
-                uint32_t B[DIL][G::NB];
-                pack_chunk<InT, L, DIL>(raw[u], B);
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
+                if constexpr (MAC == 2) {
                     uint32_t O[NOUT];
-                    mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
-                    store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O, true, G::SC);
+                    wide_chunk<L, DIL, HI16>(p, raw[u], O);           // HI16 slot = "clamp ranges are not the full int16 range"
+                    store_chunk<OutT, G::SC>(ythread + u * (kThreads * G::SC), O, true, G::SC);
+                } else {
+                    uint32_t B[DIL][G::NB];
+                    pack_chunk<InT, L, DIL>(raw[u], B);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        uint32_t O[NOUT];
+                        mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
+                        store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O, true, G::SC);
+                    }
                 }
             }
         } else {
@@ -494,14 +540,20 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             for (int u = 0; u < kSub; ++u) {
                 const long long room = left - u * (kThreads * G::SC);
                 if (room <= 0) continue;
-                uint32_t B[DIL][G::NB];
-                pack_chunk<InT, L, DIL>(raw[u], B);
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
+                if constexpr (MAC == 2) {
                     uint32_t O[NOUT];
-                    mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
-                    store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O,
-                                             p.y_vec_ok && room >= G::SC, room);
+                    wide_chunk<L, DIL, HI16>(p, raw[u], O);
+                    store_chunk<OutT, G::SC>(ythread + u * (kThreads * G::SC), O, p.y_vec_ok && room >= G::SC, room);
+                } else {
+                    uint32_t B[DIL][G::NB];
+                    pack_chunk<InT, L, DIL>(raw[u], B);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        uint32_t O[NOUT];
+                        mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
+                        store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O,
+                                                 p.y_vec_ok && room >= G::SC, room);
+                    }
                 }
             }
         }
@@ -568,6 +620,11 @@ int launch_one(const StagedParams &p, cudaStream_t stream)
 template <typename InT, typename OutT, int L, int DIL>
 int launch_modes(const StagedParams &p, bool hi16, int mac, cudaStream_t s)
 {
+#ifdef FIRGPU_STAGED_WIDE_TU             // fir1d_staged_wide.cu: the wide (signed int16) datapath only
+    static_assert(sizeof(InT) == 2 && sizeof(OutT) == 2, "wide datapath is int16 -> int16");
+    (void)mac;                           // "hi16" carries the clamp flag
+    return hi16 ? launch_one<InT, OutT, L, DIL, true, 2>(p, s) : launch_one<InT, OutT, L, DIL, false, 2>(p, s);
+#else
     if (mac == 0) {
         return hi16 ? launch_one<InT, OutT, L, DIL, true, 0>(p, s) : launch_one<InT, OutT, L, DIL, false, 0>(p, s);
     }
@@ -578,6 +635,7 @@ int launch_modes(const StagedParams &p, bool hi16, int mac, cudaStream_t s)
     } else {
         return 0;
     }
+#endif
 }
 
 template <typename InT, typename OutT, int DIL>
@@ -612,6 +670,7 @@ int launch_staged_u8_u8(const StagedParams &p, int n_taps, int dilation, bool hi
 int launch_staged_u8_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
 int launch_staged_i16_u8(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
 int launch_staged_i16_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+int launch_staged_wide(const StagedParams &p, int n_taps, int dilation, bool clamp, cudaStream_t s);
 
 }  // namespace staged
 }  // namespace firgpu
