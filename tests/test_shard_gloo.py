@@ -79,3 +79,39 @@ def test_row_and_band_plans_partition_exactly():
         assert sum(p.size for p in pieces) == rows and all(p.before == p.after == 0 for p in pieces)
     bands = shard.plan_bands(1000, 3, 3)
     assert [(b.start, b.stop, b.before, b.after) for b in bands] == [(0, 334, 0, 1), (334, 667, 1, 1), (667, 1000, 1, 0)]
+
+
+def _band_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    for p in (str(ROOT), str(ROOT / "warmup-fir-filter_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from firgpu import shard
+    from oracle import fir_oracle_np as onp
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        k = np.outer([1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16], [0.25, 0.5, 0.25]).tolist()      # 5 x 3
+        full = np.random.default_rng(7).integers(-100, 400, size=(2, 61, 40)).astype(np.int16)
+        bands = shard.plan_bands(full.shape[1], world, len(k))
+        me = bands[rank]
+        buf = torch.zeros((2, me.before + me.size + me.after, 40), dtype=torch.int16)
+        buf[:, me.before:me.before + me.size, :] = torch.from_numpy(full[:, me.start:me.stop, :])
+        shard.exchange_band_halos(buf, bands, rank, dist)
+        assert np.array_equal(buf.numpy(), full[:, me.lo:me.hi, :]), "band halo exchange delivered the wrong rows"
+        # filtering the band with its halo rows = the matching rows of the whole-image result
+        whole = onp.fir2d_fixed(full, k)
+        local = onp.fir2d_fixed(buf.numpy(), k)[:, me.before:me.before + me.size, :]
+        assert np.array_equal(local, whole[:, me.start:me.stop, :]), "band result differs from the whole-image result"
+        Path(out_dir, f"ok_{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_sharding_over_gloo(tmp_path, world):
+    import torch.multiprocessing as mp
+    mp.spawn(_band_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(p.name for p in tmp_path.glob("ok_*")) == [f"ok_{r}" for r in range(world)]

@@ -146,3 +146,37 @@ def exchange_halos(buf, lead: int, pieces: list[Piece], rank: int, dist) -> None
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+def exchange_band_halos(buf, pieces: list[Piece], rank: int, dist) -> None:
+    """Row-band analogue of :func:`exchange_halos` for images that are already
+    distributed: ``buf`` is ``[..., before + size + after, W]`` with this
+    rank's band rows in place; the halo rows receive the neighbours' edge rows
+    (send/recv of contiguous copies, once, at shard time)."""
+    import torch
+    me = pieces[rank]
+    ops, recvs, keep = [], [], []
+
+    def raw(t):
+        return t.contiguous().view(torch.uint8)
+
+    if me.before:
+        tmp = torch.empty_like(buf[..., :me.before, :]).contiguous()
+        recvs.append((tmp, slice(0, me.before)))
+        ops.append(dist.P2POp(dist.irecv, raw(tmp), rank - 1))
+    if me.after:
+        tmp = torch.empty_like(buf[..., me.before + me.size:, :]).contiguous()
+        recvs.append((tmp, slice(me.before + me.size, me.before + me.size + me.after)))
+        ops.append(dist.P2POp(dist.irecv, raw(tmp), rank + 1))
+    body = buf[..., me.before:me.before + me.size, :]
+    if rank + 1 < len(pieces) and pieces[rank + 1].before:
+        keep.append(raw(body[..., me.size - pieces[rank + 1].before:, :]))
+        ops.append(dist.P2POp(dist.isend, keep[-1], rank + 1))
+    if rank > 0 and pieces[rank - 1].after:
+        keep.append(raw(body[..., :pieces[rank - 1].after, :]))
+        ops.append(dist.P2POp(dist.isend, keep[-1], rank - 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for tmp, rows in recvs:
+        buf[..., rows, :] = tmp
