@@ -83,3 +83,18 @@ def images_inputs():
 @pytest.fixture(scope="session")
 def image_crops():
     return np.load(GOLDEN / "image_crops.npz")
+
+
+@pytest.fixture(scope="session")
+def image_large():
+    """(stem, uint8 [2999, 4499]) — the reference's largest test image."""
+    blob = np.load(GOLDEN / "image_large_input.npz")
+    stem = list(blob.keys())[0]
+    return stem, blob[stem]
+
+
+@pytest.fixture(scope="session")
+def compare_rows():
+    """Per-case metrics and summaries computed by the reference's own report
+    code on its own outputs (tests/golden/make_golden_compare.py)."""
+    return json.loads((GOLDEN / "compare_rows.json").read_text())

@@ -314,3 +314,61 @@ def test_ideal_fast_kernel_bit_identical():
         buf, body = shard.scatter_segment(x, p, "cuda")
         y = firgpu.fir1d_ideal(body, h, halo_left_valid=p.before, halo_right_valid=p.after)
         assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])
+
+
+def test_largest_reference_image_by_hash(image_large, manifest):
+    """4499 x 2999 (odd width, unaligned pitch): all 8 fixed and 8 ideal files
+    of the reference pipeline, by SHA-256 — with the other six images
+    (test_gpu_fir1d_fixed.py, above) the GPU path reproduces the complete
+    output set of `python pipeline_fir_1d.py`."""
+    from fir_1d.sim.vector.gen_fixed_output import _run_fixed_rowwise
+    from fir_1d.sim.vector.gen_ideal_output import _run_ideal_rowwise
+    stem, x = image_large
+    for tap in ("3tap", "5tap"):
+        for name, h in manifest[f"coeff_{tap}"].items():
+            assert sha(_run_fixed_rowwise(x, h, frac_bits=12, acc_bits=32, coeff_bits=16)) == manifest["fixed"][f"{stem}__{name}_{tap}"], (name, tap)
+            assert sha(_run_ideal_rowwise(x, h)) == manifest["ideal"][f"{stem}__{name}_{tap}"], (name, tap)
+
+
+def test_published_accuracy_tables_from_inputs_alone(tmp_path, images_inputs, image_large, compare_rows):
+    """SURVEY 8(f) #2 end to end: the fused compare path on the 7 input images
+    reproduces every row the reference's report code computes from its saved
+    ideal / fixed files, and the aggregate numbers printed in the reference's
+    docs (fir_1d/docs/fir_1d_3tap_compare_analysis_v1.md:44-83,
+    fir_1d_5tap_compare_analysis_v1.md:44-85, fir_1d_fixed_3tap_vs_5tap_comparison_v1.md:20-21)."""
+    from fir_1d.sim.vector import gen_fused_compare as fused
+    for stem in images_inputs.keys():
+        np.save(tmp_path / f"{stem}_x_u8.npy", images_inputs[stem])
+    np.save(tmp_path / f"{image_large[0]}_x_u8.npy", image_large[1])
+    out = {}
+    for tap in ("3", "5"):
+        rows = fused.fused_compare_rows(tmp_path, tap)
+        want_rows = compare_rows[f"{tap}tap"]["rows"]
+        assert [r["key"] for r in rows] == [w["key"] for w in want_rows] and len(rows) == 28
+        for r, w in zip(rows, want_rows):
+            assert (r["height"], r["width"], r["num_samples"]) == (w["height"], w["width"], w["num_samples"])
+            for key in ("max_abs_err", "sat_low_ratio", "sat_high_ratio", "clip_needed_ratio"):
+                assert r[key] == w[key], (r["key"], key)
+            for key in ("mae", "rmse", "mean_err", "sat_ratio"):
+                assert r[key] == pytest.approx(w[key], rel=1e-10, abs=1e-13), (r["key"], key)
+        summary = fused.summarize(rows)
+        for key, v in compare_rows[f"{tap}tap"]["summary"].items():
+            if key in summary:
+                assert summary[key] == pytest.approx(v, rel=1e-10), key
+        n_total = sum(r["num_samples"] for r in rows)
+        by_coeff = {c: float(np.mean([r["rmse"] for r in rows if r["coeff_name"] == c])) for c in ("edge", "moving_avg", "sharpen", "simple_lp")}
+        out[tap] = dict(summary=summary, w_mae=sum(r["num_samples"] * r["mae"] for r in rows) / n_total,
+                        w_rmse=sum(r["num_samples"] * r["rmse"] for r in rows) / n_total, by_coeff=by_coeff,
+                        worst=max(rows, key=lambda r: r["rmse"]))
+    r4 = lambda v: round(v, 4)
+    s3, s5 = out["3"], out["5"]
+    assert (r4(s3["summary"]["avg_mae"]), r4(s3["summary"]["avg_rmse"]), r4(s3["summary"]["avg_mean_err"]), s3["summary"]["max_max_abs_err"]) == (2.4078, 5.8063, 2.2903, 255.0)
+    assert (r4(s3["w_mae"]), r4(s3["w_rmse"])) == (0.6592, 2.6526)
+    assert {k: r4(v) for k, v in s3["by_coeff"].items()} == {"edge": 21.9354, "moving_avg": 0.2432, "sharpen": 0.7780, "simple_lp": 0.2686}
+    assert s3["worst"]["key"] == "case_004_img_005_64x64_noise_gray__edge" and r4(s3["worst"]["rmse"]) == 36.4074
+    assert (r4(s5["summary"]["avg_mae"]), r4(s5["summary"]["avg_rmse"]), r4(s5["summary"]["avg_mean_err"]), s5["summary"]["max_max_abs_err"]) == (1.1302, 2.9380, 0.8871, 118.0625)
+    assert (r4(s5["w_mae"]), r4(s5["w_rmse"])) == (0.3243, 1.2739)
+    assert {k: r4(v) for k, v in s5["by_coeff"].items()} == {"edge": 8.1020, "moving_avg": 0.2570, "sharpen": 3.1345, "simple_lp": 0.2586}
+    assert s5["worst"]["key"] == "case_004_img_005_64x64_noise_gray__edge" and r4(s5["worst"]["rmse"]) == 13.4034
+    assert round(100 * (s5["summary"]["avg_mae"] / s3["summary"]["avg_mae"] - 1), 2) == -53.06
+    assert round(100 * (s5["summary"]["avg_rmse"] / s3["summary"]["avg_rmse"] - 1), 2) == -49.40

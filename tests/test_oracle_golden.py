@@ -185,3 +185,24 @@ def test_parametrised_oracle_reduces_to_reference_at_defaults(golden_cases):
             a = opy.fir1d_fixed(x.tolist(), h, 12, 32, 16, centre=centre, in_range=rng_in, out_range=rng_out)
             b = onp.fir1d_fixed(x, h, 12, 32, 16, centre=centre, in_range=rng_in, out_range=rng_out, out_dtype=np.int64)
             assert np.array_equal(np.asarray(a, dtype=np.int64), b), (centre, rng_in, rng_out)
+
+
+def test_largest_image_by_hash(image_large, manifest):
+    """The 4499x2999 case in full: with it, the oracle reproduces all 56 fixed
+    and 56 ideal output files of the reference pipeline."""
+    stem, x = image_large
+    assert sha(x) == manifest["inputs"][stem]["sha256"]
+    for tap, name, h in _coeffs(manifest):
+        hq = onp.quantize_taps(h, 12, 16)
+        assert sha(c_oracle.fir1d_fixed(x, hq, 12, 32, threads=8)) == manifest["fixed"][f"{stem}__{name}_{tap}"]
+        assert sha(c_oracle.fir1d_ideal(x, h, threads=8)) == manifest["ideal"][f"{stem}__{name}_{tap}"]
+
+
+def test_reference_report_numbers_are_the_published_ones(compare_rows):
+    """compare_rows.json (reference code on reference outputs) carries the
+    accuracy tables the reference's docs publish
+    (fir_1d/docs/fir_1d_{3,5}tap_compare_analysis_v1.md)."""
+    s3, s5 = compare_rows["3tap"]["summary"], compare_rows["5tap"]["summary"]
+    assert s3["num_cases"] == s5["num_cases"] == 28 and s3["num_samples_total"] == 67_975_252
+    assert (round(s3["avg_mae"], 4), round(s3["avg_rmse"], 4), round(s3["avg_mean_err"], 4), s3["max_max_abs_err"]) == (2.4078, 5.8063, 2.2903, 255.0)
+    assert (round(s5["avg_mae"], 4), round(s5["avg_rmse"], 4), round(s5["avg_mean_err"], 4), s5["max_max_abs_err"]) == (1.1302, 2.9380, 0.8871, 118.0625)
