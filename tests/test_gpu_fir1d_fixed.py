@@ -146,7 +146,7 @@ def test_generic_kernel_serves_what_staged_declines(fg, torch):
     cases = [
         (12, 16, 16, [0.9, -0.7, 0.8, 0.3, -0.2]),        # acc_bits wrap is live
         (28, 32, 32, [7.5, -7.5, 0.001]),                 # 32-bit taps, wrap live
-        (12, 32, 16, rng.uniform(-0.2, 0.2, size=33).tolist()),   # long filter
+        (12, 32, 16, rng.uniform(-0.1, 0.1, size=70).tolist()),   # longer than the largest staged bucket (65)
         (12, 20, 16, [1.0]),                              # SURVEY 8(c)5 wrap case
         (3, 12, 8, [7.0, -6.5, 3.25, 1.0]),               # tiny frac_bits, 8-bit taps, wrap live
         (30, 64, 32, [0.4, 0.3]),                         # frac_bits beyond the packed path
@@ -354,3 +354,32 @@ def test_wide_signed_int16_fast_path(fg, torch):
     y = fg.fir1d_fixed(torch.from_numpy(loud).cuda(), [0.999, 0.999, 0.999], 15, 32, 16, in_range=full, out_range=full)
     assert _lib.last_path() == _lib.PATH_GENERIC            # 32767 * 3 * 32735 > 2^31: wrap is live, int64 kernel
     assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(loud, [0.999, 0.999, 0.999], 15, 32, 16, in_range=full, out_range=full, out_dtype=np.int16))
+
+
+def test_long_filters_run_in_staged_buckets(fg, torch):
+    """10..65 taps: served by the staged kernel through zero-padded tap-count
+    buckets (13/17/25/33/49/65) that keep the centre tap in place — bit-exact,
+    even and odd lengths, both containers, tile edges and shard halos."""
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(88)
+    for n_taps in (10, 11, 13, 14, 16, 17, 21, 32, 33, 40, 48, 49, 63, 64, 65):
+        h = (rng.uniform(-1, 1, size=n_taps) / n_taps).tolist()
+        for dtype in (np.uint8, np.int16):
+            for frac in (15, 12):
+                for n in (1, 50, 4095, 16384, 70_001):
+                    x = signal(rng, n, dtype)
+                    y = fg.fir1d_fixed(torch.from_numpy(x).cuda(), h, frac, 32, 16, out_dtype=dtype)
+                    assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, dtype, frac, n)
+                    assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h, frac, 32, 16, out_dtype=dtype)), (n_taps, dtype, frac, n)
+    h = (rng.uniform(-1, 1, size=31) / 31).tolist()
+    x = signal(rng, 5 * 9000, np.int16).reshape(5, 9000)
+    assert np.array_equal(fg.fir1d_fixed(torch.from_numpy(x).cuda(), h, 15, 32, 16).cpu().numpy(), onp.fir1d_fixed(x, h, 15, 32, 16))
+    sig = signal(rng, 150_000, np.int16)
+    want = onp.fir1d_fixed(sig, h, 15, 32, 16, out_dtype=np.int16)
+    for p in shard.plan_segments(sig.size, 3, 31, 1, align=4096):
+        buf, body = shard.scatter_segment(sig, p, "cuda")
+        y = fg.fir1d_fixed(body, h, 15, 32, 16, out_dtype=np.int16, halo_left_valid=p.before, halo_right_valid=p.after)
+        assert _lib.last_path() == _lib.PATH_STAGED
+        assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])
+    host = fg.fir1d_fixed(sig, h, 15, 32, 16, out_dtype=np.int16)
+    assert np.array_equal(host, want)

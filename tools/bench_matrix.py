@@ -104,9 +104,13 @@ def main():
             h = (np.ones(L) / (2 * L)).tolist()
             s = timed(lambda: firgpu.fir1d_fixed(x, h, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
             report(f"stream 2^28 i16->i16 {L}tap q1.15", s, n, 4)
-        h33 = (np.ones(33) / 66).tolist()
-        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], h33, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 26], validate=False), 5)
-        report("stream 2^26 i16->i16 33tap (generic kernel)", s, 1 << 26, 4)
+        for L in (13, 17, 33, 65):
+            hl = (np.ones(L) / (2 * L)).tolist()
+            s = timed(lambda: firgpu.fir1d_fixed(x, hl, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^28 i16->i16 {L}tap q1.15 (long-filter bucket)", s, n, 4)
+        h70 = (np.ones(70) / 140).tolist()
+        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], h70, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 26], validate=False), 5)
+        report("stream 2^26 i16->i16 70tap (generic kernel)", s, 1 << 26, 4)
         del x, y
     if "batched" in cases:
         for rows, cols in ((8192, 1 << 20), (8192, 1_000_000), (1 << 16, 4096), (1 << 20, 256)):

@@ -9,7 +9,7 @@
 
 namespace firgpu {
 
-constexpr int kFastPlanMaxTaps = 32;
+constexpr int kFastPlanMaxTaps = 65;
 
 struct FastPlan {
     bool ok = false;

@@ -36,18 +36,33 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     int mac = mac_mode();
     if (mac == 1 && !(a.n_taps == 5 && a.dilation == 1 && n_filters == 1)) mac = 0;
     if (a.n_taps > kMaxFastTaps) return 0;
+    // 10..65 taps: zero-pad to the next bucket, keeping the centre tap where it is
+    // (output n reads x[n - (k - L/2)], so the padded filter must keep h[L/2] at LB/2).
+    int n_taps = a.n_taps, bucket = 0;
+    int32_t padded[kMaxFastTaps];
+    const int32_t *taps_in = hq_host;
+    if (a.n_taps > kMaxWideTaps) {
+        if (n_filters != 1 || a.dilation != 1 || a.in_dtype != a.out_dtype) return 0;
+        mac = 0;
+        for (int b : kLongBuckets)
+            if (!bucket && b >= a.n_taps) bucket = b;
+        const int off = bucket / 2 - a.n_taps / 2;
+        for (int k = 0; k < bucket; ++k) padded[k] = (k >= off && k < off + a.n_taps) ? hq_host[k - off] : 0;
+        taps_in = padded;
+        n_taps = bucket;
+    }
     const int tap_limit = mac == 0 ? 32767 : 0x7fffffff;
     // every tap set must be provably exact in int32, and all of them share one post mode
     FastPlan plans[kMaxFilters];
     bool all_hi16 = true;
     for (int f = 0; f < n_filters; ++f) {
-        plans[f] = plan_fast(hq_host + (size_t)f * a.n_taps, a.n_taps, a.frac_bits, a.acc_bits, tap_limit);
+        plans[f] = plan_fast(taps_in + (size_t)f * n_taps, n_taps, a.frac_bits, a.acc_bits, tap_limit);
         if (!plans[f].ok) return 0;
         all_hi16 = all_hi16 && plans[f].hi16;
     }
     if (!all_hi16) {
         for (int f = 0; f < n_filters; ++f) {
-            plans[f] = plan_fast(hq_host + (size_t)f * a.n_taps, a.n_taps, a.frac_bits, a.acc_bits, tap_limit, false);
+            plans[f] = plan_fast(taps_in + (size_t)f * n_taps, n_taps, a.frac_bits, a.acc_bits, tap_limit, false);
             if (!plans[f].ok) return 0;
         }
     }
@@ -72,8 +87,11 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     const int out_align = out_vec > 16 ? 16 : out_vec;
     p.y_vec_ok = ((uintptr_t)a.y % out_align == 0) && (a.rows == 1 || (a.ld_y * os) % out_align == 0) &&
                  (n_filters == 1 || (filter_stride_y * os) % out_align == 0);
-    for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, a.n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
-    for (int k = 0; k < a.n_taps; ++k) p.hq[k] = f0.taps[k];
+    for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
+    for (int k = 0; k < n_taps && k < kMaxWideTaps; ++k) p.hq[k] = f0.taps[k];
+    if (bucket)
+        return a.in_dtype == FIRGPU_U8 ? launch_staged_long_u8(p, bucket, f0.hi16, a.stream)
+                                       : launch_staged_long_i16(p, bucket, f0.hi16, a.stream);
 
     if (a.in_dtype == FIRGPU_U8) {
         return a.out_dtype == FIRGPU_U8
@@ -98,7 +116,7 @@ int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_hos
     if (a.in_dtype != FIRGPU_I16 || a.out_dtype != FIRGPU_I16) return 0;
     if (a.dilation != 1 && a.dilation != 2) return 0;
     if (a.dilation == 2 && ((a.cols | a.halo_left | a.halo_right) & 1)) return 0;
-    if (a.n_taps > kMaxFastTaps || (a.centre >= 0 && a.centre != a.n_taps / 2)) return 0;
+    if (a.n_taps > kMaxWideTaps || (a.centre >= 0 && a.centre != a.n_taps / 2)) return 0;
     if (a.frac_bits < 1 || a.frac_bits > 30) return 0;
     if (a.in_lo < -32768 || a.in_hi > 32767 || a.out_lo < -32768 || a.out_hi > 32767) return 0;
     const char *force = getenv("FIRGPU_FORCE_GENERIC");

@@ -54,8 +54,10 @@ template <int THREADS, int SUB, int STAGES, int MINBLOCKS, int CTAS_PER_SM> stru
     static constexpr int kMinBlocks = MINBLOCKS;           // __launch_bounds__ register cap
     static constexpr int kCtasPerSm = CTAS_PER_SM;         // persistent CTAs per SM (<= occupancy)
     static constexpr int kTileBytes = THREADS * kChunk * SUB;
-    static constexpr int kStageBytes = ((kTileBytes + 2 * kPad + 127) / 128) * 128;
-    static constexpr int kSmemBytes = STAGES * kStageBytes + STAGES * 8;
+    // a stage = tile + a halo pad of PADB bytes on both sides (16 for <= 9 taps, more for long filters)
+    __host__ __device__ static constexpr int stage_bytes(int padb) { return ((kTileBytes + 2 * padb + 127) / 128) * 128; }
+    __host__ __device__ static constexpr int smem_bytes(int padb) { return STAGES * stage_bytes(padb) + STAGES * 8; }
+    static constexpr int kSmemBytes = STAGES * (((kTileBytes + 2 * kPad + 127) / 128) * 128) + STAGES * 8;   // 16-byte pads
 };
 
 // Per-container choice for long rows (HBM sweep on B200, 2^28-sample stream, 5 taps;
@@ -73,8 +75,9 @@ template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<256, 4, 2, 2, 2>
 // Rows shorter than two long-row tiles: 8 KiB tiles, three CTAs per SM.
 using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
 
-constexpr int kMaxFastTaps = 9;
-constexpr int kMaxPairs = 5;
+constexpr int kMaxFastTaps = 65;                // dp2a datapath (taps > 9 run in zero-padded buckets, see launch_long)
+constexpr int kMaxWideTaps = 9;                 // IMAD / wide datapaths
+constexpr int kMaxPairs = 33;
 constexpr int kMaxFilters = 4;                 // tap sets applied to one staged input (multi-filter mode)
 
 struct StagedParams {
@@ -91,7 +94,7 @@ struct StagedParams {
     long long filter_stride_y;                 // elements between the outputs of consecutive tap sets
     uint32_t cp_even[kMaxFilters][kMaxPairs];  // dp2a tap pairs, window starting on an even sample
     uint32_t cp_odd[kMaxFilters][kMaxPairs];   // ... on an odd sample
-    int32_t hq[kMaxFastTaps];                  // IMAD / wide mode taps
+    int32_t hq[kMaxWideTaps];                  // IMAD / wide mode taps
     uint32_t in_lo2, in_hi2, out_lo2, out_hi2; // wide mode: clamp bounds, each duplicated into both 16-bit lanes
 };
 
@@ -180,6 +183,34 @@ __device__ __forceinline__ void store_v2(void *ptr, uint32_t a, uint32_t b)
 #endif
 }
 
+// NW 32-bit words ending at a 16-byte boundary (left halo: the unaligned remainder comes first).
+template <int NW> __device__ __forceinline__ void lds_before(uint32_t end_addr, uint32_t *dst)
+{
+    constexpr int R = NW % 4, Q = NW / 4;
+    const uint32_t a = end_addr - NW * 4;
+    if constexpr (R == 1) lds_words<1>(a, dst);
+    if constexpr (R == 2) lds_words<2>(a, dst);
+    if constexpr (R == 3) {
+        lds_words<1>(a, dst);
+        lds_words<2>(a + 4, dst + 1);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) lds_words<4>(a + R * 4 + q * 16, dst + R + q * 4);
+}
+// NW 32-bit words starting at a 16-byte boundary (right halo).
+template <int NW> __device__ __forceinline__ void lds_after(uint32_t addr, uint32_t *dst)
+{
+    constexpr int R = NW % 4, Q = NW / 4;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) lds_words<4>(addr + q * 16, dst + q * 4);
+    if constexpr (R == 1) lds_words<1>(addr + Q * 16, dst + Q * 4);
+    if constexpr (R == 2) lds_words<2>(addr + Q * 16, dst + Q * 4);
+    if constexpr (R == 3) {
+        lds_words<2>(addr + Q * 16, dst + Q * 4);
+        lds_words<1>(addr + Q * 16 + 8, dst + Q * 4 + 2);
+    }
+}
+
 __host__ __device__ constexpr long long floor_div(long long a, long long b)
 {
     return a >= 0 ? a / b : -((-a + b - 1) / b);
@@ -200,8 +231,8 @@ template <typename InT, int L, int DIL> struct Geo {
     static constexpr int NB = (HL4 + S + HR4) / 4;        // byte-quads per stream
     static constexpr int NPE = (L + 1) / 2;
     static constexpr int NPO = L / 2 + 1;
-    static constexpr int PADS = kPad / ES;        // scalars per staged pad
-    static_assert(HLB <= kPad && HRB <= kPad, "halo exceeds the staged pad");
+    static constexpr int PADB = ((HLB > HRB ? HLB : HRB) + 15) / 16 * 16 < kPad ? kPad : ((HLB > HRB ? HLB : HRB) + 15) / 16 * 16;
+    static constexpr int PADS = PADB / ES;        // scalars per staged pad
     static_assert(L >= 1 && L <= kMaxFastTaps, "tap count outside the staged kernel's range");
 };
 
@@ -426,7 +457,7 @@ __global__ void __launch_bounds__(C::kThreads, C::kMinBlocks)
 fir1d_staged_kernel(const __grid_constant__ StagedParams p)
 {
     using G = Geo<InT, L, DIL>;
-    constexpr int kThreads = C::kThreads, kSub = C::kSub, kStages = C::kStages, kStageBytes = C::kStageBytes;
+    constexpr int kThreads = C::kThreads, kSub = C::kSub, kStages = C::kStages, kStageBytes = C::stage_bytes(G::PADB);
     constexpr int TS = C::kTileBytes / G::ES;      // scalars per tile
     constexpr int ES = G::ES;
     constexpr int OS = sizeof(OutT);
@@ -476,7 +507,7 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
     advance_tile(c_row, c_tcol, blockIdx.x, tpr);
     int stage = 0;
     uint32_t phase_bits = 0;
-    const uint32_t lane_off = kPad + tid * kChunk;
+    const uint32_t lane_off = G::PADB + tid * kChunk;
     for (long long i = 0; i < n_my; ++i) {
         const TilePlan t = plan_tile<G, TS>(p, c_row, c_tcol);
         const long long g0 = t.col0 - G::PADS;
@@ -507,9 +538,9 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
 #pragma unroll
         for (int u = 0; u < kSub; ++u) {
             const uint32_t a = st_base + lane_off + u * (kThreads * kChunk);
-            lds_words<G::HLB / 4>(a - G::HLB, &raw[u][0]);
+            lds_before<G::HLB / 4>(a, &raw[u][0]);
             lds_words<4>(a, &raw[u][G::HLB / 4]);
-            lds_words<G::HRB / 4>(a + kChunk, &raw[u][G::HLB / 4 + 4]);
+            lds_after<G::HRB / 4>(a + kChunk, &raw[u][G::HLB / 4 + 4]);
         }
         __syncthreads();
         if (tid == 0 && i + kStages < n_my) issue();
@@ -566,6 +597,7 @@ template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, in
 int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
 {
     auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, HI16, MAC, NF>;
+    constexpr int kSmem = C::smem_bytes(Geo<InT, L, DIL>::PADB);
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -574,9 +606,9 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
     {
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 64 && ctas_per_sm[dev] == 0) {
-            FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+            FIRGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
             int n = 0;
-            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::kThreads, C::kSmemBytes));
+            FIRGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::kThreads, kSmem));
             if (C::kCtasPerSm > 0 && n > C::kCtasPerSm) n = C::kCtasPerSm;
             ctas_per_sm[dev] = n < 1 ? 1 : n;
         }
@@ -594,7 +626,7 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
     p.total_tiles = p.tiles_per_row * p.rows;
     long long grid = (long long)sms * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, stream>>>(p);
+    kern<<<(unsigned)grid, C::kThreads, kSmem, stream>>>(p);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
@@ -663,6 +695,27 @@ int launch_dil(const StagedParams &p, int n_taps, int dilation, bool hi16, int m
     return 0;
 }
 
+
+// Long filters (10..65 taps): the same kernel, instantiated for a few tap-count
+// buckets; the host zero-pads the taps to the bucket (keeping the centre) —
+// zero taps cost dp2a slots but no accuracy.  8 KiB tiles, two CTAs per SM.
+using LongTapCfg = Cfg<256, 2, 2, 1, 2>;
+constexpr int kLongBuckets[] = {13, 17, 25, 33, 49, 65};
+template <typename T>
+int launch_long(const StagedParams &p, int bucket, bool hi16, cudaStream_t s)
+{
+    switch (bucket) {
+    case 13: return hi16 ? launch_cfg<LongTapCfg, T, T, 13, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 13, 1, false, 0>(p, s);
+    case 17: return hi16 ? launch_cfg<LongTapCfg, T, T, 17, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 17, 1, false, 0>(p, s);
+    case 25: return hi16 ? launch_cfg<LongTapCfg, T, T, 25, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 25, 1, false, 0>(p, s);
+    case 33: return hi16 ? launch_cfg<LongTapCfg, T, T, 33, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 33, 1, false, 0>(p, s);
+    case 49: return hi16 ? launch_cfg<LongTapCfg, T, T, 49, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 49, 1, false, 0>(p, s);
+    case 65: return hi16 ? launch_cfg<LongTapCfg, T, T, 65, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 65, 1, false, 0>(p, s);
+    default: return 0;
+    }
+}
+int launch_staged_long_u8(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
+int launch_staged_long_i16(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
 
 // One translation unit per (input, output) container pair instantiates these
 // (fir1d_staged_inst.cu compiled four times), which keeps the build parallel.

@@ -1,0 +1,14 @@
+// Instantiates the long-filter buckets of the staged 1-D kernel for ONE container
+// (-DFIRGPU_LONG_T=... -DFIRGPU_LONG_NAME=...).
+#include "fir1d_staged.cuh"
+
+namespace firgpu {
+namespace staged {
+
+int FIRGPU_LONG_NAME(const StagedParams &p, int bucket, bool hi16, cudaStream_t s)
+{
+    return launch_long<FIRGPU_LONG_T>(p, bucket, hi16, s);
+}
+
+}  // namespace staged
+}  // namespace firgpu
