@@ -6,12 +6,14 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace firgpu {
@@ -204,13 +206,50 @@ int copy_rows_async(void *dst, size_t dpitch, const void *src, size_t spitch, si
     return 0;
 }
 
+// Staging copies between pageable user memory and the pinned slot buffers run on
+// several host threads: one core moves about 10 GB/s, PCIe wants 50.
+int staging_threads()
+{
+    static int n = 0;
+    if (!n) {
+        const char *e = getenv("FIRGPU_STAGING_THREADS");
+        const int forced = e ? atoi(e) : 0;
+        const int hw = (int)std::thread::hardware_concurrency();
+        n = forced >= 1 ? forced : std::max(1, std::min(8, hw / 2));
+    }
+    return n;
+}
+
+void copy_rows_serial(char *dst, size_t dpitch, const char *src, size_t spitch, size_t row_bytes, size_t r0, size_t r1)
+{
+    for (size_t r = r0; r < r1; ++r) memcpy(dst + r * dpitch, src + r * spitch, row_bytes);
+}
+
 void copy_rows_host(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t nr)
 {
-    if (dpitch == row_bytes && spitch == row_bytes) {
-        memcpy(dst, src, row_bytes * nr);
+    char *d = (char *)dst;
+    const char *s = (const char *)src;
+    if (nr == 1 || (dpitch == row_bytes && spitch == row_bytes)) {   // one contiguous block: treat it as rows of 1 MiB
+        const size_t total = row_bytes * nr;
+        row_bytes = dpitch = spitch = (size_t)1 << 20;
+        nr = total / row_bytes;
+        const size_t tail = total - nr * row_bytes;
+        if (tail) memcpy(d + nr * row_bytes, s + nr * row_bytes, tail);
+    }
+    const size_t total = row_bytes * nr;
+    int threads = staging_threads();
+    if (total < ((size_t)4 << 20) || nr < 2) threads = 1;
+    if ((size_t)threads > nr) threads = (int)nr;
+    if (threads <= 1) {
+        copy_rows_serial(d, dpitch, s, spitch, row_bytes, 0, nr);
         return;
     }
-    for (size_t r = 0; r < nr; ++r) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, row_bytes);
+    std::vector<std::thread> pool;
+    pool.reserve(threads - 1);
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back(copy_rows_serial, d, dpitch, s, spitch, row_bytes, nr * t / threads, nr * (t + 1) / threads);
+    copy_rows_serial(d, dpitch, s, spitch, row_bytes, 0, nr / threads);
+    for (auto &th : pool) th.join();
 }
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -265,6 +304,9 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if ((rc = ctx_reserve(c, (size_t)max_in, (size_t)max_out, !x_pinned, !y_pinned))) return rc;
 
+    const bool trace = getenv("FIRGPU_TRACE") != nullptr;
+    double t_sync = 0, t_out = 0, t_in = 0, t_enq = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     struct Pending {
         bool busy = false;
         Piece p;
@@ -272,7 +314,10 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     } pending[kSlots];
     auto finalize = [&](int s) -> int {
         if (!pending[s].busy) return 0;
+        const double t0 = now();
         FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
+        t_sync += now() - t0;
+        const double t1 = now();
         if (!y_pinned) {
             const Piece &p = pending[s].p;
             for (int f = 0; f < n_out; ++f)
@@ -280,6 +325,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
                                (char *)c->p_out[s] + (size_t)f * pending[s].ldd_y * p.nr * os,
                                (size_t)pending[s].ldd_y * os, (size_t)p.nc * os, (size_t)p.nr);
         }
+        t_out += now() - t1;
         pending[s].busy = false;
         return 0;
     };
@@ -287,6 +333,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     for (size_t k = 0; k < pieces.size(); ++k) {
         const int s = (int)(k % kSlots);
         if ((rc = finalize(s))) return rc;
+        const double t2 = now();
         const Piece &p = pieces[k];
         const int64_t lead = round_up(p.before, q_in);                 // aligned offset of the segment
         const int64_t span = p.before + p.nc + p.after;                // scalars copied per row
@@ -300,10 +347,12 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
                 return rc;
         } else {
             copy_rows_host((char *)c->p_in[s], (size_t)span * es, src, (size_t)ld_x * es, (size_t)span * es, (size_t)p.nr);
+            t_in += now() - t2;
             if ((rc = copy_rows_async(d_first, (size_t)ldd_x * es, c->p_in[s], (size_t)span * es, (size_t)span * es,
                                       (size_t)p.nr, cudaMemcpyHostToDevice, c->stream[s])))
                 return rc;
         }
+        const double t3 = now();
         rc = run((const char *)c->d_in[s] + lead * es, c->d_out[s], p.nr, p.nc, ldd_x, ldd_y, p.before, p.after,
                  c->stream[s]);
         if (rc) return rc;
@@ -318,9 +367,13 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
         pending[s].busy = true;
         pending[s].p = p;
         pending[s].ldd_y = ldd_y;
+        t_enq += now() - t3;
     }
     for (int s = 0; s < kSlots; ++s)
         if ((rc = finalize(s))) return rc;
+    if (trace)
+        fprintf(stderr, "[firgpu] pipeline_1d: %zu pieces, pinned in/out %d/%d, staging threads %d, sync %.2f ms, copy-out %.2f ms, copy-in %.2f ms, enqueue %.2f ms\n",
+                pieces.size(), (int)x_pinned, (int)y_pinned, staging_threads(), t_sync * 1e3, t_out * 1e3, t_in * 1e3, t_enq * 1e3);
     return 0;
 }
 
@@ -384,7 +437,7 @@ int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t h
                                       (size_t)nrows, cudaMemcpyHostToDevice, c->stream[s])))
                 return rc;
         } else {
-            memcpy(c->p_in[s], src, (size_t)(nrows * width * es));
+            copy_rows_host(c->p_in[s], (size_t)width * es, src, (size_t)width * es, (size_t)width * es, (size_t)nrows);
             if ((rc = copy_rows_async(c->d_in[s], (size_t)ldd_x * es, c->p_in[s], (size_t)width * es, (size_t)width * es,
                                       (size_t)nrows, cudaMemcpyHostToDevice, c->stream[s])))
                 return rc;
