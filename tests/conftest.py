@@ -25,6 +25,11 @@ for p in (str(ROOT), str(PKG)):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The tests need the in-tree library; a fresh checkout builds it once (nvcc cross-compiles without a GPU).
+    lib = PKG / "firgpu" / "libfirgpu.so"
+    if not lib.exists():
+        import subprocess
+        subprocess.run(["make", "-s", "-j8", "-C", str(PKG / "csrc")], check=True)
 
 
 def _has_gpu() -> bool:
