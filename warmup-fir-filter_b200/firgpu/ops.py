@@ -82,16 +82,19 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
-def _np_container(x, lo: int = 0, hi: int = 255) -> np.ndarray:
+def _np_container(x, lo: int = 0, hi: int = 255, raw: bool = False) -> np.ndarray:
     """Any host input -> C-contiguous array in one of the five containers the
     kernels read.  Integer types the kernels do not read are clamped here to
     the sample range [lo, hi] (rounding is the identity on integers,
-    fir_1d_ref.py:35-41)."""
+    fir_1d_ref.py:35-41); with ``raw`` (samples used as they are) they become
+    float64 instead."""
     a = np.asarray(x)
     if a.dtype == object:
         a = np.asarray(x, dtype=np.float64)
     if a.dtype in _NP_CODE:
         pass
+    elif raw:
+        a = a.astype(np.float64)
     elif a.dtype == np.bool_:
         a = a.astype(np.uint8)
     elif a.dtype == np.int8:
@@ -105,7 +108,7 @@ def _np_container(x, lo: int = 0, hi: int = 255) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
-def _torch_container(t):
+def _torch_container(t, lo: int = 0, hi: int = 255):
     import torch
     if t.dtype in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64):
         pass
@@ -114,7 +117,7 @@ def _torch_container(t):
     elif t.dtype == torch.int8:
         t = t.to(torch.int16)
     elif t.dtype in (torch.int64,):
-        t = t.clamp(0, 255).to(torch.uint8)
+        t = t.clamp(lo, hi).to(torch.uint8 if (lo >= 0 and hi <= 255) else torch.int16)
     elif t.dtype in (torch.float16, torch.bfloat16):
         t = t.to(torch.float32)
     else:
@@ -143,7 +146,7 @@ def _check_finite_torch(t) -> None:
             raise ValueError(f"Invalid x[{index}]={float(t.reshape(-1)[index])}: x must be finite.")
 
 
-def _cuda_rows(x, allow_copy: bool):
+def _cuda_rows(x, allow_copy: bool, lo: int = 0, hi: int = 255):
     """CUDA tensor -> (tensor to read, rows, cols, row pitch in elements).
     1-D tensors and 2-D tensors whose last axis is dense are read in place,
     pitch included (that is how a shard view of a wider buffer arrives);
@@ -159,7 +162,7 @@ def _cuda_rows(x, allow_copy: bool):
         return x, rows, cols, cols
     if not allow_copy:
         raise ValueError("this tensor would need a dtype/layout copy, which is not possible for in-place shard views")
-    t = _torch_container(x)
+    t = _torch_container(x, lo, hi)
     rows, cols = _rows_cols(t.shape)
     return t, rows, cols, cols
 
@@ -254,7 +257,7 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
         return out
     if _is_torch(x) and x.is_cuda:
         import torch
-        t, rows, cols, ld = _cuda_rows(x, allow_copy=not (halo_left_valid or halo_right_valid))
+        t, rows, cols, ld = _cuda_rows(x, not (halo_left_valid or halo_right_valid), *((ex[1], ex[2]) if ex else (0, 255)))
         y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
         _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
         if (y_rows, y_cols) != (rows, cols):
@@ -311,7 +314,9 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
         import torch
         if validate:
             _check_finite_torch(x)
-        t, rows, cols, ld = _cuda_rows(x, allow_copy=not (halo_left_valid or halo_right_valid))
+        if raw and x.dtype not in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64):
+            x = x.to(torch.float64)              # raw samples of an exotic dtype: exact in float64, never clamped
+        t, rows, cols, ld = _cuda_rows(x, not (halo_left_valid or halo_right_valid), *in_range)
         y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -326,7 +331,7 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
     if halo_left_valid or halo_right_valid:
         raise ValueError("halo_*_valid apply to device-resident shards only")
     was_torch = _is_torch(x)
-    a = _np_container(x.numpy() if was_torch else x, *in_range)
+    a = _np_container(x.numpy() if was_torch else x, *in_range, raw=raw)
     if validate:
         quant.check_samples_finite(a)
     rows, cols = _rows_cols(a.shape)
