@@ -318,13 +318,16 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
             x = x.to(torch.float64)              # raw samples of an exotic dtype: exact in float64, never clamped
         t, rows, cols, ld = _cuda_rows(x, not (halo_left_valid or halo_right_valid), *in_range)
         y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
+        if (y_rows, y_cols) != (rows, cols):
+            raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             if ex is None:
-                _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
+                _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, ld_y,
                                                 _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid, stream))
             else:
-                _lib.check(L.firgpu_fir1d_ideal_ex(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, cols,
+                _lib.check(L.firgpu_fir1d_ideal_ex(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, ld_y,
                                                    _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid,
                                                    *ex, stream))
         return y
@@ -441,6 +444,8 @@ def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8,
         ld = t.stride(-2) if t.dim() >= 2 else wid
         img_stride = t.stride(-3) if t.dim() >= 3 else hgt * ld
         y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        if not y.is_contiguous() or tuple(y.shape) != tuple(t.shape):
+            raise ValueError("out must be a contiguous tensor of the input's shape")
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir2d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, wid,
@@ -522,6 +527,8 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
         t = _torch_container(x)
         n, hgt, wid = _imgs(t.shape)
         y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        if not y.is_contiguous() or tuple(y.shape) != tuple(t.shape):
+            raise ValueError("out must be a contiguous tensor of the input's shape")
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, wid, wid,
