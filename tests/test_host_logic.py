@@ -261,3 +261,16 @@ def test_sharded_result_equals_whole_signal_on_cpu():
                 local = onp.fir1d_fixed(x[p.lo:p.hi], h, 15, 32, 16, dilation=dil)
                 got[p.start:p.stop] = local[p.before:p.before + p.size]
             assert np.array_equal(got, want)
+
+
+def test_host_out_buffers_are_validated_before_the_library_writes():
+    x = np.arange(8, dtype=np.uint8)
+    for bad in (np.zeros(7, np.uint8), np.zeros(8, np.int16), np.zeros(16, np.uint8)[::2], np.zeros((2, 4), np.uint8)):
+        with pytest.raises(ValueError, match="out must be a writable C-contiguous uint8 array of shape"):
+            ops.fir1d_fixed(x, [1.0], out=bad)
+    with pytest.raises(ValueError, match="float64 array of shape"):
+        ops.fir1d_ideal(x, [1.0], out=np.zeros(8, np.float32))
+    frozen = np.zeros(8, np.uint8)
+    frozen.setflags(write=False)
+    with pytest.raises(ValueError, match="writable"):
+        ops.fir1d_fixed(x, [1.0], out=frozen)

@@ -167,6 +167,19 @@ def _cuda_rows(x, allow_copy: bool, lo: int = 0, hi: int = 255):
     return t, rows, cols, cols
 
 
+def _host_out(out, shape, dtype):
+    """The caller's ``out`` (or a fresh array) for a host-buffer call: must be a
+    C-contiguous array / CPU tensor of exactly the expected shape and dtype,
+    because the library writes through its raw pointer."""
+    if out is None:
+        return np.empty(shape, dtype=dtype)
+    arr = out.numpy() if _is_torch(out) else out
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.dtype(dtype) or tuple(arr.shape) != tuple(shape) or not arr.flags["C_CONTIGUOUS"] \
+            or not arr.flags["WRITEABLE"]:
+        raise ValueError(f"out must be a writable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+    return arr
+
+
 def _rows_cols(shape) -> tuple[int, int]:
     if len(shape) == 0:
         raise ValueError("x must have at least one dimension")
@@ -278,8 +291,8 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
     was_torch = _is_torch(x)
     a = _np_container(x.numpy() if was_torch else x, *((ex[1], ex[2]) if ex else (0, 255)))
     rows, cols = _rows_cols(a.shape)
-    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
-    y_np = y.numpy() if _is_torch(y) else y
+    y_np = _host_out(out, a.shape, out_dtype)
+    y = out if out is not None else y_np
     if ex is None:
         _lib.check(L.firgpu_fir1d_fixed_host(a.ctypes.data, y_np.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols,
                                              cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, device))
@@ -338,7 +351,7 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
     if validate:
         quant.check_samples_finite(a)
     rows, cols = _rows_cols(a.shape)
-    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    y = _host_out(out, a.shape, out_dtype)
     if ex is None:
         _lib.check(L.firgpu_fir1d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, rows, cols, cols,
                                              cols, _taps_ptr(hh), hh.size, dilation, device))
@@ -457,7 +470,7 @@ def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8,
     was_torch = _is_torch(x)
     a = _np_container(x.numpy() if was_torch else x)
     n, hgt, wid = _imgs(a.shape)
-    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    y = _host_out(out, a.shape, out_dtype)
     _lib.check(L.firgpu_fir2d_fixed_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, n, hgt, wid,
                                          _taps_ptr(hq), kh, kw, frac_bits, acc_bits, device))
     if was_torch and out is None:
@@ -539,7 +552,7 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
     if validate:
         quant.check_samples_finite(a)
     n, hgt, wid = _imgs(a.shape)
-    y = out if out is not None else np.empty(a.shape, dtype=out_dtype)
+    y = _host_out(out, a.shape, out_dtype)
     _lib.check(L.firgpu_fir2d_ideal_host(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], out_code, n, hgt, wid,
                                          _taps_ptr(hh), kh, kw, device))
     if was_torch and out is None:
