@@ -249,6 +249,11 @@ def test_full_size_stream_properties(fg, torch):
         # interior of the window is independent of the window's own zero padding
         a, b = (0 if lo == 0 else 2), (xs.size if hi == n else xs.size - 2)
         assert np.array_equal(y[lo + a:lo + b].cpu().numpy(), want[a:b]), start
+    # ... and every one of the 2**28 outputs against the C oracle on all host cores
+    import os
+    full = c_oracle.fir1d_fixed(x.cpu().numpy(), hq, 15, 32, out_dtype=np.int16, threads=max(1, len(os.sched_getaffinity(0))))
+    assert np.array_equal(y.cpu().numpy(), full)
+    del full
     # range and DC-gain properties of a unity-gain low-pass over clamped pixels
     assert int(y.min()) >= 0 and int(y.max()) <= 255
     xc = x.clamp(0, 255)

@@ -152,6 +152,11 @@ def main():
             s = timed(lambda: firgpu.fir2d_fixed_q(img8, hq, 12, 32, out=out8), args.reps, warm=2)
             report(f"2d 16384^2 u8->u8 {tag} q4.12", s, 16384 * 16384, 2)
         del img, out, img8, out8
+        small8 = rand_i16(8192 * 8192).clamp(0, 255).to(torch.uint8).view(1, 8192, 8192)
+        outf = torch.empty((1, 8192, 8192), dtype=torch.float64, device="cuda")
+        s = timed(lambda: firgpu.fir2d_ideal(small8, k3, out=outf, validate=False), 3, warm=1)
+        report("2d ideal 8192^2 u8->f64 3x3 (generic kernel)", s, 8192 * 8192, 9)
+        del small8, outf
         batch = rand_i16(4 * 8192 * 8192).view(4, 8192, 8192)
         outb = torch.empty_like(batch)
         hq = quant.quantize_taps(np.asarray(k3), 12, 16)
