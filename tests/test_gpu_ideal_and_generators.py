@@ -80,6 +80,12 @@ def test_ideal_f32_within_stated_tolerance():
         assert np.max(np.abs(got.astype(np.float64) - want)) <= tol
         got64 = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h).cpu().numpy()
         assert np.array_equal(got64, want)
+        # even width: the fast kernel's float32 variant
+        from firgpu import _lib
+        xe = np.ascontiguousarray(x[:, :50_000])
+        got32 = firgpu.fir1d_ideal(torch.from_numpy(xe).cuda(), h, out_dtype=np.float32)
+        assert _lib.last_path() == _lib.PATH_STAGED and got32.dtype == torch.float32
+        assert np.max(np.abs(got32.cpu().numpy().astype(np.float64) - onp.fir1d_ideal(xe, h))) <= tol
         host = firgpu.fir1d_ideal(x, h)
         assert np.array_equal(host, want)
 

@@ -1,5 +1,5 @@
 // Fast path of the ideal (floating-point) 1-D model for uint8 / int16 inputs and
-// float64 output: fir_1d/model/python/fir_1d_ref.py:43-65, batched as
+// float64 (bit-identical) or float32 (tolerance) output: fir_1d/model/python/fir_1d_ref.py:43-65, batched as
 // fir_1d/sim/vector/gen_ideal_output.py:37-50.
 //
 // Bound: HBM, 9-10 bytes per sample (1-2 in, 8 out) — the output dominates.
@@ -21,24 +21,28 @@ namespace firgpu {
 namespace {
 
 constexpr int kThreadsI = 256;
-constexpr int kPairs = 4;                               // output pairs per thread
-constexpr int kTileI = kThreadsI * 2 * kPairs;          // 2048 outputs per CTA
 constexpr int kMaxFastIdealTaps = 9;
 
 template <int L> struct TapsF64 {
     double v[L];
 };
 
-template <typename InT, int L>
+template <typename F> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename InT, typename F, int L, int kPairs>   // kPairs output pairs per thread: 2 * 256 * kPairs outputs per CTA
 __global__ void __launch_bounds__(kThreadsI)
-fir1d_ideal_fast_kernel(const InT *__restrict__ x, double *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
+fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
                         int64_t ld_y, int64_t tiles_per_row, TapsF64<L> h, int64_t halo_left, int64_t halo_right)
 {
+    constexpr int kTileI = kThreadsI * 2 * kPairs;
     constexpr int hi = L / 2, lo = L - 1 - hi;
     constexpr int LEAD = lo + (lo & 1);                  // even, so that window starts stay 16-byte aligned
     constexpr int WIN = (LEAD + 2 + hi + 1) / 2 * 2;     // doubles read per output pair
     constexpr int SPAN = kTileI + LEAD + ((hi + 1) / 2) * 2;
-    __shared__ __align__(16) double xs[SPAN];
+    using V2 = typename Vec2<F>::type;
+    __shared__ __align__(16) F xs[SPAN];
 
     const int64_t tile = blockIdx.x;
     const int64_t row = tile / tiles_per_row;
@@ -47,57 +51,73 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, double *__restrict__ y, int64
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
 
     // samples [col0 - LEAD, col0 - LEAD + SPAN) -> float64 in shared memory
-    constexpr int PER = kTileI / kThreadsI;               // 8 body samples per thread
+    constexpr int PER = 8;                                // body samples per vector load
     const bool interior = col0 - LEAD >= vlo && col0 - LEAD + SPAN <= vhi &&
                           ((reinterpret_cast<uintptr_t>(xr + col0) & (PER * sizeof(InT) - 1)) == 0);
     if (interior) {
-        // one vector load of 8 samples per thread, converted in registers
-        const InT *src = xr + col0 + threadIdx.x * PER;
-        InT v[PER];
-        if constexpr (sizeof(InT) == 1) {
-            *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(src);
-        } else {
-            *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(src);
-        }
-        double *dst = &xs[LEAD + threadIdx.x * PER];
+        // vector loads of 8 samples, converted in registers
 #pragma unroll
-        for (int q = 0; q < PER; q += 2)
-            *reinterpret_cast<double2 *>(dst + q) = make_double2((double)prep_sample(v[q]), (double)prep_sample(v[q + 1]));
+        for (int b = 0; b < kTileI / (kThreadsI * PER); ++b) {
+            const int first = (b * kThreadsI + threadIdx.x) * PER;
+            const InT *src = xr + col0 + first;
+            InT v[PER];
+            if constexpr (sizeof(InT) == 1) {
+                *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(src);
+            } else {
+                *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(src);
+            }
+            F *dst = &xs[LEAD + first];
+#pragma unroll
+            for (int q = 0; q < PER; q += 2) {
+                V2 pair;
+                pair.x = (F)prep_sample(v[q]);
+                pair.y = (F)prep_sample(v[q + 1]);
+                *reinterpret_cast<V2 *>(dst + q) = pair;
+            }
+        }
         // the few samples on either side of the body
-        if (threadIdx.x < LEAD) xs[threadIdx.x] = (double)prep_sample(xr[col0 - LEAD + threadIdx.x]);
+        if (threadIdx.x < LEAD) xs[threadIdx.x] = (F)prep_sample(xr[col0 - LEAD + threadIdx.x]);
         if (threadIdx.x < SPAN - LEAD - kTileI)
-            xs[LEAD + kTileI + threadIdx.x] = (double)prep_sample(xr[col0 + kTileI + threadIdx.x]);
+            xs[LEAD + kTileI + threadIdx.x] = (F)prep_sample(xr[col0 + kTileI + threadIdx.x]);
     } else {
         for (int i = threadIdx.x; i < SPAN; i += kThreadsI) {
             const int64_t g = col0 - LEAD + i;
-            xs[i] = (g >= vlo && g < vhi) ? (double)prep_sample(xr[g]) : 0.0;
+            xs[i] = (g >= vlo && g < vhi) ? (F)prep_sample(xr[g]) : (F)0;
         }
     }
     __syncthreads();
 
-    double *yr = y + row * ld_y;
-    const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & 15) == 0);
+    F *yr = y + row * ld_y;
+    const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & (2 * sizeof(F) - 1)) == 0);
 #pragma unroll
     for (int j = 0; j < kPairs; ++j) {
         const int o = j * (2 * kThreadsI) + 2 * threadIdx.x;      // first output of the pair, inside the tile
         const int64_t n = col0 + o;
         if (n >= cols) break;
-        double w[WIN];
+        F w[WIN];
 #pragma unroll
         for (int q = 0; q < WIN; q += 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(&xs[o + q]);
+            const V2 v = *reinterpret_cast<const V2 *>(&xs[o + q]);
             w[q] = v.x;
             w[q + 1] = v.y;
         }
         // output n reads samples n + hi ... n - lo  <->  w[LEAD + hi - k], k = 0..L-1
-        double a0 = 0.0, a1 = 0.0;
+        F a0 = (F)0, a1 = (F)0;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
-            a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
+            if constexpr (sizeof(F) == 8) {          // the reference's float64: unfused multiply then add
+                a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
+                a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
+            } else {                                 // float32 datapath (same as the generic kernel's)
+                a0 = fmaf((float)h.v[k], w[LEAD + hi - k], a0);
+                a1 = fmaf((float)h.v[k], w[LEAD + hi - k + 1], a1);
+            }
         }
         if (n + 1 < cols && y_vec) {
-            *reinterpret_cast<double2 *>(yr + n) = make_double2(a0, a1);
+            V2 pair;
+            pair.x = a0;
+            pair.y = a1;
+            *reinterpret_cast<V2 *>(yr + n) = pair;
         } else {
             yr[n] = a0;
             if (n + 1 < cols) yr[n + 1] = a1;
@@ -105,19 +125,34 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, double *__restrict__ y, int64
     }
 }
 
-template <typename InT, int L>
-int run(const Fir1dArgs &a, const double *h_host)
+template <typename InT, typename F, int L, int kPairs>
+int run_pairs(const Fir1dArgs &a, const double *h_host)
 {
+    constexpr int kTileI = kThreadsI * 2 * kPairs;
     TapsF64<L> h;
     for (int k = 0; k < L; ++k) h.v[k] = h_host[k];
     const int64_t tiles_per_row = (a.cols + kTileI - 1) / kTileI;
     const int64_t total = tiles_per_row * a.rows;
     if (total > 0x7fffffffLL) return 0;
-    fir1d_ideal_fast_kernel<InT, L><<<(unsigned)total, kThreadsI, 0, a.stream>>>(
-        (const InT *)a.x, (double *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, h, a.halo_left, a.halo_right);
+    fir1d_ideal_fast_kernel<InT, F, L, kPairs><<<(unsigned)total, kThreadsI, 0, a.stream>>>(
+        (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
+}
+
+template <typename InT, int L>
+int run(const Fir1dArgs &a, const double *h_host)
+{
+    // rows long enough to fill the larger tile use it (tuning knob: FIRGPU_IDEAL_PAIRS=4|8)
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("FIRGPU_IDEAL_PAIRS");
+        forced = e ? atoi(e) : 0;
+    }
+    const bool big = forced ? forced == 8 : a.cols >= 16384;
+    if (a.out_dtype == FIRGPU_F32) return big ? run_pairs<InT, float, L, 8>(a, h_host) : run_pairs<InT, float, L, 4>(a, h_host);
+    return big ? run_pairs<InT, double, L, 8>(a, h_host) : run_pairs<InT, double, L, 4>(a, h_host);
 }
 
 template <typename InT>
@@ -142,7 +177,7 @@ int by_taps(const Fir1dArgs &a, const double *h)
 // 1 = served, 0 = not eligible (caller uses the generic kernel), else error.
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
 {
-    if (a.out_dtype != FIRGPU_F64 || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
+    if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
     if (!a.is_reference_model()) return 0;
     if ((a.ld_y & 1) && a.rows > 1) return 0;            // keeps every row's pair stores 16-byte aligned or uniformly scalar
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
