@@ -3,7 +3,8 @@
 // fir_1d/sim/vector/gen_ideal_output.py:37-50.
 //
 // Bound: HBM, 9-10 bytes per sample (1-2 in, 8 out) — the output dominates.
-// A CTA converts one tile of samples to float64 ONCE into shared memory
+// Persistent CTAs prefetch the next tile's samples into registers while the
+// current tile is filtered.  A CTA converts one tile of samples to float64 ONCE into shared memory
 // (round/clamp is the identity on integers, so conversion = clamp + cast),
 // then every thread produces pairs of adjacent outputs from 128-bit shared
 // loads and writes them with one 16-byte store, so a warp writes 512
@@ -34,94 +35,133 @@ template <> struct Vec2<float> { using type = float2; };
 template <typename InT, typename F, int L, int kPairs>   // kPairs output pairs per thread: 2 * 256 * kPairs outputs per CTA
 __global__ void __launch_bounds__(kThreadsI)
 fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
-                        int64_t ld_y, int64_t tiles_per_row, TapsF64<L> h, int64_t halo_left, int64_t halo_right)
+                        int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
+                        int64_t halo_right)
 {
     constexpr int kTileI = kThreadsI * 2 * kPairs;
     constexpr int hi = L / 2, lo = L - 1 - hi;
     constexpr int LEAD = lo + (lo & 1);                  // even, so that window starts stay 16-byte aligned
-    constexpr int WIN = (LEAD + 2 + hi + 1) / 2 * 2;     // doubles read per output pair
+    constexpr int WIN = (LEAD + 2 + hi + 1) / 2 * 2;     // samples read per output pair
     constexpr int SPAN = kTileI + LEAD + ((hi + 1) / 2) * 2;
+    constexpr int TAIL = SPAN - LEAD - kTileI;
+    constexpr int PER = 8;                               // body samples per vector load
+    constexpr int NV = kTileI / (kThreadsI * PER);       // vector loads per thread per tile
+    constexpr int VW = PER * sizeof(InT) / 4;            // 32-bit words per vector load
     using V2 = typename Vec2<F>::type;
     __shared__ __align__(16) F xs[SPAN];
-
-    const int64_t tile = blockIdx.x;
-    const int64_t row = tile / tiles_per_row;
-    const int64_t col0 = (tile - row * tiles_per_row) * kTileI;
-    const InT *xr = x + row * ld_x;
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
+    const int tid = threadIdx.x;
 
-    // samples [col0 - LEAD, col0 - LEAD + SPAN) -> float64 in shared memory
-    constexpr int PER = 8;                                // body samples per vector load
-    const bool interior = col0 - LEAD >= vlo && col0 - LEAD + SPAN <= vhi &&
-                          ((reinterpret_cast<uintptr_t>(xr + col0) & (PER * sizeof(InT) - 1)) == 0);
-    if (interior) {
-        // vector loads of 8 samples, converted in registers
+    // One tile's samples, prefetched into registers while the previous tile is
+    // being filtered (persistent CTA, register double buffering).
+    struct Prefetch {
+        int64_t row, col0;
+        bool interior;
+        uint32_t body[NV][VW];
+        InT left, right;
+    };
+    auto fetch = [&](int64_t tile, Prefetch &p) {
+        p.row = tile / tiles_per_row;
+        p.col0 = (tile - p.row * tiles_per_row) * kTileI;
+        const InT *xr = x + p.row * ld_x;
+        p.interior = p.col0 - LEAD >= vlo && p.col0 - LEAD + SPAN <= vhi &&
+                     ((reinterpret_cast<uintptr_t>(xr + p.col0) & (PER * sizeof(InT) - 1)) == 0);
+        if (p.interior) {
 #pragma unroll
-        for (int b = 0; b < kTileI / (kThreadsI * PER); ++b) {
-            const int first = (b * kThreadsI + threadIdx.x) * PER;
-            const InT *src = xr + col0 + first;
-            InT v[PER];
-            if constexpr (sizeof(InT) == 1) {
-                *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(src);
-            } else {
-                *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(src);
+            for (int b = 0; b < NV; ++b) {
+                const InT *src = xr + p.col0 + (b * kThreadsI + tid) * PER;
+                if constexpr (VW == 2) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(src);
+                    p.body[b][0] = v.x;
+                    p.body[b][1] = v.y;
+                } else {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+                    p.body[b][0] = v.x;
+                    p.body[b][1] = v.y;
+                    p.body[b][2] = v.z;
+                    p.body[b][3] = v.w;
+                }
             }
-            F *dst = &xs[LEAD + first];
-#pragma unroll
-            for (int q = 0; q < PER; q += 2) {
-                V2 pair;
-                pair.x = (F)prep_sample(v[q]);
-                pair.y = (F)prep_sample(v[q + 1]);
-                *reinterpret_cast<V2 *>(dst + q) = pair;
-            }
+            if (tid < LEAD) p.left = xr[p.col0 - LEAD + tid];
+            if (tid < TAIL) p.right = xr[p.col0 + kTileI + tid];
         }
-        // the few samples on either side of the body
-        if (threadIdx.x < LEAD) xs[threadIdx.x] = (F)prep_sample(xr[col0 - LEAD + threadIdx.x]);
-        if (threadIdx.x < SPAN - LEAD - kTileI)
-            xs[LEAD + kTileI + threadIdx.x] = (F)prep_sample(xr[col0 + kTileI + threadIdx.x]);
-    } else {
-        for (int i = threadIdx.x; i < SPAN; i += kThreadsI) {
-            const int64_t g = col0 - LEAD + i;
-            xs[i] = (g >= vlo && g < vhi) ? (F)prep_sample(xr[g]) : (F)0;
-        }
-    }
-    __syncthreads();
+    };
+    auto sample_of = [](const uint32_t (&w)[VW], int q) -> InT {
+        if constexpr (sizeof(InT) == 1) return (InT)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        else return (InT)(uint16_t)((w[q >> 1] >> (16 * (q & 1))) & 0xffffu);
+    };
 
-    F *yr = y + row * ld_y;
-    const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & (2 * sizeof(F) - 1)) == 0);
+    Prefetch cur;
+    int64_t tile = blockIdx.x;
+    if (tile < total_tiles) fetch(tile, cur);
+    for (; tile < total_tiles; tile += gridDim.x) {
+        // samples [col0 - LEAD, col0 - LEAD + SPAN) -> floating point in shared memory
+        const InT *xr = x + cur.row * ld_x;
+        if (cur.interior) {
 #pragma unroll
-    for (int j = 0; j < kPairs; ++j) {
-        const int o = j * (2 * kThreadsI) + 2 * threadIdx.x;      // first output of the pair, inside the tile
-        const int64_t n = col0 + o;
-        if (n >= cols) break;
-        F w[WIN];
+            for (int b = 0; b < NV; ++b) {
+                F *dst = &xs[LEAD + (b * kThreadsI + tid) * PER];
 #pragma unroll
-        for (int q = 0; q < WIN; q += 2) {
-            const V2 v = *reinterpret_cast<const V2 *>(&xs[o + q]);
-            w[q] = v.x;
-            w[q + 1] = v.y;
-        }
-        // output n reads samples n + hi ... n - lo  <->  w[LEAD + hi - k], k = 0..L-1
-        F a0 = (F)0, a1 = (F)0;
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if constexpr (sizeof(F) == 8) {          // the reference's float64: unfused multiply then add
-                a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
-                a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
-            } else {                                 // float32 datapath (same as the generic kernel's)
-                a0 = fmaf((float)h.v[k], w[LEAD + hi - k], a0);
-                a1 = fmaf((float)h.v[k], w[LEAD + hi - k + 1], a1);
+                for (int q = 0; q < PER; q += 2) {
+                    V2 pair;
+                    pair.x = (F)prep_sample(sample_of(cur.body[b], q));
+                    pair.y = (F)prep_sample(sample_of(cur.body[b], q + 1));
+                    *reinterpret_cast<V2 *>(dst + q) = pair;
+                }
             }
-        }
-        if (n + 1 < cols && y_vec) {
-            V2 pair;
-            pair.x = a0;
-            pair.y = a1;
-            *reinterpret_cast<V2 *>(yr + n) = pair;
+            if (tid < LEAD) xs[tid] = (F)prep_sample(cur.left);
+            if (tid < TAIL) xs[LEAD + kTileI + tid] = (F)prep_sample(cur.right);
         } else {
-            yr[n] = a0;
-            if (n + 1 < cols) yr[n + 1] = a1;
+            for (int i = tid; i < SPAN; i += kThreadsI) {
+                const int64_t g = cur.col0 - LEAD + i;
+                xs[i] = (g >= vlo && g < vhi) ? (F)prep_sample(xr[g]) : (F)0;
+            }
         }
+        __syncthreads();
+
+        Prefetch nxt;
+        nxt.interior = false;
+        nxt.row = nxt.col0 = 0;
+        if (tile + gridDim.x < total_tiles) fetch(tile + gridDim.x, nxt);
+
+        F *yr = y + cur.row * ld_y;
+        const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & (2 * sizeof(F) - 1)) == 0);
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+            const int o = j * (2 * kThreadsI) + 2 * tid;          // first output of the pair, inside the tile
+            const int64_t n = cur.col0 + o;
+            if (n >= cols) break;
+            F w[WIN];
+#pragma unroll
+            for (int q = 0; q < WIN; q += 2) {
+                const V2 v = *reinterpret_cast<const V2 *>(&xs[o + q]);
+                w[q] = v.x;
+                w[q + 1] = v.y;
+            }
+            // output n reads samples n + hi ... n - lo  <->  w[LEAD + hi - k], k = 0..L-1
+            F a0 = (F)0, a1 = (F)0;
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                if constexpr (sizeof(F) == 8) {          // the reference's float64: unfused multiply then add
+                    a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
+                    a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
+                } else {                                 // float32 datapath (same as the generic kernel's)
+                    a0 = fmaf((float)h.v[k], w[LEAD + hi - k], a0);
+                    a1 = fmaf((float)h.v[k], w[LEAD + hi - k + 1], a1);
+                }
+            }
+            if (n + 1 < cols && y_vec) {
+                V2 pair;
+                pair.x = a0;
+                pair.y = a1;
+                *reinterpret_cast<V2 *>(yr + n) = pair;
+            } else {
+                yr[n] = a0;
+                if (n + 1 < cols) yr[n + 1] = a1;
+            }
+        }
+        __syncthreads();                                   // every read of xs is done before the next fill
+        cur = nxt;
     }
 }
 
@@ -134,8 +174,13 @@ int run_pairs(const Fir1dArgs &a, const double *h_host)
     const int64_t tiles_per_row = (a.cols + kTileI - 1) / kTileI;
     const int64_t total = tiles_per_row * a.rows;
     if (total > 0x7fffffffLL) return 0;
-    fir1d_ideal_fast_kernel<InT, F, L, kPairs><<<(unsigned)total, kThreadsI, 0, a.stream>>>(
-        (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, h, a.halo_left, a.halo_right);
+    int dev = 0, sms = 148;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = (int64_t)sms * 8;                      // persistent: 8 CTAs of 256 threads fill an SM
+    if (grid > total) grid = total;
+    fir1d_ideal_fast_kernel<InT, F, L, kPairs><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
+        (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
