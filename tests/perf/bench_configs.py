@@ -4,8 +4,8 @@ config 2).  Same timing rules: one process per GPU, barrier + synchronize on
 both sides, CUDA events on the launching stream, max over ranks.  STRONG
 scaling: the global problem is fixed and sharded with no data-path collective.
 
-    python tools/bench_configs.py                                   # 1 GPU
-    python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py
+    python tests/perf/bench_configs.py                                   # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N ... tests/perf/bench_configs.py
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path[:0] = [str(ROOT), str(ROOT / "warmup-fir-filter_b200")]
 import firgpu  # noqa: E402
 from firgpu import _lib, quant, shard  # noqa: E402

@@ -3,7 +3,7 @@
 (memcheck / racecheck / initcheck / synccheck), small enough to finish under
 the tool's slowdown.  Each result is also checked against the oracle.
 
-    compute-sanitizer --tool racecheck python tools/sanitize_cases.py
+    compute-sanitizer --tool racecheck python tests/perf/sweep_all_kernels.py
 """
 import sys
 from pathlib import Path
@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path[:0] = [str(ROOT), str(ROOT / "warmup-fir-filter_b200")]
 import firgpu  # noqa: E402
 from firgpu import _lib, shard  # noqa: E402
