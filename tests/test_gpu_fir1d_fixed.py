@@ -388,3 +388,71 @@ def test_long_filters_run_in_staged_buckets(fg, torch):
         assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])
     host = fg.fir1d_fixed(sig, h, 15, 32, 16, out_dtype=np.int16)
     assert np.array_equal(host, want)
+
+
+def test_float_and_int32_containers_use_the_fast_kernels(fg, torch):
+    """int32 / float32 / float64 samples: one streaming pass rounds (half up, in
+    float64) and clamps them to uint8 pixels, then the staged / tiled kernels
+    filter — bit-exact, exact .5 ties, shard halos, 1-D and 2-D."""
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(99)
+    n = 70_003
+    halves = (rng.integers(-6, 520, size=n) * 0.5)                 # every other value is an exact .5 tie
+    for x in (rng.uniform(-30, 300, size=n), halves, halves.astype(np.float32), rng.integers(-500, 700, size=n).astype(np.int32),
+              rng.uniform(-5, 260, size=(6, 9001)).astype(np.float32)):
+        for h, frac in ((SIMPLE_LP5, 15), ([0.25, 0.5, 0.25], 12), ((np.ones(21) / 42).tolist(), 15)):
+            for out_dtype in (np.uint8, np.int16):
+                y = fg.fir1d_fixed(torch.from_numpy(x).cuda(), h, frac, 32, 16, out_dtype=out_dtype)
+                # (filters longer than 9 taps are instantiated for equal container types only)
+                want_path = _lib.PATH_GENERIC if len(h) > 9 and out_dtype is np.int16 else _lib.PATH_STAGED
+                assert _lib.last_path() == want_path, (x.dtype, len(h), out_dtype)
+                assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h, frac, 32, 16, out_dtype=out_dtype)), (x.dtype, len(h), out_dtype)
+    x = rng.uniform(-30, 300, size=150_000)
+    want = onp.fir1d_fixed(x, SIMPLE_LP5, 15, 32, 16)
+    for p in shard.plan_segments(x.size, 3, 5, 1, align=4096):
+        buf, body = shard.scatter_segment(x, p, "cuda")
+        y = fg.fir1d_fixed(body, SIMPLE_LP5, 15, 32, 16, halo_left_valid=p.before, halo_right_valid=p.after)
+        assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop])
+    # wrap-live taps on a float container: uint8 copy + generic kernel
+    y = fg.fir1d_fixed(torch.from_numpy(x).cuda(), [0.9, -0.7, 0.8], 12, 16, 16)
+    assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, [0.9, -0.7, 0.8], 12, 16, 16))
+    img = rng.uniform(-20, 280, size=(2, 150, 1000))
+    for k in ([[1 / 9] * 3] * 3, np.outer(SIMPLE_LP5, SIMPLE_LP5).tolist()):
+        y = fg.fir2d_fixed(torch.from_numpy(img).cuda(), k)
+        assert _lib.last_path() == _lib.PATH_STAGED
+        assert np.array_equal(y.cpu().numpy(), onp.fir2d_fixed(img, k))
+    assert np.array_equal(fg.fir2d_fixed(img, k), onp.fir2d_fixed(img, k))           # host entry point
+    assert np.array_equal(fg.fir1d_fixed(x, SIMPLE_LP5), onp.fir1d_fixed(x, SIMPLE_LP5))
+
+
+def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):
+    """The device rounds float samples from their bit pattern; the reference
+    computes floor(x + 0.5) with a float64 add (fir_1d_ref.py:35-41).  Identity
+    filter over every x.5 tie, its float neighbours, the float64 add's one
+    inexact tie (0.5 - 2^-54 -> 1), signed zeros, denormals and huge values —
+    through the generic kernel (short input), the conversion pass + staged
+    kernel (long input) and the floating-point model."""
+    ints = np.arange(-3, 260, dtype=np.float64)
+    rng = np.random.default_rng(4)
+    special = np.concatenate([
+        ints, ints + 0.5, np.nextafter(ints + 0.5, -np.inf), np.nextafter(ints + 0.5, np.inf), np.nextafter(ints, -np.inf),
+        np.nextafter(ints, np.inf),
+        [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e300, -1e300, 0.49999999999999994, 0.5, 0.25, 2.0 ** -30, 255.49999999999997, 1.7e308],
+        np.exp(rng.uniform(-40, 40, size=500)), -np.exp(rng.uniform(-40, 40, size=100))])
+    assert onp.fir1d_fixed(np.array([0.49999999999999994]), [1.0])[0] == 1          # the reference's own behaviour
+    i32 = np.arange(-3, 260, dtype=np.float32)
+    special32 = np.concatenate([
+        i32, i32 + np.float32(0.5), np.nextafter(i32 + np.float32(0.5), np.float32(-np.inf)), np.nextafter(i32 + np.float32(0.5), np.float32(np.inf)),
+        np.nextafter(i32, np.float32(-np.inf)), np.float32([0.0, -0.0, 1e-45, -1e-45, 1e-30, 3e38, -3e38, 0.49999997, 255.49998]),
+        np.exp(rng.uniform(-40, 40, size=500)).astype(np.float32)]).astype(np.float32)
+    for base in (special, special32):
+        for reps in (1, 8):                                   # 1: generic kernel; 8: > 4096 samples, conversion pass
+            x = np.tile(base, reps)
+            want = np.clip(np.floor(x.astype(np.float64) + 0.5), 0, 255).astype(np.uint8)
+            for src in (x, torch.from_numpy(x).cuda()):
+                y = fg.fir1d_fixed(src, [1.0])
+                y = y.cpu().numpy() if hasattr(y, "cpu") else y
+                assert np.array_equal(y, want), (x.dtype, reps, type(src))
+            assert np.array_equal(np.asarray(fg.fir1d_ideal(x, [1.0]), dtype=np.float64), want.astype(np.float64))
+            img = x[: (x.size // 64) * 64].reshape(-1, 64)
+            assert np.array_equal(fg.fir2d_fixed(img, [[0, 0, 0], [0, 1.0, 0], [0, 0, 0]]), want[: img.size].reshape(img.shape))

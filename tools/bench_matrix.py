@@ -171,6 +171,23 @@ def main():
             report(f"multi-filter x4 {hgt}x{wid} u8 -> 4 x u8 5tap q4.12 (1 read + 4 writes)", s, hgt * wid, 5)
             s = timed(lambda: [firgpu.fir1d_fixed(x, h, validate=False) for h in sets], args.reps)
             report(f"4 single passes {hgt}x{wid} u8 -> u8 5tap q4.12 (same 5 B/px accounting)", s, hgt * wid, 5)
+    if "containers" in cases:
+        # int32 / float sample containers: rounding pass to uint8 + staged kernel.  Algorithmic bytes per
+        # sample = container read + 1 output byte; the uint8 temporary (1 write + 1 read) is extra traffic.
+        m = 1 << 27
+        g = torch.Generator(device="cuda").manual_seed(5)
+        base = torch.rand(m, generator=g, device="cuda", dtype=torch.float32) * 300.0 - 20.0
+        y = torch.empty(m, dtype=torch.uint8, device="cuda")
+        for dt, nb in ((torch.float32, 4), (torch.float64, 8), (torch.int32, 4)):
+            x = base.to(dt)
+            s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out=y, validate=False), args.reps)
+            report(f"stream 2^27 {str(dt).split('.')[1]}->u8 5tap q1.15 (prep + staged)", s, m, nb + 1)
+            del x
+        k3 = [[1 / 9] * 3] * 3
+        img = (torch.rand(8192 * 8192, generator=g, device="cuda", dtype=torch.float32) * 300.0 - 20.0).view(8192, 8192)
+        out = torch.empty(8192, 8192, dtype=torch.uint8, device="cuda")
+        s = timed(lambda: firgpu.fir2d_fixed(img, k3, 12, 32, 16, out=out, validate=False), args.reps)
+        report("2d 8192^2 float32->u8 3x3 box q4.12 (prep + tiled)", s, 8192 * 8192, 5)
 
 
 if __name__ == "__main__":

@@ -458,6 +458,37 @@ int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t h
     return 0;
 }
 
+// Stream-ordered scratch memory (the uint8 copy of int32 / float containers).  A pool of the library's own, one per
+// device, that keeps what it has allocated between calls (the device's default pool hands its memory back at
+// every synchronisation, which would put a fresh cuMemCreate on each call); firgpu_release_cache() trims it.
+std::mutex g_pool_mu;
+std::map<int, cudaMemPool_t> g_pools;
+
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        auto it = g_pools.find(dev);
+        if (it == g_pools.end()) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            FIRGPU_CUDA(cudaMemPoolCreate(&pool, &props));
+            uint64_t keep = ~0ULL;
+            FIRGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            g_pools[dev] = pool;
+        } else {
+            pool = it->second;
+        }
+    }
+    FIRGPU_CUDA(cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pool, stream));
+    return 0;
+}
+
 int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtype == FIRGPU_I16 ? 2 : 0; }
 int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
 
@@ -495,6 +526,27 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     }
     Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, frac_bits, acc_bits,
                 halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+    // int32 / float containers: convert to the reference's uint8 pixels in one streaming
+    // pass (into a stream-ordered temporary), then filter on the fast kernels.
+    if ((in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64) && n_taps <= 65 &&
+        (dilation == 1 || dilation == 2) && rows * cols >= 4096 && !getenv("FIRGPU_FORCE_GENERIC")) {
+        const int64_t span = halo_left_valid + cols + halo_right_valid;
+        const int64_t lead = (halo_left_valid + 15) / 16 * 16;            // keeps the row start 16-byte aligned
+        const int64_t ld_t = (lead + cols + halo_right_valid + 15) / 16 * 16;
+        uint8_t *tmp = nullptr;
+        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * rows), (cudaStream_t)stream))) return rc;
+        rc = launch_prep_u8(x, in_dtype, tmp, rows, span, ld_x, ld_t, halo_left_valid, lead - halo_left_valid,
+                            (cudaStream_t)stream);
+        if (!rc) {
+            Fir1dArgs t{tmp + lead, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, n_taps, dilation, frac_bits, acc_bits,
+                        halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+            rc = try_launch_fir1d_fixed_staged(t, hq);
+            if (rc == 1) rc = 0;
+            else if (rc == 0) rc = launch_fir1d_fixed_generic(t, hq);   // taps outside the packed path: generic kernel on the uint8 copy
+        }
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
+    }
     // Many short rows (images, short channels): the row-streaming tensor-map
     // kernel keeps whole CTAs busy where the 1-D tile kernel would stage one
     // mostly empty tile per row.  Its TMA out-of-bounds zero fill is the
@@ -576,6 +628,28 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     if (n_img == 0 || height == 0 || width == 0) {
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
+    }
+    // int32 / float containers: one streaming pass to uint8 pixels, then the tensor-map kernel.
+    if ((in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64) && out_dtype == FIRGPU_U8 &&
+        (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1) && (width & 1) == 0 &&
+        n_img * height * width >= 4096 && !getenv("FIRGPU_FORCE_GENERIC")) {
+        const int64_t band = halo_top_valid + height + halo_bottom_valid;
+        const int64_t ld_t = (width + 15) / 16 * 16;
+        uint8_t *tmp = nullptr;
+        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * band * n_img), (cudaStream_t)stream))) return rc;
+        const int es_in = dtype_size(in_dtype);
+        for (int64_t b = 0; b < n_img && !rc; ++b)
+            rc = launch_prep_u8((const char *)x + (b * img_stride_x - halo_top_valid * ld_x) * es_in, in_dtype, tmp + b * band * ld_t,
+                                band, width, ld_x, ld_t, 0, 0, (cudaStream_t)stream);
+        if (!rc) {
+            Fir2dArgs t{tmp + halo_top_valid * ld_t, y, FIRGPU_U8, out_dtype, n_img, height, width, ld_t, ld_y, band * ld_t,
+                        img_stride_y, kh, kw, frac_bits, acc_bits, halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
+            rc = try_launch_fir2d_fixed_tiled(t, hq);
+            if (rc == 1) rc = 0;
+            else if (rc == 0) rc = launch_fir2d_fixed_generic(t, hq);
+        }
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
     }
     Fir2dArgs a{x, y, in_dtype, out_dtype, n_img, height, width, ld_x, ld_y, img_stride_x, img_stride_y, kh, kw,
                 frac_bits, acc_bits, halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
@@ -883,6 +957,10 @@ int firgpu_release_cache(void)
         }
         c->d_in_cap = c->d_out_cap = c->p_in_cap = c->p_out_cap = 0;
         c->ready = false;
+    }
+    {
+        std::lock_guard<std::mutex> l3(g_pool_mu);
+        for (auto &kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
     }
     cudaSetDevice(prev);
     cudaGetLastError();

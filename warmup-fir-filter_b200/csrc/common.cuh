@@ -54,16 +54,32 @@ inline int dtype_size(int dt)
 __device__ __forceinline__ int prep_sample(uint8_t v) { return v; }
 __device__ __forceinline__ int prep_sample(int16_t v) { return min(max((int)v, 0), kPixelMax); }
 __device__ __forceinline__ int prep_sample(int32_t v) { return min(max(v, 0), kPixelMax); }
+// float64 / float32: the reference rounds half up as floor(x + 0.5) with a float64 add, then clamps
+// (fir_1d_ref.py:35-41).  The conversion instructions that spelling needs (F2F / FRND / F2I on float64) run at a
+// fraction of the integer rate, so the same value is computed from the bit pattern: for 0 <= x < 256,
+// floor(x + 0.5) = (floor(2x) + 1) >> 1 and floor(2x) is a right shift of the mantissa.  The float64 add is exact
+// on that range (0.5 is a multiple of ulp(x), and a carry into the next binade cannot reach an integer) with ONE
+// exception, the largest double below 0.5: 0.5 - 2^-54 + 0.5 is a tie that rounds to 1.0, so the reference
+// returns 1 there and so does this.  Negative inputs (x + 0.5 < 0.5) give 0 after the clamp; x >= 256 gives 255.
+// NaN / inf never reach the device: the host wrapper rejects them like _validate_x does (fir_1d_ref.py:27-33).
 __device__ __forceinline__ int prep_sample(double v)
 {
-    // floor(s + 0.5) with a correctly rounded float64 add, then clamp.  NaN /
-    // inf never reach the device: the host wrapper rejects them like
-    // _validate_x does (fir_1d_ref.py:27-33).
-    double r = floor(__dadd_rn(v, 0.5));
-    r = fmin(fmax(r, 0.0), 255.0);
-    return (int)r;
+    const uint32_t hi = (uint32_t)__double2hiint(v), lo = (uint32_t)__double2loint(v);
+    const int e = (int)((hi >> 20) & 0x7ffu);
+    const uint32_t m = (hi & 0xfffffu) | 0x100000u;            // mantissa >> 32 with the implicit one
+    const uint32_t q = m >> min(max(1042 - e, 0), 31);         // floor(2x) for x < 256
+    int r = min((int)((q + 1u) >> 1), kPixelMax);
+    if (e >= 1031) r = kPixelMax;                              // x >= 256
+    if (hi == 0x3fdfffffu && lo == 0xffffffffu) r = 1;         // the float64 tie described above
+    if (hi >> 31) r = 0;                                       // x < 0 or -0.0
+    return r;
 }
-__device__ __forceinline__ int prep_sample(float v) { return prep_sample((double)v); }
+__device__ __forceinline__ int prep_sample(float v)              // == prep_sample((double)v): the float64 add never changes the floor here
+{
+    // floor(2x) with one saturating conversion (2x is exact; +-inf-sized products saturate), then (q + 1) >> 1.
+    const int q = min(__float2int_rd(v * 2.0f), 2 * kPixelMax + 1);
+    return min(max((q + 1) >> 1, 0), kPixelMax);
+}
 
 // Parametrised forms (extended entry points): sample clamp range [lo, hi] and
 // a raw mode for the floating-point model; (0, 255) reproduces the reference.
@@ -147,6 +163,9 @@ int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
 int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_host);
 // n_filters tap sets ([n_filters][n_taps]) over one pass of the input; outputs filter_stride_y elements apart.
 int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y);
+// prep_u8.cu — int32 / float32 / float64 containers -> uint8 pixels (round half up, clamp)
+int launch_prep_u8(const void *x, int in_dtype, uint8_t *y, int64_t rows, int64_t span, int64_t ld_x, int64_t ld_y,
+                   int64_t before, int64_t shift, cudaStream_t s);
 // fir1d_compare.cu
 int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
                          const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s);
