@@ -305,7 +305,7 @@ def test_ideal_fast_kernel_bit_identical():
     for dtype in (np.uint8, np.int16):
         for n_taps in range(1, 10):
             h = rng.uniform(-8, 8, size=n_taps).tolist()
-            for shape in ((1, 1), (1, 7), (3, 2048), (2, 2050), (5, 4098), (1, 100_003)):
+            for shape in ((1, 1), (1, 7), (3, 2048), (2, 2050), (5, 4098), (1, 100_003), (7, 1501), (4, 515), (6, 1027)):
                 x = rng.integers(0, 256, size=shape).astype(dtype)
                 if dtype == np.int16:
                     x[rng.random(shape) < 0.05] = -999
@@ -313,8 +313,26 @@ def test_ideal_fast_kernel_bit_identical():
                 got = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h)
                 assert _lib.last_path() == _lib.PATH_STAGED, (dtype, n_taps, shape)
                 assert np.array_equal(got.cpu().numpy(), onp.fir1d_ideal(x, h)), (dtype, n_taps, shape)
-    x = rng.integers(-300, 600, size=50_000).astype(np.int16)
+    # odd widths and pitches: the kernel shifts every row's tile grid to keep its 16-byte stores aligned; column
+    # views of a wider image give rows whose first sample / first output sit at every alignment
+    wide = rng.integers(0, 256, size=(9, 4499)).astype(np.uint8)
+    wide_t = torch.from_numpy(wide).cuda()
     h = [0.1, -0.2, 0.3, 0.4, 0.05]
+    for out_dtype, exact in ((np.float64, True), (np.float32, False)):
+        for c0 in (0, 1, 2, 3, 5):
+            for width in (4499 - 5, 1920, 777):
+                view = wide_t[:, c0:c0 + width]
+                out = torch.full((9, 4499), -7.0, dtype=torch.float64 if exact else torch.float32, device="cuda")
+                firgpu.fir1d_ideal(view, h, out_dtype=out_dtype, out=out[:, c0:c0 + width])
+                assert _lib.last_path() == _lib.PATH_STAGED
+                want = onp.fir1d_ideal(wide[:, c0:c0 + width], h)
+                got = out.cpu().numpy()
+                if exact:
+                    assert np.array_equal(got[:, c0:c0 + width], want), (c0, width)
+                else:
+                    assert np.abs(got[:, c0:c0 + width] - want).max() <= 1e-6 * 255 * np.abs(h).sum()
+                assert (got[:, :c0] == -7.0).all() and (got[:, c0 + width:] == -7.0).all(), (c0, width)   # nothing outside the view
+    x = rng.integers(-300, 600, size=50_000).astype(np.int16)
     want = onp.fir1d_ideal(x, h)
     for p in shard.plan_segments(x.size, 3, 5, 1, align=64):
         buf, body = shard.scatter_segment(x, p, "cuda")

@@ -134,6 +134,13 @@ def main():
         s = timed(lambda: firgpu.fir1d_ideal(x, LP5, out_dtype=np.float32, out=y32, validate=False), 5)
         report("ideal 2^26 u8->f32 5tap", s, 1 << 26, 5)
         del x, y, y32
+        # the reference's image shapes (rows are filtered independently: every row has two edge tiles)
+        for hgt, wid in ((2999, 4499), (1080, 1920), (8192, 16384)):
+            x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
+            y = torch.empty(hgt, wid, dtype=torch.float64, device="cuda")
+            s = timed(lambda: firgpu.fir1d_ideal(x, LP5, out=y, validate=False), 10)
+            report(f"ideal rows {hgt}x{wid} u8->f64 5tap", s, hgt * wid, 9)
+            del x, y
     if "2d" in cases:
         img = rand_i16(16384 * 16384).view(1, 16384, 16384)
         out = torch.empty_like(img)

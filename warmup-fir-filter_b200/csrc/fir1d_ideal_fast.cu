@@ -3,15 +3,22 @@
 // fir_1d/sim/vector/gen_ideal_output.py:37-50.
 //
 // Bound: HBM, 9-10 bytes per sample (1-2 in, 8 out) — the output dominates.
-// Persistent CTAs prefetch the next tile's samples into registers while the
-// current tile is filtered.  A CTA converts one tile of samples to float64 ONCE into shared memory
-// (round/clamp is the identity on integers, so conversion = clamp + cast),
-// then every thread produces pairs of adjacent outputs from 128-bit shared
-// loads and writes them with one 16-byte store, so a warp writes 512
-// contiguous bytes.  Arithmetic is the reference's: taps in ascending k,
+// Registers only: every lane produces pairs of adjacent outputs (one 16-byte
+// store per pair, 512 contiguous bytes per warp) and reads the few sample
+// pairs its window covers straight from global memory as 2- or 4-byte loads —
+// neighbouring lanes overlap, so all but the first touch of a sector hit L1.
+// An earlier version converted a tile to float64 once into shared memory and
+// filtered from 128-bit shared loads; ncu showed it bound by the L1/shared
+// data pipe (86 % of peak: 24 B of shared loads + 8 B of 4-way conflicting
+// shared stores + 8 B of global stores per sample) at 0.63 of the HBM peak.
+// Converting per window instead costs (L + 1) / 2 conversions per output, so the
+// cast is the exact "2^52 + v" bit trick — one add on the fp64 pipe, which has
+// the headroom, instead of an I2F on the quarter-rate conversion unit.
+// Round/clamp is the identity on integers, so conversion = clamp + cast.
+// Arithmetic is the reference's: taps in ascending k,
 // __dmul_rn then __dadd_rn (no FMA contraction), accumulator starting at +0.0
-// — bit-identical to the Python model.  Zero padding outside the row is
-// stored as +0.0 samples, which adds +-0.0 to a +0.0-started sum and never
+// — bit-identical to the Python model.  Zero padding outside the row enters
+// as +0.0 samples, which adds +-0.0 to a +0.0-started sum and never
 // changes it (x + (+-0.0) == x for every x, and +0.0 + (-0.0) == +0.0), so the
 // padded form is bit-identical to the reference's "skip taps outside the row".
 #include "common.cuh"
@@ -32,154 +39,161 @@ template <typename F> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
-template <typename InT, typename F, int L, int kPairs>   // kPairs output pairs per thread: 2 * 256 * kPairs outputs per CTA
+// exact integer -> floating point for 0 <= v <= 255 without a conversion instruction
+template <typename F> __device__ __forceinline__ F pixel_to(int v);
+template <> __device__ __forceinline__ double pixel_to<double>(int v)
+{
+    return __dadd_rn(__hiloint2double(0x43300000, v), -4503599627370496.0);      // (2^52 + v) - 2^52
+}
+template <> __device__ __forceinline__ float pixel_to<float>(int v)
+{
+    return __fadd_rn(__uint_as_float(0x4b000000u | (uint32_t)v), -8388608.0f);   // (2^23 + v) - 2^23
+}
+
+template <typename InT> struct PairOf;
+template <> struct PairOf<uint8_t> { using type = uint16_t; };
+template <> struct PairOf<int16_t> { using type = uint32_t; };
+
+template <typename InT, typename F, int L, int kGroups>   // kGroups output groups per lane per tile
 __global__ void __launch_bounds__(kThreadsI)
 fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
                         int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
                         int64_t halo_right)
 {
-    constexpr int kTileI = kThreadsI * 2 * kPairs;
+    constexpr int kWarps = kThreadsI / 32;
+    constexpr int OP = 16 / (2 * (int)sizeof(F));        // output pairs per group: one 16-byte store (2 doubles / 4 floats)
+    constexpr int G = 2 * OP;                            // outputs per group
+    constexpr int kTileI = 32 * G * kGroups;             // outputs per warp tile
     constexpr int hi = L / 2, lo = L - 1 - hi;
-    constexpr int LEAD = lo + (lo & 1);                  // even, so that window starts stay 16-byte aligned
-    constexpr int WIN = (LEAD + 2 + hi + 1) / 2 * 2;     // samples read per output pair
-    constexpr int SPAN = kTileI + LEAD + ((hi + 1) / 2) * 2;
-    constexpr int TAIL = SPAN - LEAD - kTileI;
-    constexpr int PER = 8;                               // body samples per vector load
-    constexpr int NV = kTileI / (kThreadsI * PER);       // vector loads per thread per tile
-    constexpr int VW = PER * sizeof(InT) / 4;            // 32-bit words per vector load
-    using V2 = typename Vec2<F>::type;
-    __shared__ __align__(16) F xs[SPAN];
+    constexpr int PL = (lo + 1) / 2, PR = (hi + 1) / 2;  // neighbour pairs a window reaches into, left / right
+    constexpr int NP = PL + OP + PR;                     // sample pairs per window: samples base - 2 PL ... base + G - 1 + 2 PR
+    using P2 = typename PairOf<InT>::type;
+    const int lane = threadIdx.x & 31;
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
-    const int tid = threadIdx.x;
+    const int64_t step = (int64_t)gridDim.x * kWarps;
 
-    // One tile's samples, prefetched into registers while the previous tile is
-    // being filtered (persistent CTA, register double buffering).
-    struct Prefetch {
-        int64_t row, col0;
-        bool interior;
-        uint32_t body[NV][VW];
-        InT left, right;
-    };
-    auto fetch = [&](int64_t tile, Prefetch &p) {
-        p.row = tile / tiles_per_row;
-        p.col0 = (tile - p.row * tiles_per_row) * kTileI;
-        const InT *xr = x + p.row * ld_x;
-        p.interior = p.col0 - LEAD >= vlo && p.col0 - LEAD + SPAN <= vhi &&
-                     ((reinterpret_cast<uintptr_t>(xr + p.col0) & (PER * sizeof(InT) - 1)) == 0);
-        if (p.interior) {
+    // w[i] is sample base - 2 PL + i; output base + e reads samples base + e + hi - k, k = 0 .. L-1
+    auto filter_group = [&](const F (&w)[2 * NP], F (&a)[G]) {
 #pragma unroll
-            for (int b = 0; b < NV; ++b) {
-                const InT *src = xr + p.col0 + (b * kThreadsI + tid) * PER;
-                if constexpr (VW == 2) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(src);
-                    p.body[b][0] = v.x;
-                    p.body[b][1] = v.y;
-                } else {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(src);
-                    p.body[b][0] = v.x;
-                    p.body[b][1] = v.y;
-                    p.body[b][2] = v.z;
-                    p.body[b][3] = v.w;
-                }
+        for (int e = 0; e < G; ++e) a[e] = (F)0;
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+#pragma unroll
+            for (int e = 0; e < G; ++e) {
+                if constexpr (sizeof(F) == 8) a[e] = __dadd_rn(a[e], __dmul_rn(h.v[k], w[2 * PL + hi - k + e]));   // the reference's unfused float64
+                else a[e] = fmaf((float)h.v[k], w[2 * PL + hi - k + e], a[e]);                                    // float32 datapath (same as the generic kernel's)
             }
-            if (tid < LEAD) p.left = xr[p.col0 - LEAD + tid];
-            if (tid < TAIL) p.right = xr[p.col0 + kTileI + tid];
         }
     };
-    auto sample_of = [](const uint32_t (&w)[VW], int q) -> InT {
-        if constexpr (sizeof(InT) == 1) return (InT)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
-        else return (InT)(uint16_t)((w[q >> 1] >> (16 * (q & 1))) & 0xffffu);
-    };
 
-    Prefetch cur;
-    int64_t tile = blockIdx.x;
-    if (tile < total_tiles) fetch(tile, cur);
-    for (; tile < total_tiles; tile += gridDim.x) {
-        // samples [col0 - LEAD, col0 - LEAD + SPAN) -> floating point in shared memory
-        const InT *xr = x + cur.row * ld_x;
-        if (cur.interior) {
-#pragma unroll
-            for (int b = 0; b < NV; ++b) {
-                F *dst = &xs[LEAD + (b * kThreadsI + tid) * PER];
-#pragma unroll
-                for (int q = 0; q < PER; q += 2) {
-                    V2 pair;
-                    pair.x = (F)prep_sample(sample_of(cur.body[b], q));
-                    pair.y = (F)prep_sample(sample_of(cur.body[b], q + 1));
-                    *reinterpret_cast<V2 *>(dst + q) = pair;
-                }
-            }
-            if (tid < LEAD) xs[tid] = (F)prep_sample(cur.left);
-            if (tid < TAIL) xs[LEAD + kTileI + tid] = (F)prep_sample(cur.right);
+    auto widen = [](P2 r, F &w0, F &w1) {
+        if constexpr (sizeof(InT) == 1) {
+            w0 = pixel_to<F>(r & 0xff);
+            w1 = pixel_to<F>(r >> 8);
         } else {
-            for (int i = tid; i < SPAN; i += kThreadsI) {
-                const int64_t g = cur.col0 - LEAD + i;
-                xs[i] = (g >= vlo && g < vhi) ? (F)prep_sample(xr[g]) : (F)0;
-            }
+            w0 = pixel_to<F>(prep_sample((int16_t)(r & 0xffffu)));
+            w1 = pixel_to<F>(prep_sample((int16_t)(r >> 16)));
         }
-        __syncthreads();
+    };
 
-        Prefetch nxt;
-        nxt.interior = false;
-        nxt.row = nxt.col0 = 0;
-        if (tile + gridDim.x < total_tiles) fetch(tile + gridDim.x, nxt);
-
-        F *yr = y + cur.row * ld_y;
-        const bool y_vec = ((reinterpret_cast<uintptr_t>(yr) & (2 * sizeof(F) - 1)) == 0);
+    // (row, tcol) advance incrementally: no 64-bit division per tile.  Loads of a tile are all issued before its
+    // arithmetic; other resident warps cover their latency (prefetching the next tile in registers was measured
+    // and lost to the occupancy it costs).
+    // Every row's tile grid is shifted left by `pad` outputs so that group stores are 16-byte aligned whatever the
+    // row pitch (odd image widths); the first tile then starts at a negative column and skips those outputs.
+    const int64_t step_rows = step / tiles_per_row, step_cols = step - step_rows * tiles_per_row;
+    int64_t tile = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int64_t row = tile / tiles_per_row, tcol = tile - row * tiles_per_row;
+    for (; tile < total_tiles; tile += step) {
+        const InT *xr = x + row * ld_x;
+        F *yr = y + row * ld_y;
+        const int pad = (int)((reinterpret_cast<uintptr_t>(yr) / sizeof(F)) % G);
+        const int64_t col0 = tcol * kTileI - pad;
+        const bool x_pairs = (reinterpret_cast<uintptr_t>(xr + col0) & (2 * sizeof(InT) - 1)) == 0;
+        const bool interior = col0 >= 0 && col0 - 2 * PL >= vlo && col0 + kTileI + 2 * PR <= vhi && col0 + kTileI <= cols && x_pairs;
+        if (interior) {
+            P2 raw[kGroups][NP];
 #pragma unroll
-        for (int j = 0; j < kPairs; ++j) {
-            const int o = j * (2 * kThreadsI) + 2 * tid;          // first output of the pair, inside the tile
-            const int64_t n = cur.col0 + o;
-            if (n >= cols) break;
-            F w[WIN];
+            for (int j = 0; j < kGroups; ++j)
 #pragma unroll
-            for (int q = 0; q < WIN; q += 2) {
-                const V2 v = *reinterpret_cast<const V2 *>(&xs[o + q]);
-                w[q] = v.x;
-                w[q + 1] = v.y;
+                for (int p = 0; p < NP; ++p)
+                    raw[j][p] = *reinterpret_cast<const P2 *>(xr + col0 + (j * 32 + lane) * G + 2 * (p - PL));
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j) {
+                F w[2 * NP];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) widen(raw[j][p], w[2 * p], w[2 * p + 1]);
+                F a[G];
+                filter_group(w, a);
+                F *dst = yr + col0 + (j * 32 + lane) * G;
+                if constexpr (sizeof(F) == 8) *reinterpret_cast<double2 *>(dst) = make_double2(a[0], a[1]);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(a[0], a[1], a[2], a[3]);
             }
-            // output n reads samples n + hi ... n - lo  <->  w[LEAD + hi - k], k = 0..L-1
-            F a0 = (F)0, a1 = (F)0;
+        } else {
+            // row ends (two tiles per row), shard seams, rows whose samples are not pair-aligned: every sample pair
+            // checks its range (zero padding outside [vlo, vhi)), every output its column
+            for (int j = 0; j < kGroups; ++j) {
+                const int64_t n = col0 + (j * 32 + lane) * G;
+                if (n >= cols) break;
+                if (n + G <= 0) continue;
+                F w[2 * NP];
 #pragma unroll
-            for (int k = 0; k < L; ++k) {
-                if constexpr (sizeof(F) == 8) {          // the reference's float64: unfused multiply then add
-                    a0 = __dadd_rn(a0, __dmul_rn(h.v[k], w[LEAD + hi - k]));
-                    a1 = __dadd_rn(a1, __dmul_rn(h.v[k], w[LEAD + hi - k + 1]));
-                } else {                                 // float32 datapath (same as the generic kernel's)
-                    a0 = fmaf((float)h.v[k], w[LEAD + hi - k], a0);
-                    a1 = fmaf((float)h.v[k], w[LEAD + hi - k + 1], a1);
+                for (int p = 0; p < NP; ++p) {
+                    const int64_t g = n - 2 * PL + 2 * p;
+                    if (x_pairs && g >= vlo && g + 1 < vhi) {
+                        widen(*reinterpret_cast<const P2 *>(xr + g), w[2 * p], w[2 * p + 1]);
+                    } else {
+                        w[2 * p] = (g >= vlo && g < vhi) ? pixel_to<F>(prep_sample(xr[g])) : (F)0;
+                        w[2 * p + 1] = (g + 1 >= vlo && g + 1 < vhi) ? pixel_to<F>(prep_sample(xr[g + 1])) : (F)0;
+                    }
+                }
+                F a[G];
+                filter_group(w, a);
+                if (n >= 0 && n + G <= cols) {
+                    if constexpr (sizeof(F) == 8) *reinterpret_cast<double2 *>(yr + n) = make_double2(a[0], a[1]);
+                    else *reinterpret_cast<float4 *>(yr + n) = make_float4(a[0], a[1], a[2], a[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < G; ++e)
+                        if (n + e >= 0 && n + e < cols) yr[n + e] = a[e];
                 }
             }
-            if (n + 1 < cols && y_vec) {
-                V2 pair;
-                pair.x = a0;
-                pair.y = a1;
-                *reinterpret_cast<V2 *>(yr + n) = pair;
-            } else {
-                yr[n] = a0;
-                if (n + 1 < cols) yr[n + 1] = a1;
-            }
         }
-        __syncthreads();                                   // every read of xs is done before the next fill
-        cur = nxt;
+        row += step_rows;
+        tcol += step_cols;
+        if (tcol >= tiles_per_row) {
+            tcol -= tiles_per_row;
+            ++row;
+        }
     }
 }
 
-template <typename InT, typename F, int L, int kPairs>
-int run_pairs(const Fir1dArgs &a, const double *h_host)
+template <typename InT, typename F, int L, int kGroups>
+int run_groups(const Fir1dArgs &a, const double *h_host)
 {
-    constexpr int kTileI = kThreadsI * 2 * kPairs;
+    constexpr int kWarps = kThreadsI / 32;
+    constexpr int kTileI = 32 * (16 / (int)sizeof(F)) * kGroups;
     TapsF64<L> h;
     for (int k = 0; k < L; ++k) h.v[k] = h_host[k];
-    const int64_t tiles_per_row = (a.cols + kTileI - 1) / kTileI;
+    constexpr int kGroup = 16 / (int)sizeof(F);
+    const int64_t tiles_per_row = (a.cols + kGroup - 1 + kTileI - 1) / kTileI;   // room for the per-row alignment shift
     const int64_t total = tiles_per_row * a.rows;
-    if (total > 0x7fffffffLL) return 0;
     int dev = 0, sms = 148;
     FIRGPU_CUDA(cudaGetDevice(&dev));
     FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int64_t grid = (int64_t)sms * 8;                      // persistent: 8 CTAs of 256 threads fill an SM
-    if (grid > total) grid = total;
-    fir1d_ideal_fast_kernel<InT, F, L, kPairs><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
+    // One tile per warp, CTAs in address order: concurrently running CTAs then write one advancing front, which
+    // the write-dominated stream needs (a persistent grid striding over the output measured 8 % slower).
+    // FIRGPU_IDEAL_CTAS=n > 0 selects the persistent form with n CTAs per SM.
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char *e = getenv("FIRGPU_IDEAL_CTAS");
+        per_sm = e ? atoi(e) : 0;
+    }
+    int64_t grid = (total + kWarps - 1) / kWarps;
+    if (per_sm > 0 && grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
+    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+    if (grid < 1) grid = 1;
+    fir1d_ideal_fast_kernel<InT, F, L, kGroups><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
@@ -189,15 +203,17 @@ int run_pairs(const Fir1dArgs &a, const double *h_host)
 template <typename InT, int L>
 int run(const Fir1dArgs &a, const double *h_host)
 {
-    // measured: float64 output is fastest with 2048-output tiles, float32 with 4096 (tuning knob: FIRGPU_IDEAL_PAIRS=4|8)
+    // groups per lane per tile (tuning knob: FIRGPU_IDEAL_GROUPS=2|4|8)
     static int forced = -1;
     if (forced < 0) {
-        const char *e = getenv("FIRGPU_IDEAL_PAIRS");
+        const char *e = getenv("FIRGPU_IDEAL_GROUPS");
         forced = e ? atoi(e) : 0;
     }
-    const bool big = forced ? forced == 8 : (a.out_dtype == FIRGPU_F32 && a.cols >= 16384);
-    if (a.out_dtype == FIRGPU_F32) return big ? run_pairs<InT, float, L, 8>(a, h_host) : run_pairs<InT, float, L, 4>(a, h_host);
-    return big ? run_pairs<InT, double, L, 8>(a, h_host) : run_pairs<InT, double, L, 4>(a, h_host);
+    const bool f32 = a.out_dtype == FIRGPU_F32;
+    const int g = forced ? forced : (f32 ? 4 : 8);
+    if (g == 2) return f32 ? run_groups<InT, float, L, 2>(a, h_host) : run_groups<InT, double, L, 2>(a, h_host);
+    if (g == 4) return f32 ? run_groups<InT, float, L, 4>(a, h_host) : run_groups<InT, double, L, 4>(a, h_host);
+    return f32 ? run_groups<InT, float, L, 8>(a, h_host) : run_groups<InT, double, L, 8>(a, h_host);
 }
 
 template <typename InT>
@@ -224,7 +240,6 @@ int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
 {
     if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
     if (!a.is_reference_model()) return 0;
-    if ((a.ld_y & 1) && a.rows > 1) return 0;            // keeps every row's pair stores 16-byte aligned or uniformly scalar
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
     if (force && force[0] == '1') return 0;
     if (a.in_dtype == FIRGPU_U8) return by_taps<uint8_t>(a, h_host);
