@@ -423,6 +423,19 @@ def test_float_and_int32_containers_use_the_fast_kernels(fg, torch):
         assert np.array_equal(y.cpu().numpy(), onp.fir2d_fixed(img, k))
     assert np.array_equal(fg.fir2d_fixed(img, k), onp.fir2d_fixed(img, k))           # host entry point
     assert np.array_equal(fg.fir1d_fixed(x, SIMPLE_LP5), onp.fir1d_fixed(x, SIMPLE_LP5))
+    # multi-filter pass (one conversion for all tap sets) and the floating-point model
+    from fir_1d.sim.vector.h_coeff import h_coeff_5tap_map
+    sets = list(h_coeff_5tap_map.values())
+    rows = rng.uniform(-20, 280, size=(33, 1501)).astype(np.float32)
+    want = np.stack([onp.fir1d_fixed(rows, h) for h in sets])
+    assert np.array_equal(fg.fir1d_fixed_multi(torch.from_numpy(rows).cuda(), sets).cpu().numpy(), want)
+    assert _lib.last_path() == _lib.PATH_STAGED
+    assert np.array_equal(fg.fir1d_fixed_multi(rows, sets), want)
+    for src in (x, rows):
+        got = fg.fir1d_ideal(torch.from_numpy(src).cuda(), SIMPLE_LP5)
+        assert _lib.last_path() == _lib.PATH_STAGED
+        assert np.array_equal(got.cpu().numpy(), onp.fir1d_ideal(src, SIMPLE_LP5))
+        assert np.array_equal(np.asarray(fg.fir1d_ideal(src, SIMPLE_LP5)), onp.fir1d_ideal(src, SIMPLE_LP5))
 
 
 def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):

@@ -489,6 +489,29 @@ int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
     return 0;
 }
 
+bool wide_container(int in_dtype) { return in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64; }
+
+// int32 / float containers of a useful size are converted to the reference's uint8 pixels first (csrc/prep_u8.cu).
+bool convert_first(int in_dtype, int64_t samples)
+{
+    return wide_container(in_dtype) && samples >= 4096 && !getenv("FIRGPU_FORCE_GENERIC");
+}
+
+// uint8 copy of rows x (halo_left + cols + halo_right) samples in scratch memory: *body points at column 0 of row 0
+// (16-byte aligned), *ld_t is the pitch (a multiple of 16).  The caller frees *tmp with cudaFreeAsync on `stream`.
+int uint8_copy_1d(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t halo_left, int64_t halo_right,
+                  cudaStream_t stream, uint8_t **tmp, uint8_t **body, int64_t *ld_t)
+{
+    const int64_t lead = (halo_left + 15) / 16 * 16;
+    *ld_t = (lead + cols + halo_right + 15) / 16 * 16;
+    int rc = scratch_alloc((void **)tmp, (size_t)(*ld_t * rows), stream);
+    if (rc) return rc;
+    *body = *tmp + lead;
+    rc = launch_prep_u8(x, in_dtype, *tmp, rows, halo_left + cols + halo_right, ld_x, *ld_t, halo_left, lead - halo_left, stream);
+    if (rc) cudaFreeAsync(*tmp, stream);
+    return rc;
+}
+
 int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtype == FIRGPU_I16 ? 2 : 0; }
 int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
 
@@ -528,22 +551,16 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
                 halo_left_valid, halo_right_valid, (cudaStream_t)stream};
     // int32 / float containers: convert to the reference's uint8 pixels in one streaming
     // pass (into a stream-ordered temporary), then filter on the fast kernels.
-    if ((in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64) && n_taps <= 65 &&
-        (dilation == 1 || dilation == 2) && rows * cols >= 4096 && !getenv("FIRGPU_FORCE_GENERIC")) {
-        const int64_t span = halo_left_valid + cols + halo_right_valid;
-        const int64_t lead = (halo_left_valid + 15) / 16 * 16;            // keeps the row start 16-byte aligned
-        const int64_t ld_t = (lead + cols + halo_right_valid + 15) / 16 * 16;
-        uint8_t *tmp = nullptr;
-        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * rows), (cudaStream_t)stream))) return rc;
-        rc = launch_prep_u8(x, in_dtype, tmp, rows, span, ld_x, ld_t, halo_left_valid, lead - halo_left_valid,
-                            (cudaStream_t)stream);
-        if (!rc) {
-            Fir1dArgs t{tmp + lead, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, n_taps, dilation, frac_bits, acc_bits,
-                        halo_left_valid, halo_right_valid, (cudaStream_t)stream};
-            rc = try_launch_fir1d_fixed_staged(t, hq);
-            if (rc == 1) rc = 0;
-            else if (rc == 0) rc = launch_fir1d_fixed_generic(t, hq);   // taps outside the packed path: generic kernel on the uint8 copy
-        }
+    if (convert_first(in_dtype, rows * cols) && n_taps <= 65 && (dilation == 1 || dilation == 2)) {
+        uint8_t *tmp = nullptr, *body = nullptr;
+        int64_t ld_t = 0;
+        if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, halo_left_valid, halo_right_valid, (cudaStream_t)stream, &tmp, &body, &ld_t)))
+            return rc;
+        Fir1dArgs t{body, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, n_taps, dilation, frac_bits, acc_bits,
+                    halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+        rc = try_launch_fir1d_fixed_staged(t, hq);
+        if (rc == 1) rc = 0;
+        else if (rc == 0) rc = launch_fir1d_fixed_generic(t, hq);       // taps outside the packed path: generic kernel on the uint8 copy
         cudaFreeAsync(tmp, (cudaStream_t)stream);
         return rc;
     }
@@ -579,6 +596,15 @@ int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
+    if (convert_first(in_dtype, rows * cols)) {          // one conversion for all tap sets
+        uint8_t *tmp = nullptr, *body = nullptr;
+        int64_t ld_t = 0;
+        if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, 0, 0, (cudaStream_t)stream, &tmp, &body, &ld_t))) return rc;
+        rc = firgpu_fir1d_fixed_multi(body, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, filter_stride_y, hq, n_filters,
+                                      n_taps, dilation, frac_bits, acc_bits, stream);
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
+    }
     // Groups of four tap sets are served by ONE pass of the staged kernel (the
     // input is read from HBM once); the rest one tap set at a time.
     int f = 0;
@@ -611,6 +637,17 @@ int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype, int6
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
+    if (convert_first(in_dtype, rows * cols) && n_taps <= 9 && dilation == 1) {   // the floating-point model also starts from the rounded, clamped pixel
+        uint8_t *tmp = nullptr, *body = nullptr;
+        int64_t ld_t = 0;
+        if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, halo_left_valid, halo_right_valid, (cudaStream_t)stream, &tmp, &body, &ld_t)))
+            return rc;
+        Fir1dArgs t{body, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, n_taps, dilation, 0, 0,
+                    halo_left_valid, halo_right_valid, (cudaStream_t)stream};
+        rc = launch_fir1d_ideal(t, h);
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
+    }
     Fir1dArgs a{x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation, 0, 0,
                 halo_left_valid, halo_right_valid, (cudaStream_t)stream};
     return launch_fir1d_ideal(a, h);
@@ -630,9 +667,8 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         return 0;
     }
     // int32 / float containers: one streaming pass to uint8 pixels, then the tensor-map kernel.
-    if ((in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64) && out_dtype == FIRGPU_U8 &&
-        (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1) && (width & 1) == 0 &&
-        n_img * height * width >= 4096 && !getenv("FIRGPU_FORCE_GENERIC")) {
+    if (convert_first(in_dtype, n_img * height * width) && out_dtype == FIRGPU_U8 &&
+        (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1) && (width & 1) == 0) {
         const int64_t band = halo_top_valid + height + halo_bottom_valid;
         const int64_t ld_t = (width + 15) / 16 * 16;
         uint8_t *tmp = nullptr;
