@@ -118,6 +118,48 @@ def test_2d_ideal_bit_identical_and_f32_tolerance():
         assert np.max(np.abs(got32 - want)) <= 1e-6 * 255 * float(np.sum(np.abs(k)))
 
 
+def test_2d_ideal_fast_kernel_bit_identical():
+    """fir2d_ideal_fast_kernel (uint8 / int16 pixels, 3x3 / 5x5 / 3x5 / 5x3): even
+    and odd widths, column views (every store / load alignment), several
+    images, row bands with halo rows — bit-identical to the oracle in float64,
+    within the stated tolerance in float32, and nothing written outside."""
+    import torch
+    import firgpu
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(41)
+    kernels = [rng.uniform(-2, 2, size=s).tolist() for s in ((3, 3), (5, 5), (3, 5), (5, 3))]
+    for dtype in (np.uint8, np.int16):
+        for shape in ((1, 9, 16), (2, 33, 1031), (1, 70, 2050), (3, 5, 777)):
+            x = image(rng, shape, dtype)
+            for k in kernels:
+                got = firgpu.fir2d_ideal(cuda(x), k)
+                assert _lib.last_path() == _lib.PATH_STAGED, (dtype, shape)
+                assert np.array_equal(got.cpu().numpy(), onp.fir2d_ideal(x, k)), (dtype, shape, np.shape(k))
+    wide = image(rng, (2, 40, 1500), np.uint8)
+    wide_t = cuda(wide)
+    k = kernels[1]
+    for out_dtype, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        for c0, width in ((0, 1500), (1, 1498), (3, 1001), (2, 640)):
+            out = torch.full((2, 40, 1500), -7.0, dtype=tdt, device="cuda")
+            firgpu.fir2d_ideal(wide_t[:, :, c0:c0 + width], k, out_dtype=out_dtype, out=out[:, :, c0:c0 + width])
+            assert _lib.last_path() == _lib.PATH_STAGED
+            want = onp.fir2d_ideal(wide[:, :, c0:c0 + width], k)
+            got = out.cpu().numpy()
+            if out_dtype is np.float64:
+                assert np.array_equal(got[:, :, c0:c0 + width], want), (c0, width)
+            else:
+                assert np.abs(got[:, :, c0:c0 + width] - want).max() <= 1e-6 * 255 * np.abs(k).sum()
+            assert (got[:, :, :c0] == -7.0).all() and (got[:, :, c0 + width:] == -7.0).all(), (c0, width)
+    x = image(rng, (1, 300, 514), np.int16)
+    want = onp.fir2d_ideal(x, k)
+    got = np.empty_like(want)
+    for band in shard.plan_bands(300, 3, 5):
+        buf, body = shard.scatter_band(x, band, "cuda")
+        y = firgpu.fir2d_ideal(body, k, halo_top_valid=band.before, halo_bottom_valid=band.after)
+        got[..., band.start:band.stop, :] = y.cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_row_band_shards_are_seamless():
     """Config 4 sharding: row bands with duplicated halo rows give exactly the
     whole-image result."""

@@ -178,6 +178,15 @@ def main():
             report(f"multi-filter x4 {hgt}x{wid} u8 -> 4 x u8 5tap q4.12 (1 read + 4 writes)", s, hgt * wid, 5)
             s = timed(lambda: [firgpu.fir1d_fixed(x, h, validate=False) for h in sets], args.reps)
             report(f"4 single passes {hgt}x{wid} u8 -> u8 5tap q4.12 (same 5 B/px accounting)", s, hgt * wid, 5)
+    if "ideal2d" in cases:
+        img = rand_i16(8192 * 8192).clamp(0, 255).to(torch.uint8).view(8192, 8192)
+        k5 = np.outer(LP5, LP5).tolist()
+        for k, tag in (([[1 / 9] * 3] * 3, "3x3"), (k5, "5x5")):
+            for odt, tdt, nb in ((np.float64, torch.float64, 9), (np.float32, torch.float32, 5)):
+                out = torch.empty(8192, 8192, dtype=tdt, device="cuda")
+                s = timed(lambda: firgpu.fir2d_ideal(img, k, out_dtype=odt, out=out, validate=False), 5)
+                report(f"2d ideal 8192^2 u8->{np.dtype(odt).name} {tag}", s, 8192 * 8192, nb)
+                del out
     if "containers" in cases:
         # int32 / float sample containers: rounding pass to uint8 + staged kernel.  Algorithmic bytes per
         # sample = container read + 1 output byte; the uint8 temporary (1 write + 1 read) is extra traffic.

@@ -172,6 +172,8 @@ int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols
 // fir2d.cu
 int launch_fir2d_fixed_generic(const Fir2dArgs &a, const int32_t *hq_host);
 int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);
+// fir2d_ideal_fast.cu — 1 = served, 0 = not eligible
+int try_launch_fir2d_ideal_fast(const Fir2dArgs &a, const double *h_host);
 int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq_host);
 
 // Device copy of a long tap vector, freed on the stream after the launch.

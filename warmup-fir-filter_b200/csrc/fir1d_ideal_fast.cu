@@ -22,6 +22,7 @@
 // changes it (x + (+-0.0) == x for every x, and +0.0 + (-0.0) == +0.0), so the
 // padded form is bit-identical to the reference's "skip taps outside the row".
 #include "common.cuh"
+#include "ideal_common.cuh"
 
 #include <cstdlib>
 
@@ -38,21 +39,6 @@ template <int L> struct TapsF64 {
 template <typename F> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
-
-// exact integer -> floating point for 0 <= v <= 255 without a conversion instruction
-template <typename F> __device__ __forceinline__ F pixel_to(int v);
-template <> __device__ __forceinline__ double pixel_to<double>(int v)
-{
-    return __dadd_rn(__hiloint2double(0x43300000, v), -4503599627370496.0);      // (2^52 + v) - 2^52
-}
-template <> __device__ __forceinline__ float pixel_to<float>(int v)
-{
-    return __fadd_rn(__uint_as_float(0x4b000000u | (uint32_t)v), -8388608.0f);   // (2^23 + v) - 2^23
-}
-
-template <typename InT> struct PairOf;
-template <> struct PairOf<uint8_t> { using type = uint16_t; };
-template <> struct PairOf<int16_t> { using type = uint32_t; };
 
 template <typename InT, typename F, int L, int kGroups>   // kGroups output groups per lane per tile
 __global__ void __launch_bounds__(kThreadsI)

@@ -182,6 +182,9 @@ int launch_fir2d_fixed_generic(const Fir2dArgs &a, const int32_t *hq_host)
 
 int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host)
 {
+    const int fast = try_launch_fir2d_ideal_fast(a, h_host);
+    if (fast == 1) return 0;
+    if (fast != 0) return fast;
     switch (a.out_dtype) {
     case FIRGPU_F64: return dispatch_ideal_in<double>(a, h_host);
     case FIRGPU_F32: return dispatch_ideal_in<float>(a, h_host);

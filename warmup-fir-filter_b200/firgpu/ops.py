@@ -167,6 +167,24 @@ def _cuda_rows(x, allow_copy: bool, lo: int = 0, hi: int = 255):
     return t, rows, cols, cols
 
 
+def _cuda_imgs(t, what: str):
+    """CUDA tensor [..., H, W] -> (n_img, H, W, row pitch, image stride) in
+    elements when it can be addressed in place: last axis dense, at most three
+    axes (or contiguous leading axes), non-overlapping rows.  Column / row
+    views of a larger image and row bands qualify."""
+    n, hgt, wid = _imgs(t.shape)
+    if t.is_contiguous():
+        return n, hgt, wid, wid, hgt * wid
+    ok = t.dim() in (2, 3) and (t.stride(-1) == 1 or wid <= 1) and (t.stride(-2) >= wid or hgt <= 1)
+    if ok and t.dim() == 3:
+        ok = t.stride(0) >= (hgt - 1) * t.stride(-2) + wid or n <= 1
+    if not ok:
+        raise ValueError(f"{what} must be contiguous or a dense-last-axis view of at most three axes")
+    ld = int(t.stride(-2)) if hgt > 1 else wid
+    img_stride = int(t.stride(0)) if (t.dim() == 3 and n > 1) else hgt * ld
+    return n, hgt, wid, ld, img_stride
+
+
 def _host_out(out, shape, dtype):
     """The caller's ``out`` (or a fresh array) for a host-buffer call: must be a
     C-contiguous array / CPU tensor of exactly the expected shape and dtype,
@@ -526,9 +544,12 @@ def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_
     return y
 
 
-def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, validate: bool = True):
+def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, validate: bool = True,
+                halo_top_valid: int = 0, halo_bottom_valid: int = 0):
     """float64 (bit-identical to the scalar specification) or float32 2-D FIR
-    over the last two axes; taps visited row-major, unfused multiply + add."""
+    over the last two axes; taps visited row-major, unfused multiply + add.
+    CUDA tensors may be column / row views of a larger image (``x`` and ``out``
+    alike) and row bands with ``halo_*_valid`` real rows above / below."""
     hh = np.ascontiguousarray(quant.validate_taps_2d(h2d))
     kh, kw = hh.shape
     L = _lib.lib()
@@ -537,16 +558,30 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
         import torch
         if validate:
             _check_finite_torch(x)
-        t = _torch_container(x)
-        n, hgt, wid = _imgs(t.shape)
+        native = x.dtype in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64)
+        in_place = native and not x.is_contiguous() and x.dim() in (2, 3) and x.stride(-1) == 1
+        if (halo_top_valid or halo_bottom_valid) and not (native and (x.is_contiguous() or in_place)):
+            raise ValueError("halo rows need a tensor that can be read in place")
+        t = x if (native and (x.is_contiguous() or in_place)) else _torch_container(x)
+        try:
+            n, hgt, wid, ld, img_stride = _cuda_imgs(t, "x")
+        except ValueError:
+            if halo_top_valid or halo_bottom_valid:
+                raise
+            t = _torch_container(x)                      # odd view without halos: filter a dense copy
+            n, hgt, wid, ld, img_stride = _cuda_imgs(t, "x")
         y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
-        if not y.is_contiguous() or tuple(y.shape) != tuple(t.shape):
-            raise ValueError("out must be a contiguous tensor of the input's shape")
+        if tuple(y.shape) != tuple(t.shape) or y.dtype != _torch_dtype(out_dtype) or not y.is_cuda:
+            raise ValueError(f"out must be a CUDA {np.dtype(out_dtype)} tensor of the input's shape")
+        _, _, _, ld_y, img_stride_y = _cuda_imgs(y, "out")
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, wid, wid,
-                                            hgt * wid, hgt * wid, _taps_ptr(hh), kh, kw, 0, 0, stream))
+            _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, ld_y,
+                                            img_stride, img_stride_y, _taps_ptr(hh), kh, kw, halo_top_valid,
+                                            halo_bottom_valid, stream))
         return y
+    if halo_top_valid or halo_bottom_valid:
+        raise ValueError("halo_*_valid apply to device-resident shards only")
     was_torch = _is_torch(x)
     a = _np_container(x.numpy() if was_torch else x)
     if validate:
