@@ -1,7 +1,7 @@
 // Fast path of the floating-point 2-D model (DESIGN.md §2 "fir_2d": the 2-D
 // counterpart of fir_1d/model/python/fir_1d_ref.py:43-65) for uint8 / int16
 // pixels, 3x3 and 5x5 windows, float64 (bit-identical to the generic kernel and
-// the oracle) or float32 (tolerance) output.
+// the scalar specification) or float32 (tolerance) output.
 //
 // Same construction as fir1d_ideal_fast.cu: registers only, a lane produces one
 // 16-byte store worth of adjacent outputs of one row (2 doubles / 4 floats) and
