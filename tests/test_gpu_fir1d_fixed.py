@@ -303,7 +303,8 @@ def test_multi_filter_reads_input_once(fg, torch, manifest):
             want = np.stack([onp.fir1d_fixed(x, h) for h in sets])
             before = _lib.launch_count()
             got = fg.fir1d_fixed_multi(torch.from_numpy(x).cuda(), sets)
-            assert _lib.launch_count() - before == 1 and _lib.last_path() == _lib.PATH_STAGED
+            # one pass over the input; dense rows of odd pitch add one launch that rewrites the row ends of all four outputs
+            assert _lib.launch_count() - before == (2 if shape == (37, 4499) else 1) and _lib.last_path() == _lib.PATH_STAGED
             assert got.shape == (4,) + shape and np.array_equal(got.cpu().numpy(), want), (tap, shape)
             assert np.array_equal(fg.fir1d_fixed_multi(x, sets), want), (tap, shape, "host")
     x = rng.integers(-100, 400, size=(3, 10_001)).astype(np.int16)
@@ -469,3 +470,39 @@ def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):
             assert np.array_equal(np.asarray(fg.fir1d_ideal(x, [1.0]), dtype=np.float64), want.astype(np.float64))
             img = x[: (x.size // 64) * 64].reshape(-1, 64)
             assert np.array_equal(fg.fir2d_fixed(img, [[0, 0, 0], [0, 1.0, 0], [0, 0, 0]]), want[: img.size].reshape(img.shape))
+
+
+def test_dense_rows_of_odd_pitch_take_the_flattened_pass(fg, torch):
+    """Row batches whose pitch is not a multiple of 16 bytes (odd image widths,
+    the reference's 4499-wide image) are filtered as one long row by the
+    staged kernel, then the outputs within reach of a row end are rewritten:
+    bit-exact with per-row zero padding, for every container pair, I/Q
+    dilation, long filters and the four-tap-set pass."""
+    from firgpu import _lib
+    from fir_1d.sim.vector.h_coeff import h_coeff_3tap_map, h_coeff_5tap_map
+    rng = np.random.default_rng(77)
+    for shape in ((7, 1501), (33, 4499), (100, 255), (3, 1502)):
+        for in_dtype in (np.uint8, np.int16):
+            x = rng.integers(0, 256, size=shape).astype(in_dtype)
+            if in_dtype == np.int16:
+                x[rng.random(shape) < 0.03] = -4000
+                x[rng.random(shape) < 0.03] = 9000
+            xt = torch.from_numpy(x).cuda()
+            for out_dtype in (np.uint8, np.int16):
+                for h, frac in ((SIMPLE_LP5, 15), ([-1.0, 0.0, 1.0], 12), ([0.2] * 9, 12)):
+                    got = fg.fir1d_fixed(xt, h, frac, 32, 16, out_dtype=out_dtype)
+                    assert _lib.last_path() == _lib.PATH_STAGED, (shape, in_dtype, out_dtype, len(h))
+                    assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x, h, frac, 32, 16, out_dtype=out_dtype)), (shape, in_dtype, out_dtype, len(h))
+            if shape[1] % 2 == 0:                                        # interleaved I/Q rows
+                got = fg.fir1d_fixed(xt, SIMPLE_LP5, 15, 32, 16, dilation=2, out_dtype=in_dtype)
+                assert _lib.last_path() == _lib.PATH_STAGED
+                assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x, SIMPLE_LP5, 15, 32, 16, dilation=2, out_dtype=in_dtype))
+            if in_dtype == np.uint8:
+                for sets in (list(h_coeff_3tap_map.values()), list(h_coeff_5tap_map.values())):
+                    got = fg.fir1d_fixed_multi(xt, sets)
+                    assert _lib.last_path() == _lib.PATH_STAGED
+                    assert np.array_equal(got.cpu().numpy(), np.stack([onp.fir1d_fixed(x, h) for h in sets])), shape
+    x = rng.integers(0, 256, size=(5, 3001)).astype(np.uint8)            # long filter: 21 taps -> 25-tap bucket
+    h21 = (np.ones(21) / 42).tolist()
+    assert np.array_equal(fg.fir1d_fixed(torch.from_numpy(x).cuda(), h21, 15, 32, 16).cpu().numpy(), onp.fir1d_fixed(x, h21, 15, 32, 16))
+    assert _lib.last_path() == _lib.PATH_STAGED

@@ -519,6 +519,23 @@ int uint8_copy_1d(const void *x, int in_dtype, int64_t rows, int64_t cols, int64
 }
 
 int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtype == FIRGPU_I16 ? 2 : 0; }
+
+// "Flattened pass": a dense batch of rows (pitch == cols) whose pitch is not a multiple of 16 bytes — odd image
+// widths — cannot be staged row by row with bulk copies.  Filtering the whole batch as ONE long row gives the right
+// answer everywhere except within the taps' reach of a row end (where the neighbouring row's samples stand in for the
+// zero padding); launch_fir1d_fixed_edges() then rewrites exactly those outputs.
+bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                int n_taps, int dilation)
+{
+    if (rows < 2 || ld_x != cols || ld_y != cols) return false;
+    if (in_dtype != FIRGPU_U8 && in_dtype != FIRGPU_I16) return false;
+    const int es = in_dtype == FIRGPU_U8 ? 1 : 2, os = out_size_fixed(out_dtype);
+    if ((cols * es) % 16 == 0 && (cols * os) % 16 == 0) return false;          // aligned pitches: the regular paths apply
+    if (((uintptr_t)x | (uintptr_t)y) % 16) return false;
+    if (dilation == 2 && (cols & 1)) return false;                             // I/Q pairs must not straddle rows
+    if (cols < 8LL * (n_taps - 1) * dilation) return false;                    // mostly edges: not worth two launches
+    return !getenv("FIRGPU_FORCE_GENERIC") && !getenv("FIRGPU_NO_FLATTEN");
+}
 int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
 
 }  // namespace
@@ -570,6 +587,14 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         cudaFreeAsync(tmp, (cudaStream_t)stream);
         return rc;
     }
+    if (flatten_ok(x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation) && halo_left_valid == 0 && halo_right_valid == 0) {
+        Fir1dArgs flat = a;
+        flat.rows = 1;
+        flat.cols = flat.ld_x = flat.ld_y = rows * cols;
+        rc = try_launch_fir1d_fixed_staged(flat, hq);
+        if (rc == 1) return launch_fir1d_fixed_edges(a, hq);
+        if (rc != 0) return rc;
+    }
     // Many short rows (images, short channels): the row-streaming tensor-map
     // kernel keeps whole CTAs busy where the 1-D tile kernel would stage one
     // mostly empty tile per row.  Its TMA out-of-bounds zero fill is the
@@ -613,10 +638,23 @@ int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype
     }
     // Groups of four tap sets are served by ONE pass of the staged kernel (the
     // input is read from HBM once); the rest one tap set at a time.
+    const bool flatten = flatten_ok(x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, n_taps, dilation) &&
+                         ((size_t)filter_stride_y * os) % 16 == 0;
     int f = 0;
     for (; f + 4 <= n_filters; f += 4) {
         Fir1dArgs a{x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows, cols, ld_x, ld_y,
                     n_taps, dilation, frac_bits, acc_bits, 0, 0, (cudaStream_t)stream};
+        if (flatten) {                                // dense rows of odd pitch: one long row, then the row ends
+            Fir1dArgs flat = a;
+            flat.rows = 1;
+            flat.cols = flat.ld_x = flat.ld_y = rows * cols;
+            rc = try_launch_fir1d_fixed_staged_multi(flat, hq + (size_t)f * n_taps, 4, filter_stride_y);
+            if (rc == 1) {
+                if ((rc = launch_fir1d_fixed_edges(a, hq + (size_t)f * n_taps, 4, filter_stride_y))) return rc;
+                continue;
+            }
+            if (rc != 0) return rc;
+        }
         rc = try_launch_fir1d_fixed_staged_multi(a, hq + (size_t)f * n_taps, 4, filter_stride_y);
         if (rc == 1) continue;
         if (rc != 0) return rc;

@@ -154,6 +154,8 @@ struct Fir2dArgs {
 // fir1d_generic.cu
 int launch_fir1d_fixed_generic(const Fir1dArgs &a, const int32_t *hq_host);
 int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host);
+// rewrites the outputs within reach of a row end (after a flattened pass over a dense row batch)
+int launch_fir1d_fixed_edges(const Fir1dArgs &a, const int32_t *hq_host, int n_filters = 1, int64_t filter_stride_y = 0);
 // fir1d_ideal_fast.cu — 1 = served, 0 = not eligible
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /

@@ -525,13 +525,17 @@ def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_
     if is_t and x.is_cuda:
         import torch
         t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
-        y = torch.empty((nf,) + tuple(x.shape), dtype=_torch_dtype(out_dtype), device=x.device)
+        # every tap set's output starts 256-byte aligned (the kernels' vector stores and the flattened pass for odd
+        # image widths need 16): the result is a view [nf, ...] of a buffer with a padded stride between tap sets
+        n = rows * cols
+        stride = -(-n // 256) * 256
+        flat = torch.empty(nf * stride, dtype=_torch_dtype(out_dtype), device=x.device)
         with _on_device(torch, x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(L.firgpu_fir1d_fixed_multi(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld,
-                                                  cols, rows * cols, _taps_ptr(hq), nf, n_taps, 1, frac_bits, acc_bits,
+            _lib.check(L.firgpu_fir1d_fixed_multi(t.data_ptr(), flat.data_ptr(), _torch_code(t), out_code, rows, cols, ld,
+                                                  cols, stride, _taps_ptr(hq), nf, n_taps, 1, frac_bits, acc_bits,
                                                   stream))
-        return y
+        return flat.view(nf, stride)[:, :n].unflatten(1, tuple(x.shape)) if x.dim() > 0 and n else flat.view(nf, stride)[:, :n].reshape((nf,) + tuple(x.shape))
     a = _np_container(x.numpy() if is_t else x)
     rows, cols = _rows_cols(a.shape)
     y = np.empty((nf,) + a.shape, dtype=out_dtype)
