@@ -396,3 +396,33 @@ def test_published_accuracy_tables_from_inputs_alone(tmp_path, images_inputs, im
     assert s5["worst"]["key"] == "case_004_img_005_64x64_noise_gray__edge" and r4(s5["worst"]["rmse"]) == 13.4034
     assert round(100 * (s5["summary"]["avg_mae"] / s3["summary"]["avg_mae"] - 1), 2) == -53.06
     assert round(100 * (s5["summary"]["avg_rmse"] / s3["summary"]["avg_rmse"] - 1), 2) == -49.40
+
+
+def test_causal_raw_float64_model_on_the_fast_kernel():
+    """The C++ Fir1D model (causal alignment, raw float64 samples,
+    fir_1d/model/cpp/fir_1d_ref.cpp:16-63) runs on the register kernel for up to
+    nine taps: bit-identical to the oracle for every tap count, ragged lengths,
+    several rows, views at odd offsets, and block-wise streaming with carried
+    state equals one call over the whole signal."""
+    import torch
+    import firgpu
+    from firgpu import _lib
+    from fir_1d.model.python.fir_1d_stream import Fir1D
+    rng = np.random.default_rng(53)
+    for n_taps in range(1, 10):
+        h = rng.uniform(-3, 3, size=n_taps).tolist()
+        for shape in ((1, 5), (1, 70_001), (3, 2049), (4, 1501)):
+            x = rng.normal(0, 1e3, size=shape)
+            got = firgpu.fir1d_ideal(torch.from_numpy(x).cuda(), h, centre=0, raw=True)
+            assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, shape)
+            assert np.array_equal(got.cpu().numpy(), onp.fir1d_ideal(x, h, centre=0, raw=True)), (n_taps, shape)
+    big = rng.normal(0, 50, size=200_003)
+    h = [0.5, -0.25, 0.125, 0.3, -0.7]
+    want = onp.fir1d_ideal(big, h, centre=0, raw=True)
+    big_t = torch.from_numpy(big).cuda()
+    for c0 in (1, 2, 3):                                              # misaligned views
+        got = firgpu.fir1d_ideal(big_t[c0:c0 + 100_000], h, centre=0, raw=True)
+        assert np.array_equal(got.cpu().numpy(), onp.fir1d_ideal(big[c0:c0 + 100_000], h, centre=0, raw=True)), c0
+    f = Fir1D(h)
+    parts = [f.process_block(big[a:b]) for a, b in ((0, 7), (7, 50_000), (50_000, 50_001), (50_001, big.size))]
+    assert np.array_equal(np.concatenate(parts), want)

@@ -178,6 +178,13 @@ def main():
             report(f"multi-filter x4 {hgt}x{wid} u8 -> 4 x u8 5tap q4.12 (1 read + 4 writes)", s, hgt * wid, 5)
             s = timed(lambda: [firgpu.fir1d_fixed(x, h, validate=False) for h in sets], args.reps)
             report(f"4 single passes {hgt}x{wid} u8 -> u8 5tap q4.12 (same 5 B/px accounting)", s, hgt * wid, 5)
+    if "causal" in cases:
+        g = torch.Generator(device="cuda").manual_seed(9)
+        x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)
+        y = torch.empty_like(x)
+        s = timed(lambda: firgpu.fir1d_ideal(x, LP5, centre=0, raw=True, out=y, validate=False), 5)
+        report("causal raw f64->f64 2^26 5tap (C++ Fir1D model)", s, 1 << 26, 16)
+        del x, y
     if "ideal2d" in cases:
         img = rand_i16(8192 * 8192).clamp(0, 255).to(torch.uint8).view(8192, 8192)
         k5 = np.outer(LP5, LP5).tolist()

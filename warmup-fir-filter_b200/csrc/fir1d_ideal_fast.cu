@@ -40,7 +40,10 @@ template <typename F> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
-template <typename InT, typename F, int L, int kGroups>   // kGroups output groups per lane per tile
+// CAUSAL = false: the Python model (output n reads samples n + L/2 ... n - (L-1-L/2), rounded and clamped pixels).
+// CAUSAL = true, InT = double: the C++ Fir1D model (fir_1d/model/cpp/fir_1d_ref.cpp:16-63): y[n] = sum h[k] x[n-k] on the
+// samples as they are.
+template <typename InT, typename F, int L, int kGroups, bool CAUSAL>   // kGroups output groups per lane per tile
 __global__ void __launch_bounds__(kThreadsI)
 fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
                         int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
@@ -50,7 +53,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     constexpr int OP = 16 / (2 * (int)sizeof(F));        // output pairs per group: one 16-byte store (2 doubles / 4 floats)
     constexpr int G = 2 * OP;                            // outputs per group
     constexpr int kTileI = 32 * G * kGroups;             // outputs per warp tile
-    constexpr int hi = L / 2, lo = L - 1 - hi;
+    constexpr int hi = CAUSAL ? 0 : L / 2, lo = L - 1 - hi;
     constexpr int PL = (lo + 1) / 2, PR = (hi + 1) / 2;  // neighbour pairs a window reaches into, left / right
     constexpr int NP = PL + OP + PR;                     // sample pairs per window: samples base - 2 PL ... base + G - 1 + 2 PR
     using P2 = typename PairOf<InT>::type;
@@ -72,8 +75,15 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
         }
     };
 
+    auto one = [](InT v) -> F {
+        if constexpr (sizeof(InT) == 8) return (F)v;       // raw samples
+        else return pixel_to<F>(prep_sample(v));
+    };
     auto widen = [](P2 r, F &w0, F &w1) {
-        if constexpr (sizeof(InT) == 1) {
+        if constexpr (sizeof(InT) == 8) {
+            w0 = (F)r.x;
+            w1 = (F)r.y;
+        } else if constexpr (sizeof(InT) == 1) {
             w0 = pixel_to<F>(r & 0xff);
             w1 = pixel_to<F>(r >> 8);
         } else {
@@ -129,8 +139,8 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
                     if (x_pairs && g >= vlo && g + 1 < vhi) {
                         widen(*reinterpret_cast<const P2 *>(xr + g), w[2 * p], w[2 * p + 1]);
                     } else {
-                        w[2 * p] = (g >= vlo && g < vhi) ? pixel_to<F>(prep_sample(xr[g])) : (F)0;
-                        w[2 * p + 1] = (g + 1 >= vlo && g + 1 < vhi) ? pixel_to<F>(prep_sample(xr[g + 1])) : (F)0;
+                        w[2 * p] = (g >= vlo && g < vhi) ? one(xr[g]) : (F)0;
+                        w[2 * p + 1] = (g + 1 >= vlo && g + 1 < vhi) ? one(xr[g + 1]) : (F)0;
                     }
                 }
                 F a[G];
@@ -154,7 +164,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     }
 }
 
-template <typename InT, typename F, int L, int kGroups>
+template <typename InT, typename F, int L, int kGroups, bool CAUSAL>
 int run_groups(const Fir1dArgs &a, const double *h_host)
 {
     constexpr int kWarps = kThreadsI / 32;
@@ -179,7 +189,7 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
     if (per_sm > 0 && grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
     if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     if (grid < 1) grid = 1;
-    fir1d_ideal_fast_kernel<InT, F, L, kGroups><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
+    fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
@@ -189,17 +199,10 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
 template <typename InT, int L>
 int run(const Fir1dArgs &a, const double *h_host)
 {
-    // groups per lane per tile (tuning knob: FIRGPU_IDEAL_GROUPS=2|4|8)
-    static int forced = -1;
-    if (forced < 0) {
-        const char *e = getenv("FIRGPU_IDEAL_GROUPS");
-        forced = e ? atoi(e) : 0;
-    }
-    const bool f32 = a.out_dtype == FIRGPU_F32;
-    const int g = forced ? forced : (f32 ? 4 : 8);
-    if (g == 2) return f32 ? run_groups<InT, float, L, 2>(a, h_host) : run_groups<InT, double, L, 2>(a, h_host);
-    if (g == 4) return f32 ? run_groups<InT, float, L, 4>(a, h_host) : run_groups<InT, double, L, 4>(a, h_host);
-    return f32 ? run_groups<InT, float, L, 8>(a, h_host) : run_groups<InT, double, L, 8>(a, h_host);
+    // groups per lane per tile: 512-output warp tiles measured best for both output types (sweep in profiles/README.md)
+    if constexpr (sizeof(InT) == 8) return run_groups<InT, double, L, 8, true>(a, h_host);
+    else if (a.out_dtype == FIRGPU_F32) return run_groups<InT, float, L, 4, false>(a, h_host);
+    else return run_groups<InT, double, L, 8, false>(a, h_host);
 }
 
 template <typename InT>
@@ -225,9 +228,11 @@ int by_taps(const Fir1dArgs &a, const double *h)
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
 {
     if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
-    if (!a.is_reference_model()) return 0;
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
     if (force && force[0] == '1') return 0;
+    // the C++ Fir1D model: causal, raw float64 samples, float64 output
+    if (a.raw && a.centre == 0 && a.in_dtype == FIRGPU_F64 && a.out_dtype == FIRGPU_F64) return by_taps<double>(a, h_host);
+    if (!a.is_reference_model()) return 0;
     if (a.in_dtype == FIRGPU_U8) return by_taps<uint8_t>(a, h_host);
     if (a.in_dtype == FIRGPU_I16) return by_taps<int16_t>(a, h_host);
     return 0;

@@ -20,6 +20,7 @@ template <> __device__ __forceinline__ float pixel_to<float>(int v)
 template <typename InT> struct PairOf;
 template <> struct PairOf<uint8_t> { using type = uint16_t; };
 template <> struct PairOf<int16_t> { using type = uint32_t; };
+template <> struct PairOf<double> { using type = double2; };
 
 }  // namespace
 }  // namespace firgpu
