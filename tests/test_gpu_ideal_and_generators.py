@@ -285,6 +285,16 @@ def test_signed_int16_and_alignment_modes_against_oracle():
     y = firgpu.fir1d_fixed(xt, h, 12, 32, 16, centre=2, in_range=(0, 255), out_range=(0, 255))
     assert _lib.last_path() == _lib.PATH_STAGED and np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h))
     assert firgpu.fir1d_fixed(xt, h, in_range=full, out_range=full).dtype == torch.int16
+    # off-centre alignments run on the centred fast kernels with zero taps added in front / behind
+    for centre in (0, 1, 4):
+        for kw in ({}, {"in_range": full, "out_range": full}):
+            y = firgpu.fir1d_fixed(xt, h, 15, 32, 16, centre=centre, out_dtype=np.int16, **kw)
+            assert _lib.last_path() == _lib.PATH_STAGED, (centre, kw)
+            assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h, 15, 32, 16, centre=centre, out_dtype=np.int16, **kw))
+    h17 = rng.uniform(-0.2, 0.2, size=17).tolist()                       # causal 17 taps -> centred 33-tap bucket
+    y = firgpu.fir1d_fixed(xt, h17, 12, 32, 16, centre=0, out_dtype=np.int16)
+    assert _lib.last_path() == _lib.PATH_STAGED
+    assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h17, 12, 32, 16, centre=0, out_dtype=np.int16))
     # ideal model with alignment / clamp range
     for centre in (0, 3):
         want = onp.fir1d_ideal(x, h, centre=centre, in_range=(-50, 900))

@@ -4,6 +4,7 @@
 // Nothing here computes a filter on the CPU.  Every compute entry point ends
 // in a CUDA launch or fails with the cudaError_t it got; there is no fallback.
 #include "common.cuh"
+#include "fastplan.h"
 
 #include <algorithm>
 #include <chrono>
@@ -936,10 +937,25 @@ int firgpu_fir1d_fixed_ex(const void *x, void *y, int in_dtype, int out_dtype, i
     a.in_hi = in_hi;
     a.out_lo = out_lo;
     a.out_hi = out_hi;
-    if (a.is_reference_model()) {           // the reference's own parameters: the fast kernels apply
-        rc = try_launch_fir1d_fixed_staged(a, hq);
+    // Any alignment is the centred filter with zero taps in front of / behind the real ones (a zero tap adds nothing
+    // to the integer sum), so causal and other off-centre filters run on the centred fast kernels too.
+    Fir1dArgs fast = a;
+    int32_t padded[kFastPlanMaxTaps];
+    const int32_t *fast_taps = hq;
+    const int c = centre < 0 ? n_taps / 2 : centre;
+    if (c != n_taps / 2) {
+        const int reach = std::max(c, n_taps - 1 - c), wide_taps = 2 * reach + 1, off = reach - c;
+        if (wide_taps <= kFastPlanMaxTaps) {
+            for (int k = 0; k < wide_taps; ++k) padded[k] = (k >= off && k < off + n_taps) ? hq[k - off] : 0;
+            fast.n_taps = wide_taps;
+            fast.centre = -1;
+            fast_taps = padded;
+        }
+    }
+    if (fast.is_reference_model()) {        // the reference's own parameters: the fast kernels apply
+        rc = try_launch_fir1d_fixed_staged(fast, fast_taps);
     } else {                                // other clamp ranges on int16 containers: wide datapath
-        rc = try_launch_fir1d_fixed_staged_wide(a, hq);
+        rc = try_launch_fir1d_fixed_staged_wide(fast, fast_taps);
     }
     if (rc == 1) return 0;
     if (rc != 0) return rc;
