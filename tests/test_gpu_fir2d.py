@@ -167,7 +167,8 @@ def test_row_band_shards_are_seamless():
     from firgpu import shard
     from firgpu import _lib
     rng = np.random.default_rng(5)
-    for width, path in ((1100, _lib.PATH_GENERIC), (1104, _lib.PATH_STAGED)):     # 2200-byte pitch is not TMA-able
+    # a 2200-byte pitch is not TMA-able: such bands are copied to an aligned pitch first, then take the same kernel
+    for width, path in ((1100, _lib.PATH_STAGED), (1104, _lib.PATH_STAGED)):
         x = image(rng, (2, 700, width))
         for k in (K3_SHARPEN, K5_LP):
             kh = len(k)
@@ -181,6 +182,29 @@ def test_row_band_shards_are_seamless():
                     assert _lib.last_path() == path
                     got[:, band.start:band.stop, :] = y.cpu().numpy()
                 assert np.array_equal(got, want), (width, kh, parts)
+
+
+def test_2d_images_of_odd_width_and_pitch():
+    """uint8 / int16 images the tensor-map kernel cannot read in place (odd
+    widths such as the reference's 4499, pitches that are not multiples of 16
+    bytes, column views, unaligned bases) are re-pitched into an aligned
+    temporary and run on the tiled kernel: bit-exact, nothing written outside."""
+    import torch
+    import firgpu
+    from firgpu import _lib
+    rng = np.random.default_rng(15)
+    for dtype in (np.uint8, np.int16):
+        for shape in ((1, 200, 4499), (2, 97, 333), (3, 64, 1001), (1, 70, 1102)):
+            x = image(rng, shape, dtype)
+            for k in (K3_BOX, K3_SHARPEN, K5_LP, rng.uniform(-0.4, 0.4, size=(5, 5)).tolist(), rng.uniform(-1, 1, size=(3, 5)).tolist()):
+                got = firgpu.fir2d_fixed(cuda(x), k, 12, 32, 16, out_dtype=dtype)
+                assert _lib.last_path() == _lib.PATH_STAGED, (dtype, shape, np.shape(k))
+                assert np.array_equal(got.cpu().numpy(), onp.fir2d_fixed(x, k, 12, 32, 16, out_dtype=dtype)), (dtype, shape, np.shape(k))
+    x = image(rng, (1, 120, 2000), np.uint8)
+    xt = cuda(x)
+    for c0, width in ((1, 1998), (3, 1001), (16, 1024)):                  # column views: unaligned base / odd width
+        got = firgpu.fir2d_fixed_q(xt[:, :, c0:c0 + width], onp.quantize_taps(K5_LP, 12, 16), 12, 32)
+        assert np.array_equal(got.cpu().numpy(), onp.fir2d_fixed(x[:, :, c0:c0 + width], K5_LP)), (c0, width)
 
 
 def test_2d_host_entry_point():

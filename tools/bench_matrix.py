@@ -21,7 +21,7 @@ for p in (str(ROOT), str(ROOT / "warmup-fir-filter_b200")):
 import torch  # noqa: E402
 
 import firgpu  # noqa: E402
-from firgpu import _lib  # noqa: E402
+from firgpu import _lib, quant  # noqa: E402
 
 LP5 = [1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16]
 LP3 = [0.25, 0.5, 0.25]
@@ -146,7 +146,6 @@ def main():
         out = torch.empty_like(img)
         k3 = [[1 / 9] * 3] * 3
         k5 = np.outer(LP5, LP5).tolist()
-        from firgpu import quant
         kr = np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist()
         for k, tag in ((k3, "3x3 box"), (k5, "5x5 lp rank-1"), (kr, "5x5 general")):
             hq = quant.quantize_taps(np.asarray(k), 12, 16)
@@ -178,6 +177,14 @@ def main():
             report(f"multi-filter x4 {hgt}x{wid} u8 -> 4 x u8 5tap q4.12 (1 read + 4 writes)", s, hgt * wid, 5)
             s = timed(lambda: [firgpu.fir1d_fixed(x, h, validate=False) for h in sets], args.reps)
             report(f"4 single passes {hgt}x{wid} u8 -> u8 5tap q4.12 (same 5 B/px accounting)", s, hgt * wid, 5)
+    if "2dodd" in cases:
+        # the reference's largest image (odd width and pitch): re-pitched copy + tiled kernel vs the generic kernel
+        img = rand_i16(2999 * 4499).clamp(0, 255).to(torch.uint8).view(2999, 4499)
+        out = torch.empty_like(img)
+        for k, tag in (([[1 / 9] * 3] * 3, "3x3 box"), (np.outer(LP5, LP5).tolist(), "5x5 lp")):
+            hq = quant.quantize_taps(np.asarray(k), 12, 16)
+            s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out=out), args.reps)
+            report(f"2d 2999x4499 u8->u8 {tag} q4.12 (odd pitch)", s, 2999 * 4499, 2)
     if "causal" in cases:
         g = torch.Generator(device="cuda").manual_seed(9)
         x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)

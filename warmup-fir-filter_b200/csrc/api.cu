@@ -711,20 +711,33 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
-    // int32 / float containers: one streaming pass to uint8 pixels, then the tensor-map kernel.
-    if (convert_first(in_dtype, n_img * height * width) && out_dtype == FIRGPU_U8 &&
-        (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1) && (width & 1) == 0) {
+    // Images the tensor-map kernel cannot read in place are copied once into an aligned temporary and filtered there:
+    // int32 / float containers (rounded and clamped to uint8 pixels on the way), and uint8 / int16 images whose pitch
+    // or base is not 16-byte aligned or whose uint8 width is odd (every row of the copy ends in zero bytes).
+    const bool windows_ok = (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1);
+    const int es_in = dtype_size(in_dtype);
+    const bool convert = convert_first(in_dtype, n_img * height * width) && out_dtype == FIRGPU_U8;
+    const bool repitch = !convert && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16) && in_dtype == out_dtype &&
+                         n_img * height * width >= 4096 && !getenv("FIRGPU_FORCE_GENERIC") &&
+                         ((uintptr_t)x % 16 != 0 || (ld_x * es_in) % 16 != 0 || (n_img > 1 && (img_stride_x * es_in) % 16 != 0) ||
+                          (in_dtype == FIRGPU_U8 && (width & 1)));
+    if (windows_ok && (convert || repitch)) {
+        const int t_dtype = convert ? FIRGPU_U8 : in_dtype;
+        const int es_t = dtype_size(t_dtype);
         const int64_t band = halo_top_valid + height + halo_bottom_valid;
-        const int64_t ld_t = (width + 15) / 16 * 16;
+        const int64_t ld_t = ((width + 1) * es_t + 15) / 16 * 16 / es_t;       // >= one zero element after every row
         uint8_t *tmp = nullptr;
-        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * band * n_img), (cudaStream_t)stream))) return rc;
-        const int es_in = dtype_size(in_dtype);
-        for (int64_t b = 0; b < n_img && !rc; ++b)
-            rc = launch_prep_u8((const char *)x + (b * img_stride_x - halo_top_valid * ld_x) * es_in, in_dtype, tmp + b * band * ld_t,
-                                band, width, ld_x, ld_t, 0, 0, (cudaStream_t)stream);
+        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * band * n_img * es_t), (cudaStream_t)stream))) return rc;
+        for (int64_t b = 0; b < n_img && !rc; ++b) {
+            const char *src = (const char *)x + (b * img_stride_x - halo_top_valid * ld_x) * es_in;
+            uint8_t *dst = tmp + b * band * ld_t * es_t;
+            rc = convert ? launch_prep_u8(src, in_dtype, dst, band, width, ld_x, ld_t, 0, 0, (cudaStream_t)stream)
+                         : launch_repitch(src, in_dtype, dst, band, width, ld_x, ld_t, (cudaStream_t)stream);
+        }
         if (!rc) {
-            Fir2dArgs t{tmp + halo_top_valid * ld_t, y, FIRGPU_U8, out_dtype, n_img, height, width, ld_t, ld_y, band * ld_t,
+            Fir2dArgs t{tmp + halo_top_valid * ld_t * es_t, y, t_dtype, out_dtype, n_img, height, width, ld_t, ld_y, band * ld_t,
                         img_stride_y, kh, kw, frac_bits, acc_bits, halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
+            t.x_row_padded = 1;
             rc = try_launch_fir2d_fixed_tiled(t, hq);
             if (rc == 1) rc = 0;
             else if (rc == 0) rc = launch_fir2d_fixed_generic(t, hq);

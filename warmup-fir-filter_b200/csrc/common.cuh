@@ -149,6 +149,7 @@ struct Fir2dArgs {
     int kh, kw, frac_bits, acc_bits;
     int64_t halo_top, halo_bottom;
     cudaStream_t stream;
+    int x_row_padded = 0;            // uint8 rows are followed by one readable zero byte (re-pitched copies of odd widths)
 };
 
 // fir1d_generic.cu
@@ -166,6 +167,9 @@ int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_hos
 // n_filters tap sets ([n_filters][n_taps]) over one pass of the input; outputs filter_stride_y elements apart.
 int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y);
 // prep_u8.cu — int32 / float32 / float64 containers -> uint8 pixels (round half up, clamp)
+// same-type copy of rows x cols elements (uint8 / int16) to a new pitch, zero-filled up to it (pitches in elements,
+// ld_y * element size a multiple of 4, y 4-byte aligned)
+int launch_repitch(const void *x, int dtype, void *y, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y, cudaStream_t s);
 int launch_prep_u8(const void *x, int in_dtype, uint8_t *y, int64_t rows, int64_t span, int64_t ld_x, int64_t ld_y,
                    int64_t before, int64_t shift, cudaStream_t s);
 // fir1d_compare.cu

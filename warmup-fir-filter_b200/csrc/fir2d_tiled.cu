@@ -80,7 +80,9 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     // TMA needs a 16-byte aligned base and 16-byte multiples for every pitch.
     if ((uintptr_t)a.x % 16 != 0 || (a.ld_x * es) % 16 != 0) return 0;
     if (a.n_img > 1 && (a.img_stride_x * es) % 16 != 0) return 0;
-    if (es == 1 && (a.width & 1)) return 0;                  // uint8 pixels travel as 16-bit map elements: whole pairs only
+    // uint8 pixels travel as 16-bit map elements: whole pairs only, unless the rows carry a zero pad byte
+    const int64_t map_w = a.width + ((es == 1 && (a.width & 1) && a.x_row_padded) ? 1 : 0);
+    if (es == 1 && (map_w & 1)) return 0;
     if (a.width >= (1LL << 31) - 4096 || a.height + a.halo_top + a.halo_bottom >= (1LL << 31) - 64 || a.n_img >= (1LL << 31))
         return 0;
     EncodeTiledFn encode = encode_fn();
@@ -137,7 +139,7 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
 
     const long long map_rows = a.halo_top + a.height + a.halo_bottom;
     CUtensorMap map;
-    cuuint64_t dims[3] = {(cuuint64_t)(a.width * es / kMapElemBytes), (cuuint64_t)map_rows, (cuuint64_t)a.n_img};
+    cuuint64_t dims[3] = {(cuuint64_t)(map_w * es / kMapElemBytes), (cuuint64_t)map_rows, (cuuint64_t)a.n_img};
     cuuint64_t strides[2] = {(cuuint64_t)(a.ld_x * es),
                              (cuuint64_t)((a.n_img > 1 ? a.img_stride_x : map_rows * a.ld_x) * es)};
     cuuint32_t box[3] = {(cuuint32_t)kBoxElems, (cuuint32_t)bh, 1};

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace firgpu {
 namespace {
@@ -73,6 +74,29 @@ prep_u8_kernel(const InT *__restrict__ x, uint8_t *__restrict__ y, int64_t rows,
     }
 }
 
+// Same-type copy to a new pitch: a thread writes one aligned 32-bit word of the destination from element loads of
+// the source (rows of an odd pitch start at every alignment); elements past `cols` are written as 0.
+template <typename T>
+__global__ void __launch_bounds__(kPrepThreads)
+repitch_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y)
+{
+    constexpr int PER = 4 / (int)sizeof(T);
+    const int64_t words = ld_y / PER;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const T *xr = x + r * ld_x;
+        uint32_t *yr = reinterpret_cast<uint32_t *>(y + r * ld_y);
+        for (int64_t w = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; w < words; w += (int64_t)gridDim.x * kPrepThreads) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int64_t j = w * PER + q;
+                if (j < cols) v |= (uint32_t)(typename std::make_unsigned<T>::type)xr[j] << (8 * (int)sizeof(T) * q);
+            }
+            yr[w] = v;
+        }
+    }
+}
+
 template <typename InT, int Q>
 int run_prep(const void *x, uint8_t *y, int64_t rows, int64_t span, int64_t ld_x, int64_t ld_y, int64_t before, int64_t shift,
              int ctas_per_sm, cudaStream_t s)
@@ -107,6 +131,24 @@ int run_prep_q(const void *x, uint8_t *y, int64_t rows, int64_t span, int64_t ld
 }
 
 }  // namespace
+
+int launch_repitch(const void *x, int dtype, void *y, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y, cudaStream_t s)
+{
+    const int es = dtype == FIRGPU_U8 ? 1 : 2;
+    int64_t gx = (ld_y * es / 4 + kPrepThreads - 1) / kPrepThreads;
+    if (gx > 148 * 8) gx = 148 * 8;
+    if (gx < 1) gx = 1;
+    int64_t gy = rows;
+    const int64_t cap = (148 * 16 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    if (dtype == FIRGPU_U8) repitch_kernel<uint8_t><<<grid, kPrepThreads, 0, s>>>((const uint8_t *)x, (uint8_t *)y, rows, cols, ld_x, ld_y);
+    else if (dtype == FIRGPU_I16) repitch_kernel<int16_t><<<grid, kPrepThreads, 0, s>>>((const int16_t *)x, (int16_t *)y, rows, cols, ld_x, ld_y);
+    else return set_error(FIRGPU_E_DTYPE, "repitch: unsupported dtype %d", dtype);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 0;
+}
 
 // y: 16-byte aligned temporary of rows x ld_y bytes (ld_y a multiple of 16).  Sample k of the window (k = 0 is the
 // element `before` in front of the row pointer, `span` samples in all) lands at byte shift + k of its row.
