@@ -185,6 +185,12 @@ def main():
             hq = quant.quantize_taps(np.asarray(k), 12, 16)
             s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out=out), args.reps)
             report(f"2d 2999x4499 u8->u8 {tag} q4.12 (odd pitch)", s, 2999 * 4499, 2)
+    if "compare" in cases:
+        # fused fixed-vs-ideal metrics: 1 B read per sample, seven numbers out (the call synchronises to return them)
+        for hgt, wid in ((64, 64), (2999, 4499), (8192, 16384)):
+            x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
+            s = timed(lambda: firgpu.compare_metrics(x, LP5, validate=False), 5)
+            report(f"compare metrics {hgt}x{wid} u8 5tap q4.12 (fixed + ideal + 7 reductions)", s, hgt * wid, 1)
     if "causal" in cases:
         g = torch.Generator(device="cuda").manual_seed(9)
         x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)

@@ -465,37 +465,6 @@ int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t h
     return 0;
 }
 
-// Stream-ordered scratch memory (the uint8 copy of int32 / float containers).  A pool of the library's own, one per
-// device, that keeps what it has allocated between calls (the device's default pool hands its memory back at
-// every synchronisation, which would put a fresh cuMemCreate on each call); firgpu_release_cache() trims it.
-std::mutex g_pool_mu;
-std::map<int, cudaMemPool_t> g_pools;
-
-int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
-{
-    int dev = 0;
-    FIRGPU_CUDA(cudaGetDevice(&dev));
-    cudaMemPool_t pool = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(g_pool_mu);
-        auto it = g_pools.find(dev);
-        if (it == g_pools.end()) {
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = dev;
-            FIRGPU_CUDA(cudaMemPoolCreate(&pool, &props));
-            uint64_t keep = ~0ULL;
-            FIRGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            g_pools[dev] = pool;
-        } else {
-            pool = it->second;
-        }
-    }
-    FIRGPU_CUDA(cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pool, stream));
-    return 0;
-}
-
 bool wide_container(int in_dtype) { return in_dtype == FIRGPU_I32 || in_dtype == FIRGPU_F32 || in_dtype == FIRGPU_F64; }
 
 // int32 / float containers of a useful size are converted to the reference's uint8 pixels first (csrc/prep_u8.cu).
@@ -540,6 +509,40 @@ bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64
 int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
 
 }  // namespace
+
+// Stream-ordered scratch memory (the uint8 copy of int32 / float containers).  A pool of the library's own, one per
+// device, that keeps what it has allocated between calls (the device's default pool hands its memory back at
+// every synchronisation, which would put a fresh cuMemCreate on each call); firgpu_release_cache() trims it.
+namespace {
+std::mutex g_pool_mu;
+std::map<int, cudaMemPool_t> g_pools;
+}  // namespace
+
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        auto it = g_pools.find(dev);
+        if (it == g_pools.end()) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            FIRGPU_CUDA(cudaMemPoolCreate(&pool, &props));
+            uint64_t keep = ~0ULL;
+            FIRGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            g_pools[dev] = pool;
+        } else {
+            pool = it->second;
+        }
+    }
+    FIRGPU_CUDA(cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pool, stream));
+    return 0;
+}
+
 }  // namespace firgpu
 
 using namespace firgpu;

@@ -182,11 +182,15 @@ int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);
 int try_launch_fir2d_ideal_fast(const Fir2dArgs &a, const double *h_host);
 int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq_host);
 
+// api.cu — stream-ordered scratch memory from the library's own pool (keeps its pages between calls); free with
+// cudaFreeAsync on the same stream
+int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+
 // Device copy of a long tap vector, freed on the stream after the launch.
 template <typename T>
 int upload_taps(const T *host, int n, cudaStream_t s, T **dev)
 {
-    FIRGPU_CUDA(cudaMallocAsync((void **)dev, sizeof(T) * (size_t)n, s));
+    if (int rc = scratch_alloc((void **)dev, sizeof(T) * (size_t)n, s)) return rc;
     FIRGPU_CUDA(cudaMemcpyAsync(*dev, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, s));
     return 0;
 }

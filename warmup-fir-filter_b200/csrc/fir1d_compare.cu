@@ -13,6 +13,10 @@
 // Sums are float64 (block tree + one atomicAdd per block), so they agree with
 // NumPy's pairwise float64 sums to ~1e-12 relative, not bit for bit.
 #include "common.cuh"
+#include "fastplan.h"
+#include "ideal_common.cuh"
+
+#include <cstdlib>
 
 namespace firgpu {
 namespace {
@@ -32,40 +36,10 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-template <typename InT>
-__global__ void __launch_bounds__(kBlock)
-fir1d_compare_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols, int64_t ld_x, InlineTaps hq,
-                     InlineTapsF64 h, int n_taps, int frac_bits, int acc_bits, double *__restrict__ sums,
-                     unsigned long long *__restrict__ counts)
+__device__ __forceinline__ void block_reduce_and_publish(double s_abs, double s_sq, double s_diff, double m_abs, unsigned long long c_lo,
+                                                         unsigned long long c_hi, unsigned long long c_clip,
+                                                         double *__restrict__ sums, unsigned long long *__restrict__ counts)
 {
-    const int centre = n_taps / 2;
-    double s_abs = 0.0, s_sq = 0.0, s_diff = 0.0, m_abs = 0.0;
-    unsigned long long c_lo = 0, c_hi = 0, c_clip = 0;
-    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
-        const InT *xr = x + r * ld_x;
-        for (int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x; n < cols; n += (int64_t)gridDim.x * kBlock) {
-            long long acc = 0;
-            double ideal = 0.0;
-            for (int k = 0; k < n_taps; ++k) {
-                const int64_t src = n - (k - centre);
-                if (src >= 0 && src < cols) {
-                    const int s = prep_sample(xr[src]);
-                    acc += (long long)s * (long long)hq.v[k];
-                    ideal = __dadd_rn(ideal, __dmul_rn(h.v[k], (double)s));
-                }
-            }
-            const int fixed = post_accumulate(acc, frac_bits, acc_bits);
-            const double diff = (double)fixed - ideal;
-            const double ad = fabs(diff);
-            s_abs += ad;
-            s_sq += diff * diff;
-            s_diff += diff;
-            m_abs = fmax(m_abs, ad);
-            c_lo += fixed == 0;
-            c_hi += fixed == kPixelMax;
-            c_clip += (ideal < 0.0) | (ideal > 255.0);
-        }
-    }
     __shared__ double sh[4][kBlock / 32];
     __shared__ unsigned long long shc[3][kBlock / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,6 +83,130 @@ fir1d_compare_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols, int6
     }
 }
 
+// Register form for uint8 / int16 pixels and up to nine taps whose fixed-point sum provably fits int32
+// (csrc/fastplan.h): the construction of fir1d_ideal_fast.cu — a lane takes two adjacent outputs from the few sample
+// pairs its window covers (global loads, L1-backed), converts each sample once to float64 with the exact 2^52 + v bit
+// trick, evaluates the float64 model (unfused, ascending taps) and the integer model (int32 multiply-adds, the
+// host-proved no-wrap shortcut of the fast kernels), and folds the difference into the seven reductions.
+// Bound: the fp64 pipe (about 22 float64 operations per sample), not HBM (1-2 B per sample).
+template <typename InT, int L>
+__global__ void __launch_bounds__(kBlock)
+fir1d_compare_fast_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols, int64_t ld_x, InlineTaps hq, InlineTapsF64 h,
+                          int frac_bits, int bias, int64_t tiles_per_row, int64_t total_tiles, double *__restrict__ sums,
+                          unsigned long long *__restrict__ counts)
+{
+    constexpr int kWarps = kBlock / 32, kGroups = 4, kTile = 64 * kGroups;
+    constexpr int hi = L / 2, lo = L - 1 - hi;
+    constexpr int PL = (lo + 1) / 2, PR = (hi + 1) / 2, NP = PL + 1 + PR;
+    using P2 = typename PairOf<InT>::type;
+    const int lane = threadIdx.x & 31;
+    double s_abs = 0.0, s_sq = 0.0, s_diff = 0.0, m_abs = 0.0;
+    unsigned c_lo = 0, c_hi = 0, c_clip = 0;
+
+    auto fold = [&](const int (&v)[2 * NP], int e) {         // output base + e from window samples v[]
+        int acc = 0;
+        double ideal = 0.0;
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            const int sv = v[2 * PL + hi - k + e];
+            acc += hq.v[k] * sv;
+            ideal = __dadd_rn(ideal, __dmul_rn(h.v[k], pixel_to<double>(sv)));
+        }
+        const int fixed = min(max((acc + bias) >> frac_bits, 0), kPixelMax);
+        const double diff = pixel_to<double>(fixed) - ideal;
+        const double ad = fabs(diff);
+        s_abs += ad;
+        s_sq = fma(diff, diff, s_sq);
+        s_diff += diff;
+        m_abs = fmax(m_abs, ad);
+        c_lo += fixed == 0;
+        c_hi += fixed == kPixelMax;
+        c_clip += (ideal < 0.0) | (ideal > 255.0);
+    };
+
+    const int64_t step = (int64_t)gridDim.x * kWarps;
+    const int64_t step_rows = step / tiles_per_row, step_cols = step - step_rows * tiles_per_row;
+    int64_t tile = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int64_t row = tile / tiles_per_row, tcol = tile - row * tiles_per_row;
+    for (; tile < total_tiles; tile += step) {
+        const int64_t col0 = tcol * kTile;
+        const InT *xr = x + row * ld_x;
+        const bool x_pairs = (reinterpret_cast<uintptr_t>(xr) & (2 * sizeof(InT) - 1)) == 0;
+        const bool interior = col0 - 2 * PL >= 0 && col0 + kTile + 2 * PR <= cols && x_pairs;
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+            const int64_t n = col0 + j * 64 + 2 * lane;
+            if (n >= cols) break;
+            int v[2 * NP];
+            if (interior) {
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const P2 r = *reinterpret_cast<const P2 *>(xr + n + 2 * (p - PL));
+                    if constexpr (sizeof(InT) == 1) {
+                        v[2 * p] = r & 0xff;
+                        v[2 * p + 1] = r >> 8;
+                    } else {
+                        v[2 * p] = prep_sample((int16_t)(r & 0xffffu));
+                        v[2 * p + 1] = prep_sample((int16_t)(r >> 16));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2 * NP; ++i) {
+                    const int64_t g = n - 2 * PL + i;
+                    v[i] = (g >= 0 && g < cols) ? prep_sample(xr[g]) : 0;
+                }
+            }
+            fold(v, 0);
+            if (n + 1 < cols) fold(v, 1);
+        }
+        row += step_rows;
+        tcol += step_cols;
+        if (tcol >= tiles_per_row) {
+            tcol -= tiles_per_row;
+            ++row;
+        }
+    }
+    block_reduce_and_publish(s_abs, s_sq, s_diff, m_abs, c_lo, c_hi, c_clip, sums, counts);
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(kBlock)
+fir1d_compare_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols, int64_t ld_x, InlineTaps hq,
+                     InlineTapsF64 h, int n_taps, int frac_bits, int acc_bits, double *__restrict__ sums,
+                     unsigned long long *__restrict__ counts)
+{
+    const int centre = n_taps / 2;
+    double s_abs = 0.0, s_sq = 0.0, s_diff = 0.0, m_abs = 0.0;
+    unsigned long long c_lo = 0, c_hi = 0, c_clip = 0;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const InT *xr = x + r * ld_x;
+        for (int64_t n = (int64_t)blockIdx.x * kBlock + threadIdx.x; n < cols; n += (int64_t)gridDim.x * kBlock) {
+            long long acc = 0;
+            double ideal = 0.0;
+            for (int k = 0; k < n_taps; ++k) {
+                const int64_t src = n - (k - centre);
+                if (src >= 0 && src < cols) {
+                    const int s = prep_sample(xr[src]);
+                    acc += (long long)s * (long long)hq.v[k];
+                    ideal = __dadd_rn(ideal, __dmul_rn(h.v[k], (double)s));
+                }
+            }
+            const int fixed = post_accumulate(acc, frac_bits, acc_bits);
+            const double diff = (double)fixed - ideal;
+            const double ad = fabs(diff);
+            s_abs += ad;
+            s_sq += diff * diff;
+            s_diff += diff;
+            m_abs = fmax(m_abs, ad);
+            c_lo += fixed == 0;
+            c_hi += fixed == kPixelMax;
+            c_clip += (ideal < 0.0) | (ideal > 255.0);
+        }
+    }
+    block_reduce_and_publish(s_abs, s_sq, s_diff, m_abs, c_lo, c_hi, c_clip, sums, counts);
+}
+
 template <typename InT>
 int run(const void *x, int64_t rows, int64_t cols, int64_t ld_x, const InlineTaps &hq, const InlineTapsF64 &h, int n_taps,
         int frac_bits, int acc_bits, double *d_sums, unsigned long long *d_counts, cudaStream_t s)
@@ -126,6 +224,38 @@ int run(const void *x, int64_t rows, int64_t cols, int64_t ld_x, const InlineTap
     return 0;
 }
 
+template <typename InT, int L>
+int run_fast(const void *x, int64_t rows, int64_t cols, int64_t ld_x, const InlineTaps &hq, const InlineTapsF64 &h, int frac_bits,
+             int bias, double *d_sums, unsigned long long *d_counts, cudaStream_t s)
+{
+    constexpr int kTile = 64 * 4, kWarps = kBlock / 32;
+    const int64_t tiles_per_row = (cols + kTile - 1) / kTile, total = tiles_per_row * rows;
+    int64_t grid = (total + kWarps - 1) / kWarps;
+    if (grid > 148 * 8) grid = 148 * 8;                      // persistent: per-thread partial sums, one publish per CTA
+    fir1d_compare_fast_kernel<InT, L><<<(unsigned)grid, kBlock, 0, s>>>((const InT *)x, rows, cols, ld_x, hq, h, frac_bits, bias,
+                                                                       tiles_per_row, total, d_sums, d_counts);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 0;
+}
+
+template <typename InT>
+int run_fast_taps(int n_taps, const void *x, int64_t rows, int64_t cols, int64_t ld_x, const InlineTaps &hq, const InlineTapsF64 &h,
+                  int frac_bits, int bias, double *d_sums, unsigned long long *d_counts, cudaStream_t s)
+{
+    switch (n_taps) {
+    case 1: return run_fast<InT, 1>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 2: return run_fast<InT, 2>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 3: return run_fast<InT, 3>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 4: return run_fast<InT, 4>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 5: return run_fast<InT, 5>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 6: return run_fast<InT, 6>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 7: return run_fast<InT, 7>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    case 8: return run_fast<InT, 8>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    default: return run_fast<InT, 9>(x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    }
+}
+
 }  // namespace
 
 // x: DEVICE pointer.  out[7] (HOST): the seven reductions listed at the top.
@@ -141,10 +271,18 @@ int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols
         h.v[k] = h_host[k];
     }
     double *d_sums = nullptr;
-    FIRGPU_CUDA(cudaMallocAsync((void **)&d_sums, 8 * sizeof(double), s));
+    if (int rc0 = scratch_alloc((void **)&d_sums, 8 * sizeof(double), s)) return rc0;
     FIRGPU_CUDA(cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), s));
     unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(d_sums + 4);
     int rc;
+    // int32 shortcut: the wrap is provably the identity and acc + bias fits int32 (same proof as the fast filter kernels)
+    const FastPlan plan = n_taps <= 9 ? plan_fast(hq_host, n_taps, frac_bits, acc_bits, 0x7fffffff, false) : FastPlan{};
+    const char *force = getenv("FIRGPU_FORCE_GENERIC");
+    if (plan.ok && !(force && force[0] == '1') && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16)) {
+        const int bias = 1 << (frac_bits - 1);
+        rc = in_dtype == FIRGPU_U8 ? run_fast_taps<uint8_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s)
+                                   : run_fast_taps<int16_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    } else
     switch (in_dtype) {
     case FIRGPU_U8: rc = run<uint8_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
     case FIRGPU_I16: rc = run<int16_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
