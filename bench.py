@@ -143,6 +143,22 @@ def c_port_rate(threads: int, n: int, min_seconds: float) -> tuple[float, float,
             return reps * n / dt, dt, reps
 
 
+def numpy_port_rate(n: int, min_seconds: float) -> tuple[float, float, int]:
+    """The vectorised NumPy restatement (oracle/fir_oracle_np.py) on one core: SURVEY 8(d) asks for it as a second,
+    clearly labelled CPU line next to the scalar port."""
+    from oracle import fir_oracle_np as onp
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 256, size=n).astype(np.int16)
+    onp.fir1d_fixed(x[: 1 << 16], TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        onp.fir1d_fixed(x, TAPS, FRAC_BITS, ACC_BITS, COEFF_BITS, out_dtype=np.int16)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            return reps * n / dt, dt, reps
+
+
 def host_cores() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -155,12 +171,15 @@ def cpu_baseline_block(seconds_c: float = 5.0) -> dict:
     per_core = 1 << 21
     rate_py, dt_py = python_port_rate(cores, per_core)
     rate_c, dt_c, reps = c_port_rate(cores, 1 << 26, seconds_c)
+    rate_np, dt_np, reps_np = numpy_port_rate(1 << 24, 3.0)
     return {
         "value": rate_py / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": (f"oracle/fir_oracle_py.py (pure-Python per-sample loop, the reference's algorithm shape) on "
                    f"{cores} processes x 2^21 samples of the same 5-tap Q1.15 int16 workload, {dt_py:.1f} s"),
         "compiled_port": {"value": rate_c / 1e9, "unit": UNIT, "cores": cores,
                           "sample": f"oracle/fir_oracle.c (gcc -O2 -fopenmp) {reps} x 2^26 samples, {dt_c:.1f} s"},
+        "numpy_port": {"value": rate_np / 1e9, "unit": UNIT, "cores": 1,
+                       "sample": f"oracle/fir_oracle_np.py (vectorised int64 shift-and-add) {reps_np} x 2^24 samples, {dt_np:.1f} s"},
     }
 
 

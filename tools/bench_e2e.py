@@ -36,3 +36,15 @@ for _ in range(3):
 dt = (time.perf_counter() - t0) / 3
 print({"pageable": True, "ms": round(dt * 1e3, 2), "gsamples_s": round(n / dt / 1e9, 2)})
 assert np.array_equal(yp, yn)
+
+# config 4 through the host entry point: one 16384 x 16384 int16 image, 3x3 and 5x5, pinned buffers
+img = torch.randint(0, 256, (16384, 16384), dtype=torch.int16).pin_memory()
+out = torch.empty_like(img).pin_memory()
+for k, tag in (([[1 / 9] * 3] * 3, "3x3"), (np.outer(h, h).tolist(), "5x5")):
+    for _ in range(2):
+        firgpu.fir2d_fixed(img.numpy(), k, 12, 32, 16, out_dtype=np.int16, out=out.numpy(), validate=False)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        firgpu.fir2d_fixed(img.numpy(), k, 12, 32, 16, out_dtype=np.int16, out=out.numpy(), validate=False)
+    dt = (time.perf_counter() - t0) / 4
+    print({"2d": tag, "ms": round(dt * 1e3, 2), "gpixels_s": round(img.numel() / dt / 1e9, 2), "gb_s_each_way": round(2 * img.numel() / dt / 1e9, 1)})
