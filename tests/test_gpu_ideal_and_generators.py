@@ -436,3 +436,35 @@ def test_causal_raw_float64_model_on_the_fast_kernel():
     f = Fir1D(h)
     parts = [f.process_block(big[a:b]) for a, b in ((0, 7), (7, 50_000), (50_000, 50_001), (50_001, big.size))]
     assert np.array_equal(np.concatenate(parts), want)
+
+
+def test_interleaved_iq_floating_point_model_on_the_fast_kernel():
+    """dilation = 2 (interleaved I/Q, real taps) of the floating-point model on
+    the register kernel: equal to the model applied to z[0::2] and z[1::2]
+    separately, bit for bit in float64, for every tap count, even and odd
+    scalar counts, several rows and float containers."""
+    import torch
+    import firgpu
+    from firgpu import _lib
+    rng = np.random.default_rng(61)
+    for dtype in (np.uint8, np.int16, np.float32):
+        for n_taps in range(1, 10):
+            h = rng.uniform(-2, 2, size=n_taps).tolist()
+            for shape in ((1, 2), (1, 10_000), (3, 4098), (2, 4501), (5, 1026)):
+                z = rng.integers(0, 256, size=shape).astype(dtype)
+                if dtype == np.int16:
+                    z[rng.random(shape) < 0.05] = -77
+                if dtype == np.float32:
+                    z = z + rng.uniform(-0.5, 0.5, size=shape).astype(np.float32)
+                want = onp.fir1d_ideal(z, h, dilation=2)
+                if shape[1] % 2 == 0:                      # the definition: I and Q filtered separately
+                    sep = np.empty_like(want)
+                    sep[..., 0::2] = onp.fir1d_ideal(z[..., 0::2], h)
+                    sep[..., 1::2] = onp.fir1d_ideal(z[..., 1::2], h)
+                    assert np.array_equal(want, sep)
+                got = firgpu.fir1d_ideal(torch.from_numpy(z).cuda(), h, dilation=2)
+                if dtype != np.float32 or z.size >= 4096:
+                    assert _lib.last_path() == _lib.PATH_STAGED, (dtype, n_taps, shape)
+                assert np.array_equal(got.cpu().numpy(), want), (dtype, n_taps, shape)
+                got32 = firgpu.fir1d_ideal(torch.from_numpy(z).cuda(), h, dilation=2, out_dtype=np.float32).cpu().numpy()
+                assert np.abs(got32 - want).max() <= 1e-6 * 255 * np.abs(h).sum() + 1e-30

@@ -191,6 +191,12 @@ def main():
             x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
             s = timed(lambda: firgpu.compare_metrics(x, LP5, validate=False), 5)
             report(f"compare metrics {hgt}x{wid} u8 5tap q4.12 (fixed + ideal + 7 reductions)", s, hgt * wid, 1)
+    if "iqideal" in cases:
+        z = rand_i16(1 << 27)                      # 2^26 complex samples interleaved
+        y = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+        s = timed(lambda: firgpu.fir1d_ideal(z, LP5, dilation=2, out=y, validate=False), 5)
+        report("iq ideal 2^26 complex i16->f64 5tap", s, 1 << 27, 10)
+        del z, y
     if "causal" in cases:
         g = torch.Generator(device="cuda").manual_seed(9)
         x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)

@@ -685,7 +685,7 @@ int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype, int6
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
-    if (convert_first(in_dtype, rows * cols) && n_taps <= 9 && dilation == 1) {   // the floating-point model also starts from the rounded, clamped pixel
+    if (convert_first(in_dtype, rows * cols) && n_taps <= 9 && (dilation == 1 || dilation == 2)) {   // the floating-point model also starts from the rounded, clamped pixel
         uint8_t *tmp = nullptr, *body = nullptr;
         int64_t ld_t = 0;
         if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, halo_left_valid, halo_right_valid, (cudaStream_t)stream, &tmp, &body, &ld_t)))

@@ -43,7 +43,9 @@ template <> struct Vec2<float> { using type = float2; };
 // CAUSAL = false: the Python model (output n reads samples n + L/2 ... n - (L-1-L/2), rounded and clamped pixels).
 // CAUSAL = true, InT = double: the C++ Fir1D model (fir_1d/model/cpp/fir_1d_ref.cpp:16-63): y[n] = sum h[k] x[n-k] on the
 // samples as they are.
-template <typename InT, typename F, int L, int kGroups, bool CAUSAL>   // kGroups output groups per lane per tile
+// DIL = 2: interleaved I/Q with real taps (lib/mycomplex.cpp:12-22) — output n reads scalars n + 2 (hi - k); the window of
+// a group is still one contiguous run of scalars, so only its reach and the tap stride change.
+template <typename InT, typename F, int L, int kGroups, bool CAUSAL, int DIL>   // kGroups output groups per lane per tile
 __global__ void __launch_bounds__(kThreadsI)
 fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
                         int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
@@ -54,7 +56,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     constexpr int G = 2 * OP;                            // outputs per group
     constexpr int kTileI = 32 * G * kGroups;             // outputs per warp tile
     constexpr int hi = CAUSAL ? 0 : L / 2, lo = L - 1 - hi;
-    constexpr int PL = (lo + 1) / 2, PR = (hi + 1) / 2;  // neighbour pairs a window reaches into, left / right
+    constexpr int PL = DIL == 1 ? (lo + 1) / 2 : lo, PR = DIL == 1 ? (hi + 1) / 2 : hi;  // neighbour pairs a window reaches into, left / right
     constexpr int NP = PL + OP + PR;                     // sample pairs per window: samples base - 2 PL ... base + G - 1 + 2 PR
     using P2 = typename PairOf<InT>::type;
     const int lane = threadIdx.x & 31;
@@ -69,8 +71,8 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
         for (int k = 0; k < L; ++k) {
 #pragma unroll
             for (int e = 0; e < G; ++e) {
-                if constexpr (sizeof(F) == 8) a[e] = __dadd_rn(a[e], __dmul_rn(h.v[k], w[2 * PL + hi - k + e]));   // the reference's unfused float64
-                else a[e] = fmaf((float)h.v[k], w[2 * PL + hi - k + e], a[e]);                                    // float32 datapath (same as the generic kernel's)
+                if constexpr (sizeof(F) == 8) a[e] = __dadd_rn(a[e], __dmul_rn(h.v[k], w[2 * PL + DIL * (hi - k) + e]));   // the reference's unfused float64
+                else a[e] = fmaf((float)h.v[k], w[2 * PL + DIL * (hi - k) + e], a[e]);                                    // float32 datapath (same as the generic kernel's)
             }
         }
     };
@@ -164,7 +166,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     }
 }
 
-template <typename InT, typename F, int L, int kGroups, bool CAUSAL>
+template <typename InT, typename F, int L, int kGroups, bool CAUSAL, int DIL = 1>
 int run_groups(const Fir1dArgs &a, const double *h_host)
 {
     constexpr int kWarps = kThreadsI / 32;
@@ -189,7 +191,7 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
     if (per_sm > 0 && grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
     if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     if (grid < 1) grid = 1;
-    fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
+    fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL, DIL><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
@@ -201,7 +203,10 @@ int run(const Fir1dArgs &a, const double *h_host)
 {
     // groups per lane per tile: 512-output warp tiles measured best for both output types (sweep in profiles/README.md)
     if constexpr (sizeof(InT) == 8) return run_groups<InT, double, L, 8, true>(a, h_host);
-    else if (a.out_dtype == FIRGPU_F32) return run_groups<InT, float, L, 4, false>(a, h_host);
+    else if (a.dilation == 2) {                         // wider windows (L pairs per group): fewer groups in flight per lane
+        if (a.out_dtype == FIRGPU_F32) return run_groups<InT, float, L, 2, false, 2>(a, h_host);
+        return run_groups<InT, double, L, 4, false, 2>(a, h_host);
+    } else if (a.out_dtype == FIRGPU_F32) return run_groups<InT, float, L, 4, false>(a, h_host);
     else return run_groups<InT, double, L, 8, false>(a, h_host);
 }
 
@@ -227,11 +232,11 @@ int by_taps(const Fir1dArgs &a, const double *h)
 // 1 = served, 0 = not eligible (caller uses the generic kernel), else error.
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
 {
-    if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || a.dilation != 1 || a.n_taps > kMaxFastIdealTaps) return 0;
+    if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || (a.dilation != 1 && a.dilation != 2) || a.n_taps > kMaxFastIdealTaps) return 0;
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
     if (force && force[0] == '1') return 0;
     // the C++ Fir1D model: causal, raw float64 samples, float64 output
-    if (a.raw && a.centre == 0 && a.in_dtype == FIRGPU_F64 && a.out_dtype == FIRGPU_F64) return by_taps<double>(a, h_host);
+    if (a.raw && a.centre == 0 && a.in_dtype == FIRGPU_F64 && a.out_dtype == FIRGPU_F64 && a.dilation == 1) return by_taps<double>(a, h_host);
     if (!a.is_reference_model()) return 0;
     if (a.in_dtype == FIRGPU_U8) return by_taps<uint8_t>(a, h_host);
     if (a.in_dtype == FIRGPU_I16) return by_taps<int16_t>(a, h_host);
