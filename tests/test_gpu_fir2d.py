@@ -200,6 +200,13 @@ def test_2d_images_of_odd_width_and_pitch():
                 got = firgpu.fir2d_fixed(cuda(x), k, 12, 32, 16, out_dtype=dtype)
                 assert _lib.last_path() == _lib.PATH_STAGED, (dtype, shape, np.shape(k))
                 assert np.array_equal(got.cpu().numpy(), onp.fir2d_fixed(x, k, 12, 32, 16, out_dtype=dtype)), (dtype, shape, np.shape(k))
+    # int16 container in, uint8 out (the drop-in's default output type): narrowed to uint8 pixels first
+    from fir_2d.model.python.fir_2d_fixed_ref import fir_2d_fixed_golden
+    x16 = image(rng, (2, 300, 1024), np.int16)
+    for k in (K3_BOX, K5_LP):
+        got = fir_2d_fixed_golden(cuda(x16), k)
+        assert _lib.last_path() == _lib.PATH_STAGED and got.dtype == torch.uint8
+        assert np.array_equal(got.cpu().numpy(), onp.fir2d_fixed(x16, k))
     x = image(rng, (1, 120, 2000), np.uint8)
     xt = cuda(x)
     for c0, width in ((1, 1998), (3, 1001), (16, 1024)):                  # column views: unaligned base / odd width

@@ -28,6 +28,11 @@ __device__ __forceinline__ uint32_t quad(const int32_t *p)
     const int4 v = *reinterpret_cast<const int4 *>(p);
     return pack4(prep_sample(v.x), prep_sample(v.y), prep_sample(v.z), prep_sample(v.w));
 }
+__device__ __forceinline__ uint32_t quad(const int16_t *p)        // 8-byte aligned is enough here
+{
+    const short4 v = *reinterpret_cast<const short4 *>(p);
+    return pack4(prep_sample(v.x), prep_sample(v.y), prep_sample(v.z), prep_sample(v.w));
+}
 __device__ __forceinline__ uint32_t quad(const double *p)
 {
     const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
@@ -156,6 +161,7 @@ int launch_prep_u8(const void *x, int in_dtype, uint8_t *y, int64_t rows, int64_
                    int64_t before, int64_t shift, cudaStream_t s)
 {
     switch (in_dtype) {
+    case FIRGPU_I16: run_prep_q<int16_t>(x, y, rows, span, ld_x, ld_y, before, shift, s); break;
     case FIRGPU_I32: run_prep_q<int32_t>(x, y, rows, span, ld_x, ld_y, before, shift, s); break;
     case FIRGPU_F32: run_prep_q<float>(x, y, rows, span, ld_x, ld_y, before, shift, s); break;
     case FIRGPU_F64: run_prep_q<double>(x, y, rows, span, ld_x, ld_y, before, shift, s); break;
