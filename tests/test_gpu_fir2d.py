@@ -135,6 +135,12 @@ def test_2d_ideal_fast_kernel_bit_identical():
                 got = firgpu.fir2d_ideal(cuda(x), k)
                 assert _lib.last_path() == _lib.PATH_STAGED, (dtype, shape)
                 assert np.array_equal(got.cpu().numpy(), onp.fir2d_ideal(x, k)), (dtype, shape, np.shape(k))
+    for dtype in (np.float32, np.float64, np.int32):          # rounded / clamped to uint8 pixels first, then the same kernel
+        x = (rng.uniform(-30, 300, size=(2, 90, 777))).astype(dtype)
+        for k in kernels[:2]:
+            got = firgpu.fir2d_ideal(cuda(x), k)
+            assert _lib.last_path() == _lib.PATH_STAGED, dtype
+            assert np.array_equal(got.cpu().numpy(), onp.fir2d_ideal(x, k)), dtype
     wide = image(rng, (2, 40, 1500), np.uint8)
     wide_t = cuda(wide)
     k = kernels[1]

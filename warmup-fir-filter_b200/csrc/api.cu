@@ -771,6 +771,25 @@ int firgpu_fir2d_ideal(const void *x, void *y, int in_dtype, int out_dtype, int6
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
+    // int32 / float images: rounded and clamped to uint8 pixels first (what the model does to every sample anyway), so
+    // that the register kernel applies
+    if (convert_first(in_dtype, n_img * height * width) && (kh == 3 || kh == 5) && (kw == 3 || kw == 5)) {
+        const int es_in = dtype_size(in_dtype);
+        const int64_t band = halo_top_valid + height + halo_bottom_valid;
+        const int64_t ld_t = (width + 15) / 16 * 16;
+        uint8_t *tmp = nullptr;
+        if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * band * n_img), (cudaStream_t)stream))) return rc;
+        for (int64_t b = 0; b < n_img && !rc; ++b)
+            rc = launch_prep_u8((const char *)x + (b * img_stride_x - halo_top_valid * ld_x) * es_in, in_dtype, tmp + b * band * ld_t,
+                                band, width, ld_x, ld_t, 0, 0, (cudaStream_t)stream);
+        if (!rc) {
+            Fir2dArgs t{tmp + halo_top_valid * ld_t, y, FIRGPU_U8, out_dtype, n_img, height, width, ld_t, ld_y, band * ld_t,
+                        img_stride_y, kh, kw, 0, 0, halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
+            rc = launch_fir2d_ideal(t, h);
+        }
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
+    }
     Fir2dArgs a{x, y, in_dtype, out_dtype, n_img, height, width, ld_x, ld_y, img_stride_x, img_stride_y, kh, kw, 0, 0,
                 halo_top_valid, halo_bottom_valid, (cudaStream_t)stream};
     return launch_fir2d_ideal(a, h);
