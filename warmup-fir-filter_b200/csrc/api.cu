@@ -908,6 +908,14 @@ int firgpu_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
+    if (convert_first(in_dtype, rows * cols) && n_taps <= 9) {         // int32 / float containers: uint8 pixels first
+        uint8_t *tmp = nullptr, *body = nullptr;
+        int64_t ld_t = 0;
+        if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, 0, 0, (cudaStream_t)stream, &tmp, &body, &ld_t))) return rc;
+        rc = launch_fir1d_compare(body, FIRGPU_U8, rows, cols, ld_t, hq, h, n_taps, frac_bits, acc_bits, metrics, (cudaStream_t)stream);
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return rc;
+    }
     return launch_fir1d_compare(x, in_dtype, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, metrics, (cudaStream_t)stream);
 }
 
