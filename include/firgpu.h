@@ -66,7 +66,8 @@ enum firgpu_status {
 enum firgpu_path {
     FIRGPU_PATH_NONE = 0,
     FIRGPU_PATH_GENERIC = 1,      /* int64 accumulate, any shape / alignment / acc_bits */
-    FIRGPU_PATH_STAGED = 2,       /* bulk-copy (TMA) staged, packed int32 datapath */
+    FIRGPU_PATH_STAGED = 2,       /* a fast kernel: bulk-copy (TMA) staged / tensor-map tiled packed int32 datapath,
+                                     or the register kernels of the floating-point model */
     FIRGPU_PATH_EMPTY = 3         /* zero-sized input, nothing launched */
 };
 
@@ -134,8 +135,11 @@ int firgpu_fir1d_ideal(const void *x, void *y, int in_dtype, int out_dtype,
 /* ------------------------------------------------------------------------
  * Extended 1-D entry points: the reference model with its fixed choices made
  * parameters.  (centre = n_taps/2, in [0,255], out [0,255], raw = 0) IS the
- * reference model and is served by the same kernels as the plain calls; any
- * other setting runs on the generic int64 / fp64 kernels.
+ * reference model and is served by the same kernels as the plain calls.  Other
+ * alignments of the fixed-point model also run on them (the taps are zero-padded
+ * to the centred form), other ranges on int16 containers on the wide datapath,
+ * the causal raw float64 model on the register kernel; the remaining settings
+ * run on the generic int64 / fp64 kernels.
  *
  *   centre   taps ahead of the output position: y[n] = sum_k h[k] x[n-(k-centre)*dilation].
  *            centre = 0 is the causal form of Fir1D::process_sample / fir_1d_idel
