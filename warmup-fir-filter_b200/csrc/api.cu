@@ -583,11 +583,9 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         int64_t ld_t = 0;
         if ((rc = uint8_copy_1d(x, in_dtype, rows, cols, ld_x, halo_left_valid, halo_right_valid, (cudaStream_t)stream, &tmp, &body, &ld_t)))
             return rc;
-        Fir1dArgs t{body, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, n_taps, dilation, frac_bits, acc_bits,
-                    halo_left_valid, halo_right_valid, (cudaStream_t)stream};
-        rc = try_launch_fir1d_fixed_staged(t, hq);
-        if (rc == 1) rc = 0;
-        else if (rc == 0) rc = launch_fir1d_fixed_generic(t, hq);       // taps outside the packed path: generic kernel on the uint8 copy
+        // the uint8 copy then takes the ordinary routing below (short-row kernel, staged kernel, generic kernel)
+        rc = firgpu_fir1d_fixed(body, y, FIRGPU_U8, out_dtype, rows, cols, ld_t, ld_y, hq, n_taps, dilation, frac_bits, acc_bits,
+                                halo_left_valid, halo_right_valid, stream);
         cudaFreeAsync(tmp, (cudaStream_t)stream);
         return rc;
     }
