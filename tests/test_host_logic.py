@@ -274,3 +274,22 @@ def test_host_out_buffers_are_validated_before_the_library_writes():
     frozen.setflags(write=False)
     with pytest.raises(ValueError, match="writable"):
         ops.fir1d_fixed(x, [1.0], out=frozen)
+
+
+def test_image_view_addressing():
+    """ops._cuda_imgs: which [..., H, W] views can be addressed in place (pitch /
+    image stride in elements) and which must be refused — pure stride logic,
+    checked here on CPU tensors."""
+    import torch
+    from firgpu import ops
+    base = torch.zeros(3, 40, 100, dtype=torch.int16)
+    assert ops._cuda_imgs(base, "x") == (3, 40, 100, 100, 4000)
+    assert ops._cuda_imgs(base[:, :, 5:71], "x") == (3, 40, 66, 100, 4000)          # column view
+    assert ops._cuda_imgs(base[:, 7:19, :], "x") == (3, 12, 100, 100, 4000)         # row band of every image
+    assert ops._cuda_imgs(base[1, 3:9, 2:50], "x") == (1, 6, 48, 100, 600)          # one image, window
+    assert ops._cuda_imgs(base[:1, :, 1:2], "x")[:3] == (1, 40, 1)
+    four = torch.zeros(2, 3, 8, 16)
+    assert ops._cuda_imgs(four, "x") == (6, 8, 16, 16, 128)                         # contiguous leading axes fold into the batch
+    for bad in (base[:, :, ::2], base.transpose(1, 2), four[:, :, :, 2:9]):
+        with pytest.raises(ValueError):
+            ops._cuda_imgs(bad, "x")
