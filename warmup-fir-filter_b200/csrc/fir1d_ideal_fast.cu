@@ -51,7 +51,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
                         int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
                         int64_t halo_right)
 {
-    constexpr int kWarps = kThreadsI / 32;
+    const int kWarps = (int)(blockDim.x >> 5);           // block size is a launch-time choice (<= kThreadsI)
     constexpr int OP = 16 / (2 * (int)sizeof(F));        // output pairs per group: one 16-byte store (2 doubles / 4 floats)
     constexpr int G = 2 * OP;                            // outputs per group
     constexpr int kTileI = 32 * G * kGroups;             // outputs per warp tile
@@ -169,7 +169,13 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
 template <typename InT, typename F, int L, int kGroups, bool CAUSAL, int DIL = 1>
 int run_groups(const Fir1dArgs &a, const double *h_host)
 {
-    constexpr int kWarps = kThreadsI / 32;
+    static int threads = -1;
+    if (threads < 0) {
+        const char *e = getenv("FIRGPU_IDEAL_THREADS");
+        threads = e ? atoi(e) : kThreadsI;
+        if (threads < 32 || threads > kThreadsI || (threads & 31)) threads = kThreadsI;
+    }
+    const int kWarps = threads / 32;
     constexpr int kTileI = 32 * (16 / (int)sizeof(F)) * kGroups;
     TapsF64<L> h;
     for (int k = 0; k < L; ++k) h.v[k] = h_host[k];
@@ -191,7 +197,7 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
     if (per_sm > 0 && grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
     if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     if (grid < 1) grid = 1;
-    fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL, DIL><<<(unsigned)grid, kThreadsI, 0, a.stream>>>(
+    fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL, DIL><<<(unsigned)grid, threads, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
