@@ -132,3 +132,63 @@ def test_fuzz_fir2d():
         if case % 5 == 0:
             assert np.array_equal(firgpu.fir2d_fixed(x, k, 12, acc, 16, out_dtype=out_dtype), want), tag + ("host",)
         assert np.array_equal(firgpu.fir2d_ideal(xt, k).cpu().numpy(), onp.fir2d_ideal(x, k)), tag + ("ideal",)
+
+
+def test_fuzz_extended_modes_and_shards():
+    """The extended entry points (alignment, clamp ranges, raw samples) and
+    shard seams (segments with real halo samples, row bands with halo rows) at
+    random: OUR specification restated by the oracle, equal to the reference
+    model at the defaults."""
+    import torch
+    import firgpu
+    from firgpu import shard
+    rng = np.random.default_rng(9090 + SEED)
+    ranges = ((0, 255), (-32768, 32767), (-100, 100), (0, 1023), (-7, 300))
+    for case in range(60 * SCALE):
+        rows, cols = pick_shape(rng, max_rows=12, max_cols=6000)
+        n_taps = int(rng.choice((1, 2, 3, 5, 5, 7, 9, 12, 20)))
+        h = random_taps(rng, n_taps, 1.2)
+        x = rng.integers(-32768, 32768, size=(rows, cols)).astype(np.int16)
+        xt = torch.from_numpy(x).cuda()
+        kw = {"centre": int(rng.integers(0, n_taps)) if rng.random() < 0.6 else None,
+              "in_range": ranges[int(rng.integers(len(ranges)))], "out_range": ranges[int(rng.integers(len(ranges)))]}
+        frac, acc = int(rng.choice((12, 15))), int(rng.choice((32, 48, 24)))
+        if frac == 15:
+            h = [v * 0.8 for v in h]
+        tag = (case, rows, cols, n_taps, frac, acc, kw)
+        want = onp.fir1d_fixed(x, h, frac, acc, 16, out_dtype=np.int16, **kw)
+        assert np.array_equal(firgpu.fir1d_fixed(xt, h, frac, acc, 16, out_dtype=np.int16, **kw).cpu().numpy(), want), tag
+        raw = bool(rng.random() < 0.5)
+        xf = rng.normal(0, 500, size=(rows, cols)) if raw else x
+        ikw = {"centre": kw["centre"], "raw": raw} if raw else {"centre": kw["centre"], "in_range": kw["in_range"]}
+        want = onp.fir1d_ideal(xf, h, **ikw)
+        assert np.array_equal(firgpu.fir1d_ideal(torch.from_numpy(xf).cuda(), h, **ikw).cpu().numpy(), want), tag + ("ideal", raw)
+    for case in range(12 * SCALE):                           # shard seams
+        n = int(rng.integers(5_000, 120_000))
+        n_taps = int(rng.choice((3, 5, 9, 17)))
+        dil = int(rng.choice((1, 1, 2)))
+        if dil == 2:
+            n -= n % 2
+            n_taps = min(n_taps, 9)
+        h = random_taps(rng, n_taps, 0.9)
+        dtype = (np.uint8, np.int16, np.float32)[int(rng.integers(3))]
+        x = make(rng, (n,), dtype)
+        want = onp.fir1d_fixed(x, h, 12, 32, 16, dilation=dil)
+        parts = int(rng.integers(2, 6))
+        for p in shard.plan_segments(n, parts, n_taps, dil, align=int(rng.choice((16, 64, 4096)))):
+            buf, body = shard.scatter_segment(x, p, "cuda")
+            y = firgpu.fir1d_fixed(body, h, 12, 32, 16, dilation=dil, halo_left_valid=p.before, halo_right_valid=p.after)
+            assert np.array_equal(y.cpu().numpy(), want[p.start:p.stop]), (case, n, n_taps, dil, np.dtype(dtype).name, parts, p)
+        hgt, wid = int(rng.integers(20, 200)), int(rng.choice((64, 333, 1000, 1102)))
+        kh = int(rng.choice((3, 5)))
+        k = rng.uniform(-0.4, 0.4, size=(kh, kh)).tolist()
+        img = make(rng, (2, hgt, wid), (np.uint8, np.int16)[int(rng.integers(2))])
+        want = onp.fir2d_fixed(img, k)
+        got = np.empty_like(want)
+        for band in shard.plan_bands(hgt, int(rng.integers(2, 5)), kh):
+            if band.size == 0:
+                continue
+            buf, body = shard.scatter_band(img, band, "cuda")
+            y = firgpu.fir2d_fixed(body, k, halo_top_valid=band.before, halo_bottom_valid=band.after)
+            got[:, band.start:band.stop, :] = y.cpu().numpy()
+        assert np.array_equal(got, want), (case, "bands", hgt, wid, kh)
