@@ -197,6 +197,15 @@ def main():
         s = timed(lambda: firgpu.fir1d_ideal(z, LP5, dilation=2, out=y, validate=False), 5)
         report("iq ideal 2^26 complex i16->f64 5tap", s, 1 << 27, 10)
         del z, y
+    if "narrow" in cases:
+        # batches of short aligned rows: row-streaming tensor-map kernel vs flattened pass + row-end fix-up
+        for cols in (64, 128, 256, 512, 1024, 2048, 4096):
+            rows = (1 << 27) // cols
+            x = rand_i16(rows * cols).view(rows, cols)
+            y = torch.empty_like(x)
+            s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"batched {rows}x{cols} i16->i16 5tap q1.15", s, rows * cols, 4)
+            del x, y
     if "causal" in cases:
         g = torch.Generator(device="cuda").manual_seed(9)
         x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)

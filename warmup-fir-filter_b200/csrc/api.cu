@@ -494,13 +494,24 @@ int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtyp
 // widths — cannot be staged row by row with bulk copies.  Filtering the whole batch as ONE long row gives the right
 // answer everywhere except within the taps' reach of a row end (where the neighbouring row's samples stand in for the
 // zero padding); launch_fir1d_fixed_edges() then rewrites exactly those outputs.
+// Narrow aligned rows (at most this many bytes) also go the flattened way: the row-streaming kernel stages 2 KiB wide
+// strips, so a batch of 512-byte rows keeps only a quarter of its threads busy.
+constexpr long kFlattenNarrowBytes = 256;   // measured (int16, 2^27 samples): 64 B rows 2.6x, 256 B rows 1.5x faster flattened, 512 B a tie, wider rows slower
+
 bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                 int n_taps, int dilation)
 {
     if (rows < 2 || ld_x != cols || ld_y != cols) return false;
     if (in_dtype != FIRGPU_U8 && in_dtype != FIRGPU_I16) return false;
     const int es = in_dtype == FIRGPU_U8 ? 1 : 2, os = out_size_fixed(out_dtype);
-    if ((cols * es) % 16 == 0 && (cols * os) % 16 == 0) return false;          // aligned pitches: the regular paths apply
+    if ((cols * es) % 16 == 0 && (cols * os) % 16 == 0) {                      // aligned pitches: the regular paths apply ...
+        static long narrow = -1;                                               // ... except for narrow rows (see below)
+        if (narrow < 0) {
+            const char *e = getenv("FIRGPU_FLATTEN_NARROW_BYTES");
+            narrow = e ? atol(e) : kFlattenNarrowBytes;
+        }
+        if (cols * es > narrow || rows < 64) return false;
+    }
     if (((uintptr_t)x | (uintptr_t)y) % 16) return false;
     if (dilation == 2 && (cols & 1)) return false;                             // I/Q pairs must not straddle rows
     if (cols < 8LL * (n_taps - 1) * dilation) return false;                    // mostly edges: not worth two launches
