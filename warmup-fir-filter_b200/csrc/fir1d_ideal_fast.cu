@@ -61,7 +61,6 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     using P2 = typename PairOf<InT>::type;
     const int lane = threadIdx.x & 31;
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
-    const int64_t step = (int64_t)gridDim.x * kWarps;
 
     // w[i] is sample base - 2 PL + i; output base + e reads samples base + e + hi - k, k = 0 .. L-1
     auto filter_group = [&](const F (&w)[2 * NP], F (&a)[G]) {
@@ -94,15 +93,18 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
         }
     };
 
-    // (row, tcol) advance incrementally: no 64-bit division per tile.  Loads of a tile are all issued before its
-    // arithmetic; other resident warps cover their latency (prefetching the next tile in registers was measured
-    // and lost to the occupancy it costs).
+    // One tile per warp; the tile index fits 32 bits (2^32 tiles would be 2^41 outputs), so locating the tile costs
+    // one 32-bit division — skipped for a single row.  (A persistent grid-stride form measured 8 % slower, and its
+    // 64-bit tile arithmetic was a third of all instructions executed: 150 per tile against 12 per output.)
+    // Loads of a tile are all issued before its arithmetic; other resident warps cover their latency.
     // Every row's tile grid is shifted left by `pad` outputs so that group stores are 16-byte aligned whatever the
     // row pitch (odd image widths); the first tile then starts at a negative column and skips those outputs.
-    const int64_t step_rows = step / tiles_per_row, step_cols = step - step_rows * tiles_per_row;
-    int64_t tile = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    int64_t row = tile / tiles_per_row, tcol = tile - row * tiles_per_row;
-    for (; tile < total_tiles; tile += step) {
+    const uint32_t tile = blockIdx.x * (uint32_t)kWarps + (threadIdx.x >> 5);
+    if (tile >= (uint32_t)total_tiles) return;
+    const uint32_t tpr = (uint32_t)tiles_per_row;
+    const uint32_t row32 = rows == 1 ? 0u : tile / tpr;
+    const int64_t row = row32, tcol = tile - row32 * tpr;
+    {
         const InT *xr = x + row * ld_x;
         F *yr = y + row * ld_y;
         const int pad = (int)((reinterpret_cast<uintptr_t>(yr) / sizeof(F)) % G);
@@ -157,12 +159,6 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
                 }
             }
         }
-        row += step_rows;
-        tcol += step_cols;
-        if (tcol >= tiles_per_row) {
-            tcol -= tiles_per_row;
-            ++row;
-        }
     }
 }
 
@@ -182,21 +178,11 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
     constexpr int kGroup = 16 / (int)sizeof(F);
     const int64_t tiles_per_row = (a.cols + kGroup - 1 + kTileI - 1) / kTileI;   // room for the per-row alignment shift
     const int64_t total = tiles_per_row * a.rows;
-    int dev = 0, sms = 148;
-    FIRGPU_CUDA(cudaGetDevice(&dev));
-    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // One tile per warp, CTAs in address order: concurrently running CTAs then write one advancing front, which
-    // the write-dominated stream needs (a persistent grid striding over the output measured 8 % slower).
-    // FIRGPU_IDEAL_CTAS=n > 0 selects the persistent form with n CTAs per SM.
-    static int per_sm = -1;
-    if (per_sm < 0) {
-        const char *e = getenv("FIRGPU_IDEAL_CTAS");
-        per_sm = e ? atoi(e) : 0;
-    }
-    int64_t grid = (total + kWarps - 1) / kWarps;
-    if (per_sm > 0 && grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
-    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
-    if (grid < 1) grid = 1;
+    // the write-dominated stream needs.
+    if (total >= 0xffffffffLL) return 0;                  // (2^41 outputs: not a real case; the generic kernel takes it)
+    const int64_t grid = (total + kWarps - 1) / kWarps;
+    if (grid > 0x7fffffffLL) return 0;
     fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL, DIL><<<(unsigned)grid, threads, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
     FIRGPU_CUDA(cudaGetLastError());
