@@ -740,7 +740,8 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         const int t_dtype = convert ? FIRGPU_U8 : in_dtype;
         const int es_t = dtype_size(t_dtype);
         const int64_t band = halo_top_valid + height + halo_bottom_valid;
-        const int64_t ld_t = ((width + 1) * es_t + 15) / 16 * 16 / es_t;       // >= one zero element after every row
+        // pitch: a multiple of 128 bytes (whole L2 lines per row), with at least one zero element after an odd uint8 width
+        const int64_t ld_t = ((width + (t_dtype == FIRGPU_U8 ? (width & 1) : 0)) * es_t + 127) / 128 * 128 / es_t;
         uint8_t *tmp = nullptr;
         if ((rc = scratch_alloc((void **)&tmp, (size_t)(ld_t * band * n_img * es_t), (cudaStream_t)stream))) return rc;
         for (int64_t b = 0; b < n_img && !rc; ++b) {
