@@ -478,8 +478,8 @@ bool convert_first(int in_dtype, int64_t samples)
 int uint8_copy_1d(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t halo_left, int64_t halo_right,
                   cudaStream_t stream, uint8_t **tmp, uint8_t **body, int64_t *ld_t)
 {
-    const int64_t lead = (halo_left + 15) / 16 * 16;
-    *ld_t = (lead + cols + halo_right + 15) / 16 * 16;
+    const int64_t lead = (halo_left + 127) / 128 * 128;                  // body and pitch on 128-byte (L2 line) boundaries
+    *ld_t = (lead + cols + halo_right + 127) / 128 * 128;
     int rc = scratch_alloc((void **)tmp, (size_t)(*ld_t * rows), stream);
     if (rc) return rc;
     *body = *tmp + lead;
