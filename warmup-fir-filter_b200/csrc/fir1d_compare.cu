@@ -103,14 +103,13 @@ fir1d_compare_fast_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols,
     double s_abs = 0.0, s_sq = 0.0, s_diff = 0.0, m_abs = 0.0;
     unsigned c_lo = 0, c_hi = 0, c_clip = 0;
 
-    auto fold = [&](const int (&v)[2 * NP], int e) {         // output base + e from window samples v[]
+    auto fold = [&](const int (&v)[2 * NP], const double (&vd)[2 * NP], int e) {   // output base + e from the window samples
         int acc = 0;
         double ideal = 0.0;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            const int sv = v[2 * PL + hi - k + e];
-            acc += hq.v[k] * sv;
-            ideal = __dadd_rn(ideal, __dmul_rn(h.v[k], pixel_to<double>(sv)));
+            acc += hq.v[k] * v[2 * PL + hi - k + e];
+            ideal = __dadd_rn(ideal, __dmul_rn(h.v[k], vd[2 * PL + hi - k + e]));
         }
         const int fixed = min(max((acc + bias) >> frac_bits, 0), kPixelMax);
         const double diff = pixel_to<double>(fixed) - ideal;
@@ -157,8 +156,11 @@ fir1d_compare_fast_kernel(const InT *__restrict__ x, int64_t rows, int64_t cols,
                     v[i] = (g >= 0 && g < cols) ? prep_sample(xr[g]) : 0;
                 }
             }
-            fold(v, 0);
-            if (n + 1 < cols) fold(v, 1);
+            double vd[2 * NP];                               // each sample converted once for both outputs
+#pragma unroll
+            for (int i = 0; i < 2 * NP; ++i) vd[i] = pixel_to<double>(v[i]);
+            fold(v, vd, 0);
+            if (n + 1 < cols) fold(v, vd, 1);
         }
         row += step_rows;
         tcol += step_cols;
