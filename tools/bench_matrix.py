@@ -206,6 +206,13 @@ def main():
             s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
             report(f"batched {rows}x{cols} i16->i16 5tap q1.15", s, rows * cols, 4)
             del x, y
+    if "2dmixed" in cases:
+        img = rand_i16(16384 * 16384).view(16384, 16384)
+        out = torch.empty(16384, 16384, dtype=torch.uint8, device="cuda")
+        for k, tag in (([[1 / 9] * 3] * 3, "3x3 box"), (np.outer(LP5, LP5).tolist(), "5x5 lp")):
+            hq = quant.quantize_taps(np.asarray(k), 12, 16)
+            s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out=out), args.reps)
+            report(f"2d 16384^2 i16->u8 {tag} q4.12 (narrowing pass + uint8 kernel)", s, 16384 * 16384, 3)
     if "causal" in cases:
         g = torch.Generator(device="cuda").manual_seed(9)
         x = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)
