@@ -728,11 +728,9 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     // or base is not 16-byte aligned or whose uint8 width is odd (every row of the copy ends in zero bytes).
     const bool windows_ok = (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1);
     const int es_in = dtype_size(in_dtype);
-    // (int16 containers with uint8 output — the drop-in's default — are narrowed the same way: the tensor-map kernel is
-    // instantiated for equal container types only)
-    const bool convert = out_dtype == FIRGPU_U8 && (convert_first(in_dtype, n_img * height * width) ||
-                                                    (in_dtype == FIRGPU_I16 && convert_first(FIRGPU_I32, n_img * height * width)));
-    const bool repitch = !convert && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16) && in_dtype == out_dtype &&
+    const bool convert = out_dtype == FIRGPU_U8 && convert_first(in_dtype, n_img * height * width);
+    const bool repitch = !convert && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16) &&
+                         (in_dtype == out_dtype || (in_dtype == FIRGPU_I16 && out_dtype == FIRGPU_U8)) &&
                          n_img * height * width >= 4096 && !getenv("FIRGPU_FORCE_GENERIC") &&
                          ((uintptr_t)x % 16 != 0 || (ld_x * es_in) % 16 != 0 || (n_img > 1 && (img_stride_x * es_in) % 16 != 0) ||
                           (in_dtype == FIRGPU_U8 && (width & 1)));

@@ -72,7 +72,8 @@ bool factor_rank1(const int32_t *hq, int kh, int kw, long long *a, long long *b)
 
 int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
 {
-    if (a.in_dtype != a.out_dtype || (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16)) return 0;
+    const bool narrowing = a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8;       // int16 pixels in, uint8 out
+    if ((a.in_dtype != a.out_dtype && !narrowing) || (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16)) return 0;
     if (!shape_supported(a.kh, a.kw)) return 0;
     const char *force = getenv("FIRGPU_FORCE_GENERIC");
     if (force && force[0] == '1') return 0;
@@ -135,7 +136,9 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     p.halo_top = (int)a.halo_top;
     p.shift = f.shift;
     p.bias = f.bias;
-    p.y_vec_ok = ((uintptr_t)a.y % 16 == 0) && (a.ld_y * es) % 16 == 0 && (a.n_img == 1 || (a.img_stride_y * es) % 16 == 0);
+    const int os = dtype_size(a.out_dtype);
+    const int va = 16 * os / es;                             // bytes per thread store: 16, or 8 when narrowing
+    p.y_vec_ok = ((uintptr_t)a.y % va == 0) && (a.ld_y * os) % va == 0 && (a.n_img == 1 || (a.img_stride_y * os) % va == 0);
 
     const long long map_rows = a.halo_top + a.height + a.halo_bottom;
     CUtensorMap map;
@@ -150,6 +153,7 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 0;                          // shape the TMA cannot describe: generic kernel
 
+    if (narrowing) return launch_tiled_i16u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
     return es == 1 ? launch_tiled_u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream)
                    : launch_tiled_i16(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
 }

@@ -140,14 +140,15 @@ __device__ __forceinline__ void mac_row(const uint32_t (&cpe)[kMaxPairs2], const
     }
 }
 
-template <typename T, int KH, int KW, bool HI16, bool SEP>
+template <typename T, int KH, int KW, bool HI16, bool SEP, typename OutT = T>
 __global__ void __launch_bounds__(kBlock2, FIRGPU_T2_MINBLOCKS)
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
     using G = Geo2<T, KH, KW>;
     using G1 = typename G::G1;
     constexpr int ES = G::ES;
-    constexpr int NOUT = 4;                       // 16 output bytes per thread per row
+    constexpr int OS = sizeof(OutT);
+    constexpr int NOUT = G1::SC * OS / 4;         // output words per thread per row: 16 bytes, or 8 for int16 -> uint8
 
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t smem_base = smem_u32(smem);
@@ -259,7 +260,7 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int col = col0 + tid * G1::SC;
         int rows_here = p.height - row0;
         if (rows_here > p.band_rows) rows_here = p.band_rows;
-        T *ycol = reinterpret_cast<T *>(p.y) + (long long)img * p.img_stride_y + (long long)row0 * p.ld_y + col;
+        OutT *ycol = reinterpret_cast<OutT *>(p.y) + (long long)img * p.img_stride_y + (long long)row0 * p.ld_y + col;
         const bool vec = p.y_vec_ok && col + G1::SC <= p.width;
         const int room = p.width - col;            // columns this thread may write
         for (int j = 0; j < spi; ++j) {
@@ -314,22 +315,23 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                             for (int q = 0; q < G1::S / 2; ++q) V[q] = post_pair<HI16>(acc[2 * q], acc[2 * q + 1], p.shift);
                             uint32_t O[NOUT];
-                            if constexpr (ES == 2) {
+                            if constexpr (OS == 2) {
 #pragma unroll
                                 for (int q = 0; q < NOUT; ++q) O[q] = V[q];
                             } else {
 #pragma unroll
                                 for (int q = 0; q < NOUT; ++q) O[q] = __byte_perm(V[2 * q], V[2 * q + 1], 0x6420u);
                             }
-                            T *dst = ycol + (long long)o * p.ld_y;
+                            OutT *dst = ycol + (long long)o * p.ld_y;
                             if (vec) {
-                                store_v4(dst, O[0], O[1], O[2], O[3]);
+                                if constexpr (NOUT == 4) store_v4(dst, O[0], O[1], O[2], O[3]);
+                                else *reinterpret_cast<uint2 *>(dst) = make_uint2(O[0], O[1]);
                             } else {
 #pragma unroll
                                 for (int e = 0; e < G1::SC; ++e) {
                                     if (e < room) {
-                                        if constexpr (ES == 2) dst[e] = (T)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
-                                        else dst[e] = (T)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
+                                        if constexpr (OS == 2) dst[e] = (OutT)((O[e / 2] >> (16 * (e & 1))) & 0xffffu);
+                                        else dst[e] = (OutT)((O[e / 4] >> (8 * (e & 3))) & 0xffu);
                                     }
                                 }
                             }
@@ -350,11 +352,11 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 
 // ---- launch helpers -------------------------------------------------------------
-template <typename T, int KH, int KW, bool HI16, bool SEP>
+template <typename T, int KH, int KW, bool HI16, bool SEP, typename OutT = T>
 int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t stream)
 {
     using G = Geo2<T, KH, KW>;
-    auto kern = fir2d_tiled_kernel<T, KH, KW, HI16, SEP>;
+    auto kern = fir2d_tiled_kernel<T, KH, KW, HI16, SEP, OutT>;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -387,27 +389,27 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     return 1;
 }
 
-template <typename T, int KH, int KW>
+template <typename T, int KH, int KW, typename OutT = T>
 int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, bool hi16, bool sep, cudaStream_t s)
 {
     if constexpr (KH > 1 && KW >= 3 && !(KH == 3 && KW == 3)) {
         if (sep)
-            return hi16 ? launch_tiled_one<T, KH, KW, true, true>(map, p, s) : launch_tiled_one<T, KH, KW, false, true>(map, p, s);
+            return hi16 ? launch_tiled_one<T, KH, KW, true, true, OutT>(map, p, s) : launch_tiled_one<T, KH, KW, false, true, OutT>(map, p, s);
     }
-    return hi16 ? launch_tiled_one<T, KH, KW, true, false>(map, p, s) : launch_tiled_one<T, KH, KW, false, false>(map, p, s);
+    return hi16 ? launch_tiled_one<T, KH, KW, true, false, OutT>(map, p, s) : launch_tiled_one<T, KH, KW, false, false, OutT>(map, p, s);
 }
 
-template <typename T>
+template <typename T, typename OutT = T>
 int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
 {
-    if (kh == 1 && kw == 3) return launch_tiled_modes<T, 1, 3>(map, p, hi16, sep, s);   // short-row batches of the 1-D filter
-    if (kh == 1 && kw == 5) return launch_tiled_modes<T, 1, 5>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5>(map, p, hi16, sep, s);
+    if (kh == 1 && kw == 3) return launch_tiled_modes<T, 1, 3, OutT>(map, p, hi16, sep, s);   // short-row batches of the 1-D filter
+    if (kh == 1 && kw == 5) return launch_tiled_modes<T, 1, 5, OutT>(map, p, hi16, sep, s);
+    if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1, OutT>(map, p, hi16, sep, s);
+    if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3, OutT>(map, p, hi16, sep, s);
+    if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5, OutT>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1, OutT>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3, OutT>(map, p, hi16, sep, s);
+    if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5, OutT>(map, p, hi16, sep, s);
     return 0;
 }
 
@@ -419,6 +421,7 @@ inline bool shape_supported(int kh, int kw)
 }
 int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
 int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
+int launch_tiled_i16u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);   // int16 pixels in, uint8 out
 
 }  // namespace tiled
 }  // namespace firgpu
