@@ -507,3 +507,20 @@ def test_dense_rows_of_odd_pitch_take_the_flattened_pass(fg, torch):
     h21 = (np.ones(21) / 42).tolist()
     assert np.array_equal(fg.fir1d_fixed(torch.from_numpy(x).cuda(), h21, 15, 32, 16).cpu().numpy(), onp.fir1d_fixed(x, h21, 15, 32, 16))
     assert _lib.last_path() == _lib.PATH_STAGED
+
+
+def test_long_filters_int16_in_uint8_out(fg, torch):
+    """10..65 taps on an int16 container with the drop-in's default uint8 output:
+    served by the long-filter buckets of the staged kernel, bit-exact."""
+    from firgpu import _lib
+    rng = np.random.default_rng(123)
+    x = signal(rng, 300_001, np.int16)
+    xt = torch.from_numpy(x).cuda()
+    for n_taps in (10, 13, 21, 33, 50, 65):
+        h = (rng.uniform(-1, 1, size=n_taps) / n_taps * 4).tolist()
+        got = fg.fir1d_fixed(xt, h, 12, 32, 16)
+        assert _lib.last_path() == _lib.PATH_STAGED, n_taps
+        assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x, h, 12, 32, 16)), n_taps
+    rows = signal(rng, (5, 40_000), np.int16)
+    h = (np.ones(17) / 17).tolist()
+    assert np.array_equal(fg.fir1d_fixed(torch.from_numpy(rows).cuda(), h).cpu().numpy(), onp.fir1d_fixed(rows, h))

@@ -42,7 +42,8 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     int32_t padded[kMaxFastTaps];
     const int32_t *taps_in = hq_host;
     if (a.n_taps > kMaxWideTaps) {
-        if (n_filters != 1 || a.dilation != 1 || a.in_dtype != a.out_dtype) return 0;
+        const bool long_pair = a.in_dtype == a.out_dtype || (a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8);
+        if (n_filters != 1 || a.dilation != 1 || !long_pair) return 0;
         mac = 0;
         for (int b : kLongBuckets)
             if (!bucket && b >= a.n_taps) bucket = b;
@@ -89,9 +90,11 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
                  (n_filters == 1 || (filter_stride_y * os) % out_align == 0);
     for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
     for (int k = 0; k < n_taps && k < kMaxWideTaps; ++k) p.hq[k] = f0.taps[k];
-    if (bucket)
-        return a.in_dtype == FIRGPU_U8 ? launch_staged_long_u8(p, bucket, f0.hi16, a.stream)
-                                       : launch_staged_long_i16(p, bucket, f0.hi16, a.stream);
+    if (bucket) {
+        if (a.in_dtype == FIRGPU_U8) return launch_staged_long_u8(p, bucket, f0.hi16, a.stream);
+        return a.out_dtype == FIRGPU_U8 ? launch_staged_long_i16u8(p, bucket, f0.hi16, a.stream)
+                                        : launch_staged_long_i16(p, bucket, f0.hi16, a.stream);
+    }
 
     if (a.in_dtype == FIRGPU_U8) {
         return a.out_dtype == FIRGPU_U8

@@ -701,21 +701,22 @@ int launch_dil(const StagedParams &p, int n_taps, int dilation, bool hi16, int m
 // zero taps cost dp2a slots but no accuracy.  8 KiB tiles, two CTAs per SM.
 using LongTapCfg = Cfg<256, 2, 2, 1, 2>;
 constexpr int kLongBuckets[] = {13, 17, 25, 33, 49, 65};
-template <typename T>
+template <typename T, typename OutT = T>
 int launch_long(const StagedParams &p, int bucket, bool hi16, cudaStream_t s)
 {
     switch (bucket) {
-    case 13: return hi16 ? launch_cfg<LongTapCfg, T, T, 13, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 13, 1, false, 0>(p, s);
-    case 17: return hi16 ? launch_cfg<LongTapCfg, T, T, 17, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 17, 1, false, 0>(p, s);
-    case 25: return hi16 ? launch_cfg<LongTapCfg, T, T, 25, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 25, 1, false, 0>(p, s);
-    case 33: return hi16 ? launch_cfg<LongTapCfg, T, T, 33, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 33, 1, false, 0>(p, s);
-    case 49: return hi16 ? launch_cfg<LongTapCfg, T, T, 49, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 49, 1, false, 0>(p, s);
-    case 65: return hi16 ? launch_cfg<LongTapCfg, T, T, 65, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, T, 65, 1, false, 0>(p, s);
+    case 13: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 13, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 13, 1, false, 0>(p, s);
+    case 17: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 17, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 17, 1, false, 0>(p, s);
+    case 25: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 25, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 25, 1, false, 0>(p, s);
+    case 33: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 33, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 33, 1, false, 0>(p, s);
+    case 49: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 49, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 49, 1, false, 0>(p, s);
+    case 65: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 65, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 65, 1, false, 0>(p, s);
     default: return 0;
     }
 }
 int launch_staged_long_u8(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
 int launch_staged_long_i16(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
+int launch_staged_long_i16u8(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);   // int16 samples in, uint8 out
 
 // One translation unit per (input, output) container pair instantiates these
 // (fir1d_staged_inst.cu compiled four times), which keeps the build parallel.
