@@ -12,7 +12,10 @@ scaling, no collective in the timed region).  Inputs (512 MiB per rank) are
 larger than the 126 MB L2, so every step streams from HBM.
 
 Printed JSON (one line, rank 0): the base contract plus ``roofline``,
-``cpu_baseline``, ``e2e``, ``clocks``, ``gpu_launches``.
+``cpu_baseline``, ``e2e``, ``clocks``, ``gpu_launches`` and ``configs`` — BASELINE
+configs 3, 4 and 5 measured in the same run, STRONG-scaled over the N ranks
+(fixed global problem, sharded as SURVEY 8(e) says: channels / segments with
+halo / row bands with halo, no collective in any timed region).
 """
 from __future__ import annotations
 
@@ -242,6 +245,136 @@ def make_segment(torch, dist, rank: int, world: int, device):
     return piece, lead, buf, body
 
 
+# ----------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5: strong scaling at the N the driver passes
+# ----------------------------------------------------------------------------
+def device_signal(torch, shape, seed, device):
+    """SURVEY 8(d) input recipe on the device: 99 % pixels in [0,255], 1 % anywhere in int16."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randint(0, 256, shape, generator=g, device=device, dtype=torch.int16)
+    n = x.numel()
+    where = torch.randint(0, n, (n // 100,), generator=g, device=device)
+    x.view(-1)[where] = torch.randint(-32768, 32768, (n // 100,), generator=g, device=device, dtype=torch.int32).to(torch.int16)
+    return x
+
+
+def other_configs(args, torch, dist, rank: int, world: int, device, peak: float) -> dict:
+    """One step = one pass over this rank's shard, submitted as a recorded sequence (firgpu.Recording: the library's
+    batch entry, a CUDA graph of the same launches the public call makes) so that a 20-microsecond kernel is not
+    timed behind 25 microseconds of Python.  Timing: barrier + synchronize, CUDA events on the launching stream,
+    max over ranks.  `consistent` is a self-consistency check between two different kernel paths of the library
+    (parity against the oracle is the job of tests/, which cover these configs at full size)."""
+    import firgpu
+    from firgpu import _lib, quant, shard
+
+    reps = max(5, min(args.steps, 20))
+    out = {}
+
+    def timed(step):
+        rec = firgpu.Recording(step)
+        for _ in range(3):
+            rec.replay()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            rec.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / reps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), rec.kernels
+
+    def all_ok(flag: bool) -> bool:
+        t = torch.tensor([1 if flag else 0], device=device, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def entry(name, ms, kernels, units, unit_name, ok, how, partition):
+        gbs = units * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "value": units / (ms * 1e-3) / 1e9, "unit": unit_name, "scaling": "strong", "n_gpus": world,
+                     "roofline": {"bound": "hbm", "achieved_per_gpu": gbs / world, "peak": peak, "unit": "GB/s",
+                                  "frac": gbs / world / peak, "bytes_per_unit": BYTES_PER_SAMPLE},
+                     "kernels_per_step": kernels, "steps": reps, "partition": partition, "consistent": ok, "consistency_check": how}
+
+    hq5 = quant.quantize_taps(TAPS, FRAC_BITS, COEFF_BITS)
+
+    # ---- config 3: 8192 channels x 2^20 samples, channel-sharded, no halo ----------------------------
+    rows, cols = 8192, 1 << 20
+    mine = shard.plan_rows(rows, world)[rank]
+    need = 2 * mine.size * cols * 2 + (2 << 30)
+    if torch.cuda.mem_get_info(device)[0] > need:
+        x = torch.empty((mine.size, cols), dtype=torch.int16, device=device)
+        for b in range(0, mine.size, 512):
+            e = min(b + 512, mine.size)
+            x[b:e] = device_signal(torch, (e - b, cols), 1234 + (mine.start + b) // 512, device)
+        y = torch.empty_like(x)
+        ms, kernels = timed(lambda: firgpu.fir1d_fixed_q(x, hq5, FRAC_BITS, ACC_BITS, out_dtype=np.int16, out=y))
+        assert _lib.last_path() == _lib.PATH_STAGED
+        r = mine.size // 2                      # a channel filtered alone (single-row tile walk) equals its row of the batch
+        ok = torch.equal(firgpu.fir1d_fixed_q(x[r], hq5, FRAC_BITS, ACC_BITS, out_dtype=np.int16), y[r])
+        entry("config3", ms, kernels, rows * cols, "Gsamples/s", all_ok(ok), "one channel filtered alone == its row of the batch",
+              f"channels x{world}, no halo")
+        del x, y
+    else:
+        out["config3"] = {"skipped": "not enough free HBM for 8192 x 2^20 int16 in + out on this rank"}
+
+    # ---- config 5: interleaved I/Q, 2^27 complex samples, contiguous segments + halo -----------------
+    n = 1 << 28
+    pieces = shard.plan_segments(n, world, len(TAPS), 2, align=4096)
+    me = pieces[rank]
+    lead = shard.aligned_lead(me.before, 2)
+    buf = torch.zeros(lead + me.size + me.after, dtype=torch.int16, device=device)
+    buf[lead:lead + me.size] = device_signal(torch, (me.size,), 5678 + rank, device)
+    if world > 1:
+        shard.exchange_halos(buf, lead, pieces, rank, dist)
+    body = buf[lead:lead + me.size]
+    y = torch.empty(me.size, dtype=torch.int16, device=device)
+    ms, kernels = timed(lambda: firgpu.fir1d_fixed_q(body, hq5, FRAC_BITS, ACC_BITS, dilation=2, out_dtype=np.int16, out=y,
+                                                    halo_left_valid=me.before, halo_right_valid=me.after))
+    assert _lib.last_path() == _lib.PATH_STAGED
+    w = min(me.size, 1 << 22)                   # Re of a window filtered as a plain 1-D signal (dilation 1) equals Re of the I/Q pass
+    win = buf[lead - me.before:lead + w + me.after]
+    re = firgpu.fir1d_fixed_q(win[0::2].contiguous(), hq5, FRAC_BITS, ACC_BITS, out_dtype=np.int16)
+    skip = me.before // 2
+    ok = torch.equal(re[skip:skip + w // 2 - 2], y[0:w:2][:w // 2 - 2])
+    entry("config5", ms, kernels, n, "Gsamples/s", all_ok(ok), "Re of a window filtered as a 1-D signal == Re of the interleaved pass",
+          f"segments x{world}, halo {me.before}+{me.after} scalars duplicated at shard time")
+    del buf, y, body, win, re
+
+    # ---- config 4: [4, 16384, 16384] int16 images, row bands + halo ------------------------------------
+    b_img, hgt, wid = 4, 16384, 16384
+    lp = np.asarray(TAPS)
+    k_general = np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5))
+    for key, k in (("config4_3x3", np.full((3, 3), 1 / 9)), ("config4_5x5_rank1", np.outer(lp, lp)), ("config4_5x5_general", k_general)):
+        kh = k.shape[0]
+        bands = shard.plan_bands(hgt, world, kh)
+        me = bands[rank]
+        buf = torch.zeros((b_img, me.before + me.size + me.after, wid), dtype=torch.int16, device=device)
+        buf[:, me.before:me.before + me.size, :] = device_signal(torch, (b_img, me.size, wid), 4321 + rank, device)
+        if world > 1:
+            shard.exchange_band_halos(buf, bands, rank, dist)
+        body = buf[:, me.before:me.before + me.size, :]
+        res = torch.empty((b_img, me.size, wid), dtype=torch.int16, device=device)
+        hq = quant.quantize_taps(k, 12, 16)
+        ms, kernels = timed(lambda: firgpu.fir2d_fixed_q(body, hq, 12, 32, out_dtype=np.int16, out=res,
+                                                        halo_top_valid=me.before, halo_bottom_valid=me.after))
+        assert _lib.last_path() == _lib.PATH_STAGED
+        # a sub-band with its own halo rows, filtered as a shard of its own, equals the same rows of the band
+        r0 = me.size // 2
+        sub = firgpu.fir2d_fixed_q(body[1:2, r0:r0 + 256, :], hq, 12, 32, out_dtype=np.int16, halo_top_valid=min(r0, kh - 1 - kh // 2),
+                                   halo_bottom_valid=min(me.size - r0 - 256, kh // 2))
+        ok = torch.equal(sub[0], res[1, r0:r0 + 256, :])
+        entry(key, ms, kernels, b_img * hgt * wid, "Gpixels/s", all_ok(ok), "a 256-row sub-band with halo rows == the same rows of the band",
+              f"row bands x{world}, {kh - 1} halo rows duplicated at shard time")
+        del buf, res, body, sub
+    return out
+
+
 def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     import torch
     import torch.distributed as dist
@@ -322,18 +455,30 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
         e2e_value = world * piece.size * e2e_steps / float(e2e_s.item()) / 1e9
         e2e_ok = bool(torch.equal(y_host[piece.before:piece.before + piece.size], y.cpu())) if rank == 0 else None
 
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    configs = None
+    if not args.no_configs:
+        del buf, body, y
+        if not args.no_e2e:
+            del x_host, y_host, x_np, y_np
+        torch.cuda.empty_cache()
+        clocks.region(True)
+        configs = other_configs(args, torch, dist, rank, world, device, peak)
+        clocks.region(False)
+
     clock_summary = clocks.summary()
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = BYTES_PER_SAMPLE * piece.size / (ms_per_step * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("fir1d_staged_i16_i16_5tap_2p28_dram_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("fir1d_staged_i16_i16_5tap_2p28_dram_bytes_per_launch")
+            traffic_src = tj.get("source")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -343,13 +488,15 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                        "acc_bits": ACC_BITS, "coeff_bits": COEFF_BITS, "samples_per_gpu": piece.size,
                        "l2": "inputs (512 MiB/GPU) larger than L2, no flush needed", "parallelism": f"segments x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_launch": BYTES_PER_SAMPLE * piece.size, "kernel": "fir1d_staged_kernel<int16,int16,5,1>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_host * world,
                     "d2h_bytes_per_step": 2 * n_host * world, "steps": e2e_steps,
                     "api": "firgpu.fir1d_fixed(host int16 ndarray, pinned) -> firgpu_fir1d_fixed_host", "matches_device_run": e2e_ok},
             "gpu_launches": int(launches), "clocks": clock_summary,
         }
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line), flush=True)
@@ -366,6 +513,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-configs", action="store_true", help="profiling runs only: skip BASELINE configs 3 / 4 / 5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FIRGPU_VERSION 100          /* 0.1.0 */
+#define FIRGPU_VERSION 200          /* 0.2.0 */
 #define FIRGPU_MAX_TAPS 1024        /* per filter; 2-D: kh*kw */
 
 enum firgpu_dtype { FIRGPU_U8 = 0, FIRGPU_I16 = 1, FIRGPU_I32 = 2, FIRGPU_F32 = 3, FIRGPU_F64 = 4 };
@@ -77,6 +77,9 @@ int firgpu_last_path(void);
 /* Number of kernels this library has launched from the calling thread. */
 int64_t firgpu_launch_count(void);
 int firgpu_device_count(int *count);
+/* Current CUDA device of the calling thread (device entry points run on it). */
+int firgpu_get_device(int *device);
+int firgpu_set_device(int device);
 
 /* ------------------------------------------------------------------------
  * 1-D fixed-point FIR, row-batched.
@@ -237,6 +240,18 @@ int firgpu_fir1d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
                             const int32_t *hq, int n_taps, int dilation,
                             int frac_bits, int acc_bits, int device);
 
+/* The same call spread over several devices of one box (devices[n_devices],
+ * CUDA ordinals): rows are split evenly, a single long row is cut into
+ * contiguous segments that read the taps' reach from the neighbouring host
+ * samples (the partitioning of SURVEY 8(e): no collective, no device-to-device
+ * traffic).  One host thread and one copy/compute pipeline per device; returns
+ * when y is complete. */
+int firgpu_fir1d_fixed_host_multi(const void *x, void *y, int in_dtype, int out_dtype,
+                                  int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                                  const int32_t *hq, int n_taps, int dilation,
+                                  int frac_bits, int acc_bits,
+                                  const int *devices, int n_devices);
+
 /* n_filters tap sets over one host input: y holds n_filters outputs,
  * filter_stride_y elements apart (gen_fixed_output.py:91-104 in one call). */
 int firgpu_fir1d_fixed_multi_host(const void *x, void *y, int in_dtype, int out_dtype,
@@ -257,6 +272,73 @@ int firgpu_fir2d_fixed_host(const void *x, void *y, int in_dtype, int out_dtype,
 int firgpu_fir2d_ideal_host(const void *x, void *y, int in_dtype, int out_dtype,
                             int64_t n_img, int64_t height, int64_t width,
                             const double *h, int kh, int kw, int device);
+
+/* ------------------------------------------------------------------------
+ * Streaming filters with the history resident on the device.
+ *
+ * Stand behind the reference's C++ class
+ *   Fir1D::process_sample / reset     fir_1d/model/cpp/fir_1d_ref.cpp:16-35
+ * whose reg_ member carries the last n_taps samples between calls.  A stream
+ * object is the causal filter y[n] = sum_k h[k] * x[n - k*dilation] over an
+ * unbounded signal delivered in blocks; the (n_taps-1)*dilation most recent
+ * scalars live in HBM between calls.  Concatenating the outputs of any
+ * blocking of a signal is bit-identical to one firgpu_fir1d_*_ex call with
+ * centre = 0 over the whole signal (and, for the raw float64 ideal model, to
+ * Fir1D::process_sample sample by sample).
+ *
+ *   create_fixed  the fixed-point model (parameters as firgpu_fir1d_fixed_ex;
+ *                 (0,255,0,255) = the reference's clamp / saturation ranges);
+ *   create_ideal  the floating-point model (parameters as firgpu_fir1d_ideal_ex;
+ *                 raw = 1 with F64 samples is the C++ Fir1D);
+ *   process       x, y: DEVICE pointers to n scalars; stream-ordered and
+ *                 asynchronous; blocks of one object must be submitted in
+ *                 signal order on streams that respect that order;
+ *   process_host  x, y: HOST pointers (pinned memory is DMA'd directly);
+ *                 returns when y is complete;
+ *   reset         zero the history (Fir1D::reset).
+ * device < 0 = the current device.  Objects are thread-safe (one call at a
+ * time per object).
+ * ------------------------------------------------------------------------ */
+typedef struct firgpu_stream_s *firgpu_stream_t;
+int firgpu_stream_create_fixed(firgpu_stream_t *out, int in_dtype, int out_dtype,
+                               const int32_t *hq, int n_taps, int dilation,
+                               int frac_bits, int acc_bits,
+                               int in_lo, int in_hi, int out_lo, int out_hi, int device);
+int firgpu_stream_create_ideal(firgpu_stream_t *out, int in_dtype, int out_dtype,
+                               const double *h, int n_taps, int dilation,
+                               int in_lo, int in_hi, int raw, int device);
+int firgpu_stream_process(firgpu_stream_t s, const void *x, void *y, int64_t n, void *stream);
+int firgpu_stream_process_host(firgpu_stream_t s, const void *x, void *y, int64_t n);
+int firgpu_stream_reset(firgpu_stream_t s, void *stream);
+int firgpu_stream_history(firgpu_stream_t s, int64_t *scalars);   /* (n_taps-1)*dilation */
+int firgpu_stream_destroy(firgpu_stream_t s);
+
+/* ------------------------------------------------------------------------
+ * Recorded launch sequences (the batch entry point).
+ *
+ * The reference pipeline filters 7 images with 8 coefficient sets, one
+ * Python call per image row (fir_1d/sim/vector/gen_fixed_output.py:91-104,
+ * 44-59); here a whole such sequence of DEVICE entry-point calls is recorded
+ * once and replayed with one submission:
+ *
+ *     firgpu_record_begin(stream);
+ *     ... any firgpu_* device entry points on `stream`, this thread ...
+ *     firgpu_record_end(stream, &g);          nothing has executed yet
+ *     firgpu_graph_launch(g, stream);         as often as wanted
+ *
+ * Pointers, shapes and taps are frozen into the recording; the buffers'
+ * CONTENTS are read at replay time.  Each distinct call pattern must have run
+ * once eagerly before it is recorded (first use of a kernel configures it).
+ * Entry points that synchronise (firgpu_fir1d_compare, every *_host form)
+ * cannot be recorded.  `stream` must not be the NULL stream.
+ * ------------------------------------------------------------------------ */
+typedef struct firgpu_graph_s *firgpu_graph_t;
+int firgpu_record_begin(void *stream);
+int firgpu_record_end(void *stream, firgpu_graph_t *out);
+int firgpu_record_abort(void *stream);                 /* leave recording mode after an error, discarding it */
+int firgpu_graph_launch(firgpu_graph_t g, void *stream);
+int firgpu_graph_nodes(firgpu_graph_t g, int64_t *kernels);   /* kernel launches one replay performs */
+int firgpu_graph_destroy(firgpu_graph_t g);
 
 /* Page-locked host memory for callers without their own allocator (NumPy
  * arrays wrapped around it are DMA'd directly by the _host entry points). */

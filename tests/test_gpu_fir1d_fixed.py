@@ -138,22 +138,26 @@ def test_staged_all_tap_counts(fg, torch, in_dtype, out_dtype, n_taps):
 
 
 def test_generic_kernel_serves_what_staged_declines(fg, torch):
-    """acc_bits wrap live, 32-bit taps, long filters, other containers."""
+    """A live acc_bits wrap and 32-bit taps are served by the staged kernel (WRAP post mode, IMAD for taps beyond
+    int16); filters beyond the largest bucket, accumulators wider than 32 bits whose sums do not fit int32, and small
+    float / int32 inputs go to the generic kernels."""
     from firgpu import _lib
     rng = np.random.default_rng(9)
     x = signal(rng, 5000, np.int16)
     xt = torch.from_numpy(x).cuda()
+    S, G = _lib.PATH_STAGED, _lib.PATH_GENERIC
     cases = [
-        (12, 16, 16, [0.9, -0.7, 0.8, 0.3, -0.2]),        # acc_bits wrap is live
-        (28, 32, 32, [7.5, -7.5, 0.001]),                 # 32-bit taps, wrap live
-        (12, 32, 16, rng.uniform(-0.1, 0.1, size=70).tolist()),   # longer than the largest staged bucket (65)
-        (12, 20, 16, [1.0]),                              # SURVEY 8(c)5 wrap case
-        (3, 12, 8, [7.0, -6.5, 3.25, 1.0]),               # tiny frac_bits, 8-bit taps, wrap live
-        (30, 64, 32, [0.4, 0.3]),                         # frac_bits beyond the packed path
+        (12, 16, 16, [0.9, -0.7, 0.8, 0.3, -0.2], S),     # acc_bits wrap is live
+        (28, 32, 32, [7.5, -7.5, 0.001], S),              # 32-bit taps, wrap live
+        (12, 32, 16, rng.uniform(-0.1, 0.1, size=70).tolist(), G),   # longer than the largest staged bucket (65)
+        (12, 20, 16, [1.0], S),                           # SURVEY 8(c)5 wrap case
+        (3, 12, 8, [7.0, -6.5, 3.25, 1.0], S),            # tiny frac_bits, 8-bit taps, wrap live
+        (30, 64, 32, [0.4, 0.3], G),                      # 64-bit accumulator, sums beyond int32
+        (28, 40, 32, [0.001, 0.002], S),                  # wider accumulator, but the sums provably fit int32
     ]
-    for frac, acc, cb, h in cases:
+    for frac, acc, cb, h, path in cases:
         y = fg.fir1d_fixed(xt, h, frac, acc, cb).cpu().numpy()
-        assert _lib.last_path() == _lib.PATH_GENERIC, (frac, acc, cb)
+        assert _lib.last_path() == path, (frac, acc, cb)
         assert np.array_equal(y, onp.fir1d_fixed(x, h, frac, acc, cb)), (frac, acc, cb)
     for dt in (np.int32, np.float32, np.float64):
         xs = (rng.uniform(-20, 300, size=3001)).astype(dt)
@@ -303,9 +307,8 @@ def test_multi_filter_reads_input_once(fg, torch, manifest):
             want = np.stack([onp.fir1d_fixed(x, h) for h in sets])
             before = _lib.launch_count()
             got = fg.fir1d_fixed_multi(torch.from_numpy(x).cuda(), sets)
-            # one pass over the input; dense rows of odd pitch and batches of narrow rows (flattened pass) add one launch
-            # that rewrites the row ends of all four outputs
-            assert _lib.launch_count() - before == (2 if shape in ((37, 4499), (64, 64)) else 1) and _lib.last_path() == _lib.PATH_STAGED
+            # one pass over the input, row ends included
+            assert _lib.launch_count() - before == 1 and _lib.last_path() == _lib.PATH_STAGED
             assert got.shape == (4,) + shape and np.array_equal(got.cpu().numpy(), want), (tap, shape)
             assert np.array_equal(fg.fir1d_fixed_multi(x, sets), want), (tap, shape, "host")
     x = rng.integers(-100, 400, size=(3, 10_001)).astype(np.int16)
@@ -476,7 +479,7 @@ def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):
 def test_dense_rows_of_odd_pitch_take_the_flattened_pass(fg, torch):
     """Row batches whose pitch is not a multiple of 16 bytes (odd image widths,
     the reference's 4499-wide image) are filtered as one long row by the
-    staged kernel, then the outputs within reach of a row end are rewritten:
+    staged kernel, which zero-pads every row on its own inside the kernel:
     bit-exact with per-row zero padding, for every container pair, I/Q
     dilation, long filters and the four-tap-set pass."""
     from firgpu import _lib

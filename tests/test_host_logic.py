@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), f"{name} declared in include/firgpu.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
-    assert _lib.lib().firgpu_version() == 100
+    assert _lib.lib().firgpu_version() == 200
 
 
 def test_header_has_no_torch_or_cuda_types():

@@ -186,6 +186,19 @@ struct DeviceGuard {
     }
 };
 
+// Leaves a host pipeline only after every slot stream is idle.  The success path has already waited for each slot;
+// on an error exit, copies queued on the other slots may still be reading or writing the CALLER's (pinned) buffers
+// and the slot buffers the next call will reuse.
+struct SlotDrain {
+    HostCtx *c;
+    ~SlotDrain()
+    {
+        if (!c->ready) return;
+        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(c->stream[s]);
+        cudaGetLastError();
+    }
+};
+
 // A rectangular piece of a [rows x cols] problem plus the neighbour columns /
 // rows that travel with it.
 struct Piece {
@@ -260,8 +273,11 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 // launches the device entry point on one piece.
 template <typename Run>
 int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
-                int64_t reach_before, int64_t reach_after, int device, Run run, int n_out = 1, int64_t out_stride = 0)
+                int64_t reach_before, int64_t reach_after, int device, Run run, int n_out = 1, int64_t out_stride = 0,
+                int64_t avail_before = 0, int64_t avail_after = 0)
 {
+    // avail_before / avail_after (rows == 1 only): real samples of a longer host signal that lie in front of x / behind
+    // x + cols — this call filters a segment of it (one device's share of a multi-device call) and reads them as halo.
     if (rows == 0 || cols == 0) {
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
@@ -279,7 +295,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     std::vector<Piece> pieces;
     const int64_t row_bytes = cols * es;
     const int64_t q_in = 16 / es;                      // scalars per 16 bytes
-    if ((size_t)row_bytes <= chunk_target()) {
+    if ((size_t)row_bytes <= chunk_target() && avail_before == 0 && avail_after == 0) {
         int64_t per = (int64_t)(chunk_target() / (size_t)row_bytes);
         if (per < 1) per = 1;
         // keep at least kSlots pieces in flight when there is enough work
@@ -293,7 +309,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
         for (int64_t r = 0; r < rows; ++r)
             for (int64_t c0 = 0; c0 < cols; c0 += seg) {
                 const int64_t nc = std::min(seg, cols - c0);
-                pieces.push_back({r, 1, c0, nc, std::min(reach_before, c0), std::min(reach_after, cols - c0 - nc)});
+                pieces.push_back({r, 1, c0, nc, std::min(reach_before, c0 + avail_before), std::min(reach_after, cols - c0 - nc + avail_after)});
             }
     }
     // Device layout of a piece: rows at a 16-byte-aligned pitch; a column
@@ -306,6 +322,7 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
     }
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if ((rc = ctx_reserve(c, (size_t)max_in, (size_t)max_out, !x_pinned, !y_pinned))) return rc;
+    SlotDrain drain{c};                                // on every exit, errors included: no copy of ours outlives the call
 
     const bool trace = getenv("FIRGPU_TRACE") != nullptr;
     double t_sync = 0, t_out = 0, t_in = 0, t_enq = 0;
@@ -341,13 +358,13 @@ int pipeline_1d(const void *x, void *y, int es, int os, int64_t rows, int64_t co
         // A column segment is copied from `pre` scalars before its first one, with pre >= its halo and a multiple of
         // 256 bytes: source and destination of the DMA then start 256-byte aligned (segments start at multiples of
         // 16384 scalars), which measured 8 % faster than starting at the 2-scalar halo.  The extra scalars are ignored.
-        const int64_t pre = p.before ? round_up(p.before, 256 / es) : 0;
-        const int64_t lead = pre;                                      // aligned offset of the segment in the slot
+        const int64_t lead = p.before ? round_up(p.before, 256 / es) : 0;   // aligned offset of the segment in the slot
+        const int64_t pre = lead <= p.c0 + avail_before ? lead : p.before;  // (a segment at the very start of the host signal has only its halo in front)
         const int64_t span = pre + p.nc + p.after;                     // scalars copied per row
         const int64_t ldd_x = round_up(lead + p.nc + p.after, q_in);
         const int64_t ldd_y = round_up(p.nc, 16);
         const char *src = (const char *)x + (p.r0 * ld_x + p.c0 - pre) * es;
-        char *d_first = (char *)c->d_in[s];                            // where the first copied scalar lands
+        char *d_first = (char *)c->d_in[s] + (lead - pre) * es;        // where the first copied scalar lands
         if (x_pinned) {
             if ((rc = copy_rows_async(d_first, (size_t)ldd_x * es, src, (size_t)ld_x * es, (size_t)span * es,
                                       (size_t)p.nr, cudaMemcpyHostToDevice, c->stream[s])))
@@ -417,6 +434,7 @@ int pipeline_2d(const void *x, void *y, int es, int os, int64_t n_img, int64_t h
     const size_t max_out = (size_t)(ldd_y * band * os + 256);
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if ((rc = ctx_reserve(c, max_in, max_out, !x_pinned, !y_pinned))) return rc;
+    SlotDrain drain{c};
 
     struct Pending {
         bool busy = false;
@@ -470,7 +488,7 @@ bool wide_container(int in_dtype) { return in_dtype == FIRGPU_I32 || in_dtype ==
 // int32 / float containers of a useful size are converted to the reference's uint8 pixels first (csrc/prep_u8.cu).
 bool convert_first(int in_dtype, int64_t samples)
 {
-    return wide_container(in_dtype) && samples >= 4096 && !getenv("FIRGPU_FORCE_GENERIC");
+    return wide_container(in_dtype) && samples >= 4096 && !force_generic();
 }
 
 // uint8 copy of rows x (halo_left + cols + halo_right) samples in scratch memory: *body points at column 0 of row 0
@@ -490,13 +508,14 @@ int uint8_copy_1d(const void *x, int in_dtype, int64_t rows, int64_t cols, int64
 
 int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtype == FIRGPU_I16 ? 2 : 0; }
 
-// "Flattened pass": a dense batch of rows (pitch == cols) whose pitch is not a multiple of 16 bytes — odd image
-// widths — cannot be staged row by row with bulk copies.  Filtering the whole batch as ONE long row gives the right
-// answer everywhere except within the taps' reach of a row end (where the neighbouring row's samples stand in for the
-// zero padding); launch_fir1d_fixed_edges() then rewrites exactly those outputs.
-// Narrow aligned rows (at most this many bytes) also go the flattened way: the row-streaming kernel stages 2 KiB wide
-// strips, so a batch of 512-byte rows keeps only a quarter of its threads busy.
-constexpr long kFlattenNarrowBytes = 256;   // measured (int16, 2^27 samples): 64 B rows 2.6x, 256 B rows 1.5x faster flattened, 512 B a tie, wider rows slower
+// "Flattened pass": a dense batch of rows (pitch == cols) is filtered by the staged kernel as ONE row of rows * cols
+// samples — base pointers are 16-byte aligned, so every tile is a bulk copy whatever the row pitch (odd image widths,
+// the reference's 2999 x 4499 image) and no tile is left mostly empty by a short row.  The kernel is told the row
+// length (`period`) and forms the sums of the few chunks whose window straddles a row boundary once per side, so each
+// row keeps its own zero padding (fir_1d/sim/vector/gen_fixed_output.py:44-59).  One launch.
+// Rows wider than kFlattenMaxBytes with a 16-byte aligned pitch stay on the per-row tile walk (whole tiles per row,
+// no per-chunk boundary test).
+constexpr long kFlattenMaxBytes = 64 << 10;
 
 bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                 int n_taps, int dilation)
@@ -504,18 +523,17 @@ bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64
     if (rows < 2 || ld_x != cols || ld_y != cols) return false;
     if (in_dtype != FIRGPU_U8 && in_dtype != FIRGPU_I16) return false;
     const int es = in_dtype == FIRGPU_U8 ? 1 : 2, os = out_size_fixed(out_dtype);
-    if ((cols * es) % 16 == 0 && (cols * os) % 16 == 0) {                      // aligned pitches: the regular paths apply ...
-        static long narrow = -1;                                               // ... except for narrow rows (see below)
-        if (narrow < 0) {
-            const char *e = getenv("FIRGPU_FLATTEN_NARROW_BYTES");
-            narrow = e ? atol(e) : kFlattenNarrowBytes;
-        }
-        if (cols * es > narrow || rows < 64) return false;
-    }
+    static const long max_bytes = [] {
+        const char *e = getenv("FIRGPU_FLATTEN_MAX_BYTES");
+        return e ? atol(e) : kFlattenMaxBytes;
+    }();
+    static const bool disabled = getenv("FIRGPU_NO_FLATTEN") != nullptr;
+    if (disabled || force_generic()) return false;
+    if ((cols * es) % 16 == 0 && (cols * os) % 16 == 0 && cols * es > max_bytes) return false;
     if (((uintptr_t)x | (uintptr_t)y) % 16) return false;
     if (dilation == 2 && (cols & 1)) return false;                             // I/Q pairs must not straddle rows
-    if (cols < 8LL * (n_taps - 1) * dilation) return false;                    // mostly edges: not worth two launches
-    return !getenv("FIRGPU_FORCE_GENERIC") && !getenv("FIRGPU_NO_FLATTEN");
+    (void)n_taps;                                                              // (the launcher checks cols against the chunk window)
+    return true;
 }
 int out_size_ideal(int out_dtype) { return out_dtype == FIRGPU_F64 ? 8 : out_dtype == FIRGPU_F32 ? 4 : 0; }
 
@@ -604,8 +622,9 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
         Fir1dArgs flat = a;
         flat.rows = 1;
         flat.cols = flat.ld_x = flat.ld_y = rows * cols;
+        flat.period = cols;
         rc = try_launch_fir1d_fixed_staged(flat, hq);
-        if (rc == 1) return launch_fir1d_fixed_edges(a, hq);
+        if (rc == 1) return 0;
         if (rc != 0) return rc;
     }
     // Many short rows (images, short channels): the row-streaming tensor-map
@@ -657,15 +676,13 @@ int firgpu_fir1d_fixed_multi(const void *x, void *y, int in_dtype, int out_dtype
     for (; f + 4 <= n_filters; f += 4) {
         Fir1dArgs a{x, (char *)y + (size_t)f * (size_t)filter_stride_y * os, in_dtype, out_dtype, rows, cols, ld_x, ld_y,
                     n_taps, dilation, frac_bits, acc_bits, 0, 0, (cudaStream_t)stream};
-        if (flatten) {                                // dense rows of odd pitch: one long row, then the row ends
+        if (flatten) {                                // dense rows: one long row with in-kernel row ends
             Fir1dArgs flat = a;
             flat.rows = 1;
             flat.cols = flat.ld_x = flat.ld_y = rows * cols;
+            flat.period = cols;
             rc = try_launch_fir1d_fixed_staged_multi(flat, hq + (size_t)f * n_taps, 4, filter_stride_y);
-            if (rc == 1) {
-                if ((rc = launch_fir1d_fixed_edges(a, hq + (size_t)f * n_taps, 4, filter_stride_y))) return rc;
-                continue;
-            }
+            if (rc == 1) continue;
             if (rc != 0) return rc;
         }
         rc = try_launch_fir1d_fixed_staged_multi(a, hq + (size_t)f * n_taps, 4, filter_stride_y);
@@ -731,7 +748,7 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     const bool convert = out_dtype == FIRGPU_U8 && convert_first(in_dtype, n_img * height * width);
     const bool repitch = !convert && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16) &&
                          (in_dtype == out_dtype || (in_dtype == FIRGPU_I16 && out_dtype == FIRGPU_U8)) &&
-                         n_img * height * width >= 4096 && !getenv("FIRGPU_FORCE_GENERIC") &&
+                         n_img * height * width >= 4096 && !force_generic() &&
                          ((uintptr_t)x % 16 != 0 || (ld_x * es_in) % 16 != 0 || (n_img > 1 && (img_stride_x * es_in) % 16 != 0) ||
                           (in_dtype == FIRGPU_U8 && (width & 1)));
     if (windows_ok && (convert || repitch)) {
@@ -939,20 +956,136 @@ int firgpu_fir1d_compare_host(const void *x, int in_dtype, int64_t rows, int64_t
         tl_path = FIRGPU_PATH_EMPTY;
         return 0;
     }
+    // Row pieces travel H2D on the slot streams while earlier pieces are being reduced; every piece adds into one
+    // device accumulator (the kernels publish with atomics), read back once at the end.
     DeviceGuard guard;
     if ((rc = guard.enter(device))) return rc;
+    int dev = 0;
+    FIRGPU_CUDA(cudaGetDevice(&dev));
+    HostCtx *c = ctx_for(dev);
+    std::lock_guard<std::mutex> lock(c->mu);
     const int es = dtype_size(in_dtype);
-    const size_t pitch = (size_t)round_up(cols * es, 16);
-    void *d_x = nullptr;
-    FIRGPU_CUDA(cudaMalloc(&d_x, pitch * (size_t)rows));
-    cudaError_t e = cudaMemcpy2D(d_x, pitch, x, (size_t)ld_x * es, (size_t)cols * es, (size_t)rows, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(d_x);
-        return check_cuda(e, "cudaMemcpy2D");
+    const int64_t pitch = round_up(cols * es, 16);
+    int64_t per = std::max<int64_t>(1, (int64_t)(chunk_target() / (size_t)pitch));
+    if (rows >= 2 * kSlots && per > (rows + 2 * kSlots - 1) / (2 * kSlots) && pitch * rows > (4 << 20))
+        per = (rows + 2 * kSlots - 1) / (2 * kSlots);
+    per = std::min(per, rows);
+    const bool x_pinned = is_pinned(x);
+    if ((rc = ctx_reserve(c, (size_t)(pitch * per + 256), 16, !x_pinned, false))) return rc;
+    SlotDrain drain{c};
+    double *d_sums = nullptr;
+    if ((rc = scratch_alloc((void **)&d_sums, 8 * sizeof(double), c->stream[0]))) return rc;
+    FIRGPU_CUDA(cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), c->stream[0]));
+    FIRGPU_CUDA(cudaStreamSynchronize(c->stream[0]));
+    bool busy[kSlots] = {};
+    int64_t k = 0;
+    for (int64_t r0 = 0; r0 < rows && !rc; r0 += per, ++k) {
+        const int s = (int)(k % kSlots);
+        const int64_t nr = std::min(per, rows - r0);
+        if (busy[s]) FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
+        const char *src = (const char *)x + r0 * ld_x * es;
+        size_t spitch = (size_t)ld_x * es;
+        if (!x_pinned) {
+            copy_rows_host(c->p_in[s], (size_t)cols * es, src, spitch, (size_t)cols * es, (size_t)nr);
+            src = (const char *)c->p_in[s];
+            spitch = (size_t)cols * es;
+        }
+        rc = copy_rows_async(c->d_in[s], (size_t)pitch, src, spitch, (size_t)cols * es, (size_t)nr, cudaMemcpyHostToDevice, c->stream[s]);
+        if (!rc)
+            rc = launch_fir1d_compare_into(c->d_in[s], in_dtype, nr, cols, pitch / es, hq, h, n_taps, frac_bits, acc_bits, d_sums, c->stream[s]);
+        busy[s] = true;
     }
-    rc = launch_fir1d_compare(d_x, in_dtype, rows, cols, (int64_t)(pitch / es), hq, h, n_taps, frac_bits, acc_bits, metrics, 0);
-    cudaFree(d_x);
-    return rc;
+    double host[8] = {};
+    if (!rc) {
+        for (int s = 0; s < kSlots; ++s)
+            if (busy[s]) FIRGPU_CUDA(cudaStreamSynchronize(c->stream[s]));
+        FIRGPU_CUDA(cudaMemcpyAsync(host, d_sums, sizeof(host), cudaMemcpyDeviceToHost, c->stream[0]));
+    }
+    cudaFreeAsync(d_sums, c->stream[0]);
+    FIRGPU_CUDA(cudaStreamSynchronize(c->stream[0]));
+    if (rc) return rc;
+    compare_unpack(host, metrics);
+    return 0;
+}
+
+// ---- recorded launch sequences (CUDA graphs) ----------------------------------------------------------------------
+// Between firgpu_record_begin and firgpu_record_end the device entry points called on `stream` from this thread are
+// captured instead of executed; the resulting graph replays the whole sequence with one submission.  This is the
+// batch entry point: the reference pipeline's 7 images x 8 tap sets, or the steps of a streaming loop, become one
+// host call (a few microseconds) instead of one per launch.
+struct firgpu_graph_s {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int device = 0;
+    size_t nodes = 0;
+};
+
+int firgpu_record_begin(void *stream)
+{
+    if (!stream) return set_error(FIRGPU_E_NULL, "firgpu_record_begin: a recorded sequence needs an explicit (non-default) stream");
+    FIRGPU_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+
+int firgpu_record_end(void *stream, firgpu_graph_t *out)
+{
+    if (!stream || !out) return set_error(FIRGPU_E_NULL, "firgpu_record_end: NULL");
+    cudaGraph_t graph = nullptr;
+    FIRGPU_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+    firgpu_graph_s *g = new firgpu_graph_s();
+    g->graph = graph;
+    cudaGetDevice(&g->device);
+    size_t n_nodes = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess && n_nodes) {     // kernels only: that is what a replay launches
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
+        for (size_t i = 0; i < n_nodes; ++i) {
+            cudaGraphNodeType t;
+            if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++g->nodes;
+        }
+    }
+    cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        delete g;
+        return check_cuda(e, "cudaGraphInstantiate");
+    }
+    *out = g;
+    return 0;
+}
+
+int firgpu_record_abort(void *stream)
+{
+    if (!stream) return 0;
+    cudaGraph_t graph = nullptr;
+    cudaStreamEndCapture((cudaStream_t)stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return 0;
+}
+
+int firgpu_graph_launch(firgpu_graph_t g, void *stream)
+{
+    if (!g || !g->exec) return set_error(FIRGPU_E_NULL, "firgpu_graph_launch: NULL graph");
+    FIRGPU_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    tl_launches += (int64_t)g->nodes;
+    return 0;
+}
+
+int firgpu_graph_nodes(firgpu_graph_t g, int64_t *nodes)
+{
+    if (!g || !nodes) return set_error(FIRGPU_E_NULL, "firgpu_graph_nodes: NULL");
+    *nodes = (int64_t)g->nodes;
+    return 0;
+}
+
+int firgpu_graph_destroy(firgpu_graph_t g)
+{
+    if (!g) return 0;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
 }
 
 // ---- extended entry points: alignment, clamp / saturation bounds, raw samples ----
@@ -1073,6 +1206,91 @@ int firgpu_fir1d_ideal_ex_host(const void *x, void *y, int in_dtype, int out_dty
                            return firgpu_fir1d_ideal_ex(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, h, n_taps, dilation,
                                                         before, after, centre, in_lo, in_hi, raw, (void *)s);
                        });
+}
+
+// ---- one host array, several devices --------------------------------------------------------------------------
+// A single ctypes caller with one big NumPy array gets the whole box: the problem is partitioned like firgpu/shard.py
+// does it for one process per GPU (rows split evenly; a single long row cut into contiguous segments whose taps' reach
+// is read from the neighbouring host samples, cuts on 16384-scalar boundaries so I/Q pairs stay whole) and every
+// device runs its own H2D -> kernel -> D2H pipeline on a host thread of its own.  No device talks to another.
+int firgpu_fir1d_fixed_host_multi(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                                  int64_t ld_y, const int32_t *hq, int n_taps, int dilation, int frac_bits, int acc_bits,
+                                  const int *devices, int n_devices)
+{
+    int rc = check_1d("firgpu_fir1d_fixed_host_multi", x, y, in_dtype, rows, cols, ld_x, ld_y, hq, n_taps, dilation, 0, 0);
+    if (rc) return rc;
+    if ((rc = check_bits("firgpu_fir1d_fixed_host_multi", frac_bits, acc_bits))) return rc;
+    const int os = out_size_fixed(out_dtype), es = dtype_size(in_dtype);
+    if (!os) return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_fixed_host_multi: out_dtype must be U8 or I16, got %d", out_dtype);
+    if (!devices || n_devices < 1 || n_devices > 64) return set_error(FIRGPU_E_SHAPE, "firgpu_fir1d_fixed_host_multi: n_devices=%d", n_devices);
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    struct Share {
+        int device;
+        int64_t r0, nr, c0, nc;
+        int rc = 0, path = FIRGPU_PATH_NONE;
+        int64_t launches = 0;
+        char error[512] = "";
+    };
+    std::vector<Share> shares;
+    const int64_t centre = n_taps / 2, reach_before = (n_taps - 1 - centre) * (int64_t)dilation, reach_after = centre * (int64_t)dilation;
+    if (rows >= 2) {
+        const int parts = (int)std::min<int64_t>(n_devices, rows);
+        for (int d = 0; d < parts; ++d) {
+            const int64_t r0 = rows * d / parts, r1 = rows * (d + 1) / parts;
+            shares.push_back({devices[d], r0, r1 - r0, 0, cols});
+        }
+    } else {
+        const int64_t unit = 16384, units = (cols + unit - 1) / unit;
+        const int parts = (int)std::min<int64_t>(n_devices, units);
+        for (int d = 0; d < parts; ++d) {
+            const int64_t c0 = std::min(cols, units * d / parts * unit), c1 = std::min(cols, units * (d + 1) / parts * unit);
+            if (c1 > c0) shares.push_back({devices[d], 0, 1, c0, c1 - c0});
+        }
+    }
+    auto work = [&](Share &sh) {
+        const char *xs = (const char *)x + (sh.r0 * ld_x + sh.c0) * es;
+        char *ys = (char *)y + (sh.r0 * ld_y + sh.c0) * os;
+        const int64_t before0 = tl_launches;
+        sh.rc = pipeline_1d(xs, ys, es, os, sh.nr, sh.nc, ld_x, ld_y, reach_before, reach_after, sh.device,
+                            [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before, int64_t after,
+                                cudaStream_t s) {
+                                return firgpu_fir1d_fixed(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, hq, n_taps, dilation, frac_bits,
+                                                          acc_bits, before, after, (void *)s);
+                            },
+                            1, 0, rows == 1 ? sh.c0 : 0, rows == 1 ? cols - sh.c0 - sh.nc : 0);
+        sh.path = tl_path;
+        sh.launches = tl_launches - before0;
+        if (sh.rc) snprintf(sh.error, sizeof(sh.error), "%s", tl_error);
+    };
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < shares.size(); ++i) pool.emplace_back(work, std::ref(shares[i]));
+    work(shares[0]);
+    for (auto &t : pool) t.join();
+    for (size_t i = 0; i < shares.size(); ++i) {
+        if (i) tl_launches += shares[i].launches;           // (share 0 ran on this thread and counted itself)
+        if (shares[i].path == FIRGPU_PATH_GENERIC || tl_path == FIRGPU_PATH_NONE) tl_path = shares[i].path;
+        if (shares[i].rc && !rc) {
+            rc = shares[i].rc;
+            snprintf(tl_error, sizeof(tl_error), "device %d: %s", shares[i].device, shares[i].error);
+        }
+    }
+    return rc;
+}
+
+int firgpu_get_device(int *device)
+{
+    if (!device) return set_error(FIRGPU_E_NULL, "firgpu_get_device: NULL");
+    FIRGPU_CUDA(cudaGetDevice(device));
+    return 0;
+}
+
+int firgpu_set_device(int device)
+{
+    FIRGPU_CUDA(cudaSetDevice(device));
+    return 0;
 }
 
 int firgpu_pinned_alloc(void **ptr, size_t bytes)

@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/firgpu.h"
@@ -30,6 +31,17 @@ struct InlineTapsF64 {
 int set_error(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 void note_launch(int path);
+
+// FIRGPU_FORCE_GENERIC=1 routes every call to the one-thread-per-output kernels (tests of the seams between kernel
+// families); read once per process.
+inline bool force_generic()
+{
+    static const bool on = [] {
+        const char *e = getenv("FIRGPU_FORCE_GENERIC");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
 
 #define FIRGPU_CUDA(call)                                                  \
     do {                                                                   \
@@ -135,6 +147,8 @@ struct Fir1dArgs {
     int in_lo = 0, in_hi = 255;      // sample clamp range
     int out_lo = 0, out_hi = 255;    // output saturation range
     int raw = 0;                     // ideal model only: use samples as they are (no round / clamp)
+    int64_t period = 0;              // staged kernel only: this one row is really rows of `period` scalars, each zero-padded
+                                     // on its own (a dense row batch filtered in one flattened pass)
     bool is_reference_model() const
     {
         return (centre < 0 || centre == n_taps / 2) && in_lo == 0 && in_hi == 255 && out_lo == 0 && out_hi == 255 && !raw;
@@ -155,8 +169,6 @@ struct Fir2dArgs {
 // fir1d_generic.cu
 int launch_fir1d_fixed_generic(const Fir1dArgs &a, const int32_t *hq_host);
 int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host);
-// rewrites the outputs within reach of a row end (after a flattened pass over a dense row batch)
-int launch_fir1d_fixed_edges(const Fir1dArgs &a, const int32_t *hq_host, int n_filters = 1, int64_t filter_stride_y = 0);
 // fir1d_ideal_fast.cu — 1 = served, 0 = not eligible
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
@@ -175,6 +187,10 @@ int launch_prep_u8(const void *x, int in_dtype, uint8_t *y, int64_t rows, int64_
 // fir1d_compare.cu
 int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
                          const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s);
+// accumulating form (d_sums: 8 zeroed doubles on the device) + unpacking of the accumulator read back to the host
+int launch_fir1d_compare_into(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
+                              const double *h_host, int n_taps, int frac_bits, int acc_bits, double *d_sums, cudaStream_t s);
+void compare_unpack(const double (&host)[8], double *out);
 // fir2d.cu
 int launch_fir2d_fixed_generic(const Fir2dArgs &a, const int32_t *hq_host);
 int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);

@@ -14,7 +14,10 @@ constexpr int kFastPlanMaxTaps = 65;
 struct FastPlan {
     bool ok = false;
     bool hi16 = false;                       // taps pre-scaled so that the shift is exactly 16 bits
+    bool wrap = false;                       // live acc_bits wrap evaluated in the post stage (plan_wrap)
     int shift = 0, bias = 0;
+    int wrap_sh = 0;                         // wrap: 32 - acc_bits
+    uint32_t post_bias = 0, frac_mask = 0;   // wrap: 2^(frac-1), 2^frac - 1
     int32_t taps[kFastPlanMaxTaps] = {0};    // possibly pre-scaled
 };
 
@@ -54,6 +57,34 @@ inline FastPlan plan_fast(const int32_t *hq, int n_taps, int frac_bits, int acc_
     f.hi16 = false;
     f.shift = frac_bits;
     f.bias = (int)bias;
+    for (int k = 0; k < n_taps; ++k) f.taps[k] = hq[k];
+    return f;
+}
+
+// Wrap plan: int32 arithmetic is exact modulo 2^32, so for acc_bits <= 32 the low acc_bits bits of the int32 sum ARE
+// the reference's wrapped accumulator whatever the taps and however large the true sum (fir_1d_fixed_ref.py:110-115);
+// the post stage sign-extends them, adds the bias without re-wrapping (:118) and floor-shifts (:121).  The sum starts
+// at 0, not at the bias.  tap_limit as in plan_fast (dp2a operands must fit int16; IMAD takes any int32).
+inline FastPlan plan_wrap(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int tap_limit)
+{
+    FastPlan f;
+    if (n_taps < 1 || n_taps > kFastPlanMaxTaps || frac_bits < 1 || frac_bits > 31 || acc_bits < 1) return f;
+    long long sum_abs = 0;
+    for (int k = 0; k < n_taps; ++k) {
+        if (hq[k] > tap_limit || hq[k] < -(long long)tap_limit - 1) return f;
+        sum_abs += hq[k] < 0 ? -(long long)hq[k] : (long long)hq[k];
+    }
+    if (acc_bits > 32) {                     // a wider accumulator never wraps a sum that fits int32: same as acc_bits = 32
+        if (255LL * sum_abs > 0x7fffffffLL) return f;
+        acc_bits = 32;
+    }
+    f.ok = true;
+    f.wrap = true;
+    f.shift = frac_bits;
+    f.bias = 0;
+    f.wrap_sh = 32 - acc_bits;
+    f.post_bias = 1u << (frac_bits - 1);
+    f.frac_mask = (1u << frac_bits) - 1u;
     for (int k = 0; k < n_taps; ++k) f.taps[k] = hq[k];
     return f;
 }

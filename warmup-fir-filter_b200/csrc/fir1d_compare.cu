@@ -260,10 +260,10 @@ int run_fast_taps(int n_taps, const void *x, int64_t rows, int64_t cols, int64_t
 
 }  // namespace
 
-// x: DEVICE pointer.  out[7] (HOST): the seven reductions listed at the top.
-// Synchronises the stream before returning.
-int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
-                         const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s)
+// x: DEVICE pointer.  d_sums: DEVICE accumulator of 8 doubles (4 float64 sums / max + 3 uint64 counters + pad),
+// zeroed by the caller; the kernels ADD to it, so several pieces of one case may be accumulated (on any streams).
+int launch_fir1d_compare_into(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
+                              const double *h_host, int n_taps, int frac_bits, int acc_bits, double *d_sums, cudaStream_t s)
 {
     if (n_taps > kInlineTaps) return set_error(FIRGPU_E_TAPS, "firgpu_fir1d_compare: n_taps=%d exceeds %d", n_taps, kInlineTaps);
     InlineTaps hq{};
@@ -272,35 +272,27 @@ int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols
         hq.v[k] = hq_host[k];
         h.v[k] = h_host[k];
     }
-    double *d_sums = nullptr;
-    if (int rc0 = scratch_alloc((void **)&d_sums, 8 * sizeof(double), s)) return rc0;
-    FIRGPU_CUDA(cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), s));
     unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(d_sums + 4);
-    int rc;
     // int32 shortcut: the wrap is provably the identity and acc + bias fits int32 (same proof as the fast filter kernels)
     const FastPlan plan = n_taps <= 9 ? plan_fast(hq_host, n_taps, frac_bits, acc_bits, 0x7fffffff, false) : FastPlan{};
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (plan.ok && !(force && force[0] == '1') && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16)) {
+    if (plan.ok && !force_generic() && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16)) {
         const int bias = 1 << (frac_bits - 1);
-        rc = in_dtype == FIRGPU_U8 ? run_fast_taps<uint8_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s)
-                                   : run_fast_taps<int16_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
-    } else
+        return in_dtype == FIRGPU_U8 ? run_fast_taps<uint8_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s)
+                                     : run_fast_taps<int16_t>(n_taps, x, rows, cols, ld_x, hq, h, frac_bits, bias, d_sums, d_counts, s);
+    }
     switch (in_dtype) {
-    case FIRGPU_U8: rc = run<uint8_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
-    case FIRGPU_I16: rc = run<int16_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
-    case FIRGPU_I32: rc = run<int32_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
-    case FIRGPU_F32: rc = run<float>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
-    case FIRGPU_F64: rc = run<double>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s); break;
-    default: rc = set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_compare: unsupported in_dtype %d", in_dtype);
+    case FIRGPU_U8: return run<uint8_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s);
+    case FIRGPU_I16: return run<int16_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s);
+    case FIRGPU_I32: return run<int32_t>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s);
+    case FIRGPU_F32: return run<float>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s);
+    case FIRGPU_F64: return run<double>(x, rows, cols, ld_x, hq, h, n_taps, frac_bits, acc_bits, d_sums, d_counts, s);
+    default: return set_error(FIRGPU_E_DTYPE, "firgpu_fir1d_compare: unsupported in_dtype %d", in_dtype);
     }
-    if (rc) {
-        cudaFreeAsync(d_sums, s);
-        return rc;
-    }
-    double host[8];
-    FIRGPU_CUDA(cudaMemcpyAsync(host, d_sums, sizeof(host), cudaMemcpyDeviceToHost, s));
-    FIRGPU_CUDA(cudaFreeAsync(d_sums, s));
-    FIRGPU_CUDA(cudaStreamSynchronize(s));
+}
+
+// The accumulator as read back from the device -> the seven reductions of firgpu_fir1d_compare.
+void compare_unpack(const double (&host)[8], double *out)
+{
     unsigned long long cnt[3];
     memcpy(cnt, &host[4], sizeof(cnt));
     out[0] = host[0];
@@ -310,6 +302,26 @@ int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols
     out[4] = (double)cnt[0];
     out[5] = (double)cnt[1];
     out[6] = (double)cnt[2];
+}
+
+// x: DEVICE pointer.  out[7] (HOST): the seven reductions listed at the top.
+// Synchronises the stream before returning.
+int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
+                         const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s)
+{
+    double *d_sums = nullptr;
+    if (int rc0 = scratch_alloc((void **)&d_sums, 8 * sizeof(double), s)) return rc0;
+    FIRGPU_CUDA(cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), s));
+    int rc = launch_fir1d_compare_into(x, in_dtype, rows, cols, ld_x, hq_host, h_host, n_taps, frac_bits, acc_bits, d_sums, s);
+    if (rc) {
+        cudaFreeAsync(d_sums, s);
+        return rc;
+    }
+    double host[8];
+    FIRGPU_CUDA(cudaMemcpyAsync(host, d_sums, sizeof(host), cudaMemcpyDeviceToHost, s));
+    FIRGPU_CUDA(cudaFreeAsync(d_sums, s));
+    FIRGPU_CUDA(cudaStreamSynchronize(s));
+    compare_unpack(host, out);
     return 0;
 }
 

@@ -75,64 +75,6 @@ fir1d_ideal_kernel(const InT *__restrict__ x, OutT *__restrict__ y,
     }
 }
 
-// Row-end outputs only: the first `edge_left` and the last `edge_right` columns of every row, one thread each.
-// Used after a pass that filtered a dense row batch as one long row (api.cu, "flattened pass"): only outputs whose
-// window crosses a row end differ from the per-row zero padding, and this kernel rewrites exactly those.
-template <typename InT, typename OutT>
-__global__ void __launch_bounds__(kBlock)
-fir1d_fixed_edges_kernel(const InT *__restrict__ x, OutT *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
-                         InlineTaps inline_taps, const int32_t *__restrict__ long_taps, int n_taps, int dilation, int frac_bits,
-                         int acc_bits, int centre, int in_lo, int in_hi, int out_lo, int out_hi, int edge_left, int edge_right,
-                         int n_filters, int64_t filter_stride_y)
-{
-    // taps: [n_filters][n_taps]; tap set f writes to y + f * filter_stride_y
-    const int per_row = edge_left + edge_right;
-    const int64_t per_filter = rows * per_row, total = per_filter * n_filters;
-    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < total; t += (int64_t)gridDim.x * kBlock) {
-        const int f = (int)(t / per_filter);
-        const int64_t tf = t - f * per_filter;
-        const int64_t r = tf / per_row;
-        const int e = (int)(tf - r * per_row);
-        const int64_t n = e < edge_left ? e : cols - per_row + e;
-        if (n < 0 || n >= cols || (e >= edge_left && n < edge_left)) continue;      // rows shorter than the two edges: no column twice
-        const InT *xr = x + r * ld_x;
-        long long acc = 0;
-        for (int k = 0; k < n_taps; ++k) {
-            const int64_t src = n - (int64_t)(k - centre) * dilation;
-            if (src >= 0 && src < cols) {
-                const int32_t tap = long_taps ? long_taps[f * n_taps + k] : inline_taps.v[f * n_taps + k];
-                acc += (long long)prep_sample_range(xr[src], in_lo, in_hi) * (long long)tap;
-            }
-        }
-        y[f * filter_stride_y + r * ld_y + n] = (OutT)post_accumulate(acc, frac_bits, acc_bits, out_lo, out_hi);
-    }
-}
-
-template <typename InT, typename OutT>
-int run_edges(const Fir1dArgs &a, const int32_t *hq_host, int edge_left, int edge_right, int n_filters, int64_t filter_stride_y)
-{
-    InlineTaps it{};
-    int32_t *dev_taps = nullptr;
-    const int nt = a.n_taps * n_filters;
-    if (nt <= kInlineTaps) {
-        for (int k = 0; k < nt; ++k) it.v[k] = hq_host[k];
-    } else {
-        int rc = upload_taps(hq_host, nt, a.stream, &dev_taps);
-        if (rc) return rc;
-    }
-    int64_t blocks = (a.rows * (edge_left + edge_right) * n_filters + kBlock - 1) / kBlock;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    if (blocks < 1) blocks = 1;
-    fir1d_fixed_edges_kernel<InT, OutT><<<(unsigned)blocks, kBlock, 0, a.stream>>>(
-        (const InT *)a.x, (OutT *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, it, dev_taps, a.n_taps, a.dilation, a.frac_bits,
-        a.acc_bits, a.centre < 0 ? a.n_taps / 2 : a.centre, a.in_lo, a.in_hi, a.out_lo, a.out_hi, edge_left, edge_right, n_filters,
-        filter_stride_y);
-    FIRGPU_CUDA(cudaGetLastError());
-    note_launch(FIRGPU_PATH_STAGED);
-    if (dev_taps) FIRGPU_CUDA(cudaFreeAsync(dev_taps, a.stream));
-    return 0;
-}
-
 dim3 grid_for(int64_t rows, int64_t cols)
 {
     int64_t gx = (cols + kBlock - 1) / kBlock;
@@ -221,20 +163,6 @@ int launch_fir1d_fixed_generic(const Fir1dArgs &a, const int32_t *hq_host)
     case FIRGPU_I16: return dispatch_fixed_in<int16_t>(a, hq_host);
     default: return set_error(FIRGPU_E_DTYPE, "fir1d_fixed: out_dtype must be U8 or I16, got %d", a.out_dtype);
     }
-}
-
-// Recompute the outputs within reach of a row end (uint8 / int16 containers, no halos).
-int launch_fir1d_fixed_edges(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y)
-{
-    const int centre = a.centre < 0 ? a.n_taps / 2 : a.centre;
-    const int edge_left = (a.n_taps - 1 - centre) * a.dilation;      // outputs whose window starts before column 0
-    const int edge_right = centre * a.dilation;                      // ... ends after the last column
-    if (edge_left + edge_right == 0) return 0;
-    if (a.in_dtype == FIRGPU_U8 && a.out_dtype == FIRGPU_U8) return run_edges<uint8_t, uint8_t>(a, hq_host, edge_left, edge_right, n_filters, filter_stride_y);
-    if (a.in_dtype == FIRGPU_U8 && a.out_dtype == FIRGPU_I16) return run_edges<uint8_t, int16_t>(a, hq_host, edge_left, edge_right, n_filters, filter_stride_y);
-    if (a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8) return run_edges<int16_t, uint8_t>(a, hq_host, edge_left, edge_right, n_filters, filter_stride_y);
-    if (a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_I16) return run_edges<int16_t, int16_t>(a, hq_host, edge_left, edge_right, n_filters, filter_stride_y);
-    return set_error(FIRGPU_E_DTYPE, "fir1d_fixed edges: containers must be U8 or I16");
 }
 
 int launch_fir1d_ideal(const Fir1dArgs &a, const double *h_host)

@@ -225,8 +225,7 @@ int by_taps(const Fir1dArgs &a, const double *h)
 int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host)
 {
     if ((a.out_dtype != FIRGPU_F64 && a.out_dtype != FIRGPU_F32) || (a.dilation != 1 && a.dilation != 2) || a.n_taps > kMaxFastIdealTaps) return 0;
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (force && force[0] == '1') return 0;
+    if (force_generic()) return 0;
     // the C++ Fir1D model: causal, raw float64 samples, float64 output
     if (a.raw && a.centre == 0 && a.in_dtype == FIRGPU_F64 && a.out_dtype == FIRGPU_F64 && a.dilation == 1) return by_taps<double>(a, h_host);
     if (!a.is_reference_model()) return 0;

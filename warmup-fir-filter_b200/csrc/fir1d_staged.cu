@@ -31,10 +31,8 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     if (a.out_dtype != FIRGPU_U8 && a.out_dtype != FIRGPU_I16) return 0;
     if (a.dilation == 2 && (a.cols & 1)) return 0;           // I/Q pairs must be whole
     if (a.dilation == 2 && ((a.halo_left | a.halo_right) & 1)) return 0;
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (force && force[0] == '1') return 0;
-    int mac = mac_mode();
-    if (mac == 1 && !(a.n_taps == 5 && a.dilation == 1 && n_filters == 1)) mac = 0;
+    if (force_generic()) return 0;
+    const bool force_imad = mac_mode() == 1 && n_filters == 1 && a.n_taps <= kMaxWideTaps;   // FIRGPU_MAC=1: A/B runs of the IMAD datapath
     if (a.n_taps > kMaxFastTaps) return 0;
     // 10..65 taps: zero-pad to the next bucket, keeping the centre tap where it is
     // (output n reads x[n - (k - L/2)], so the padded filter must keep h[L/2] at LB/2).
@@ -44,7 +42,6 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     if (a.n_taps > kMaxWideTaps) {
         const bool long_pair = a.in_dtype == a.out_dtype || (a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8);
         if (n_filters != 1 || a.dilation != 1 || !long_pair) return 0;
-        mac = 0;
         for (int b : kLongBuckets)
             if (!bucket && b >= a.n_taps) bucket = b;
         const int off = bucket / 2 - a.n_taps / 2;
@@ -52,21 +49,34 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
         taps_in = padded;
         n_taps = bucket;
     }
-    const int tap_limit = mac == 0 ? 32767 : 0x7fffffff;
-    // every tap set must be provably exact in int32, and all of them share one post mode
+    // Every tap set must be provably exact in int32, and all of them share one post mode: the 16-bit-shift form
+    // when every set can be pre-scaled, else the plain shift, else — wrap live, taps beyond int16, a shifted
+    // result beyond 16 bits — the WRAP form (dp2a while the taps fit int16, IMAD with full int32 taps otherwise).
     FastPlan plans[kMaxFilters];
-    bool all_hi16 = true;
-    for (int f = 0; f < n_filters; ++f) {
-        plans[f] = plan_fast(taps_in + (size_t)f * n_taps, n_taps, a.frac_bits, a.acc_bits, tap_limit);
-        if (!plans[f].ok) return 0;
-        all_hi16 = all_hi16 && plans[f].hi16;
-    }
-    if (!all_hi16) {
+    int post = POST_HI16, mac = 0;
+    auto plan_all = [&](auto &&make) {
         for (int f = 0; f < n_filters; ++f) {
-            plans[f] = plan_fast(taps_in + (size_t)f * n_taps, n_taps, a.frac_bits, a.acc_bits, tap_limit, false);
-            if (!plans[f].ok) return 0;
+            plans[f] = make(taps_in + (size_t)f * n_taps);
+            if (!plans[f].ok) return false;
+        }
+        return true;
+    };
+    bool ok = !force_imad && plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, a.frac_bits, a.acc_bits, 32767); });
+    if (ok) {
+        for (int f = 0; f < n_filters; ++f)
+            if (!plans[f].hi16) post = POST_SHIFT;
+        if (post == POST_SHIFT)
+            ok = plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, a.frac_bits, a.acc_bits, 32767, false); });
+    }
+    if (!ok) {
+        post = POST_WRAP;
+        ok = !force_imad && plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, a.frac_bits, a.acc_bits, 32767); });
+        if (!ok && !bucket && n_filters == 1) {
+            mac = 1;
+            ok = plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, a.frac_bits, a.acc_bits, 0x7fffffff); });
         }
     }
+    if (!ok) return 0;
     const FastPlan &f0 = plans[0];
 
     const int es = dtype_size(a.in_dtype), os = dtype_size(a.out_dtype);
@@ -83,6 +93,11 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     p.filter_stride_y = filter_stride_y;
     p.shift = f0.shift;
     p.bias = f0.bias;
+    p.wrap_sh = f0.wrap_sh;
+    p.post_bias = f0.post_bias;
+    p.frac_mask = f0.frac_mask;
+    p.period = a.period;
+    p.pdl = 1;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * es) % 16 == 0);
     const int out_vec = (int)((kChunk / es) * os);           // bytes per vector store: 8, 16 or 32
     const int out_align = out_vec > 16 ? 16 : out_vec;
@@ -91,19 +106,19 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
     for (int k = 0; k < n_taps && k < kMaxWideTaps; ++k) p.hq[k] = f0.taps[k];
     if (bucket) {
-        if (a.in_dtype == FIRGPU_U8) return launch_staged_long_u8(p, bucket, f0.hi16, a.stream);
-        return a.out_dtype == FIRGPU_U8 ? launch_staged_long_i16u8(p, bucket, f0.hi16, a.stream)
-                                        : launch_staged_long_i16(p, bucket, f0.hi16, a.stream);
+        if (a.in_dtype == FIRGPU_U8) return launch_staged_long_u8(p, bucket, post, a.stream);
+        return a.out_dtype == FIRGPU_U8 ? launch_staged_long_i16u8(p, bucket, post, a.stream)
+                                        : launch_staged_long_i16(p, bucket, post, a.stream);
     }
-
+    const bool d2 = a.dilation == 2;
     if (a.in_dtype == FIRGPU_U8) {
-        return a.out_dtype == FIRGPU_U8
-                   ? launch_staged_u8_u8(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream)
-                   : launch_staged_u8_i16(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream);
+        if (a.out_dtype == FIRGPU_U8)
+            return d2 ? launch_staged_u8_u8_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_u8_u8_d1(p, a.n_taps, post, mac, a.stream);
+        return d2 ? launch_staged_u8_i16_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_u8_i16_d1(p, a.n_taps, post, mac, a.stream);
     }
-    return a.out_dtype == FIRGPU_U8
-               ? launch_staged_i16_u8(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream)
-               : launch_staged_i16_i16(p, a.n_taps, a.dilation, f0.hi16, mac, a.stream);
+    if (a.out_dtype == FIRGPU_U8)
+        return d2 ? launch_staged_i16_u8_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_i16_u8_d1(p, a.n_taps, post, mac, a.stream);
+    return d2 ? launch_staged_i16_i16_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_i16_i16_d1(p, a.n_taps, post, mac, a.stream);
 }
 
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)
@@ -122,8 +137,7 @@ int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_hos
     if (a.n_taps > kMaxWideTaps || (a.centre >= 0 && a.centre != a.n_taps / 2)) return 0;
     if (a.frac_bits < 1 || a.frac_bits > 30) return 0;
     if (a.in_lo < -32768 || a.in_hi > 32767 || a.out_lo < -32768 || a.out_hi > 32767) return 0;
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (force && force[0] == '1') return 0;
+    if (force_generic()) return 0;
     long long sum_abs = 0;
     for (int k = 0; k < a.n_taps; ++k) sum_abs += hq_host[k] < 0 ? -(long long)hq_host[k] : (long long)hq_host[k];
     const long long m = std::max<long long>(a.in_lo < 0 ? -(long long)a.in_lo : a.in_lo, a.in_hi < 0 ? -(long long)a.in_hi : a.in_hi);
@@ -143,6 +157,7 @@ int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_hos
     p.halo_left = a.halo_left;
     p.halo_right = a.halo_right;
     p.n_filters = 1;
+    p.pdl = 1;
     p.shift = a.frac_bits;
     p.bias = (int)bias;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * 2) % 16 == 0);

@@ -96,7 +96,17 @@ struct StagedParams {
     uint32_t cp_odd[kMaxFilters][kMaxPairs];   // ... on an odd sample
     int32_t hq[kMaxWideTaps];                  // IMAD / wide mode taps
     uint32_t in_lo2, in_hi2, out_lo2, out_hi2; // wide mode: clamp bounds, each duplicated into both 16-bit lanes
+    // WRAP post mode (live acc_bits wrap, fir_1d_fixed_ref.py:110-118): sign-extend the low acc_bits bits of the
+    // int32 sum (wrap_sh = 32 - acc_bits), add the rounding bias WITHOUT re-wrapping, floor-shift, saturate
+    int wrap_sh;
+    uint32_t post_bias, frac_mask;             // 2^(frac-1), 2^frac - 1
+    // flattened batch: the one long row is really rows of `period` scalars, each zero-padded on its own
+    // (gen_fixed_output.py:44-59); 0 = rows are what rows / cols say
+    long long period;
+    int pdl;                                   // launch with programmatic stream serialisation
 };
+
+enum { POST_SHIFT = 0, POST_HI16 = 1, POST_WRAP = 2 };
 
 // ---- PTX wrappers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -303,8 +313,8 @@ __device__ __forceinline__ void mac_stream(const StagedParams &p, const int f, c
 #pragma unroll
             for (int d = -G::lo; d <= G::hi; ++d) {
                 const int s = G::HL4 + i + d;
-                const int v = (int)__byte_perm(B[s >> 2], 0u, 0x4440u | (unsigned)(s & 3));
-                a += p.hq[G::hi - d] * v;
+                const uint32_t v = __byte_perm(B[s >> 2], 0u, 0x4440u | (unsigned)(s & 3));
+                a = (int)((uint32_t)a + (uint32_t)p.hq[G::hi - d] * v);      // modulo 2^32: exact under the acc_bits wrap
             }
         }
         acc[i] = a;
@@ -322,6 +332,24 @@ __device__ __forceinline__ uint32_t post_pair(int a0, int a1, int shift)
         v = __byte_perm((uint32_t)(a0 >> shift), (uint32_t)(a1 >> shift), 0x5410u);
     }
     return __vimin_s16x2_relu(v, 0x00ff00ffu);
+}
+
+// Same for the kernel's POST mode.  WRAP: the int32 sum is exact modulo 2^32 (dp2a and IMAD wrap), so its low
+// acc_bits bits are those of the reference's unbounded sum; (w + bias) >> frac is evaluated as
+// (w >> frac) + (((w mod 2^frac) + bias) >> frac), which cannot overflow for any acc_bits <= 32, frac <= 31.
+template <int POST>
+__device__ __forceinline__ uint32_t post_pair_mode(int a0, int a1, const StagedParams &p)
+{
+    if constexpr (POST == POST_WRAP) {
+        const int w0 = (a0 << p.wrap_sh) >> p.wrap_sh, w1 = (a1 << p.wrap_sh) >> p.wrap_sh;
+        int v0 = (w0 >> p.shift) + (int)((((uint32_t)w0 & p.frac_mask) + p.post_bias) >> p.shift);
+        int v1 = (w1 >> p.shift) + (int)((((uint32_t)w1 & p.frac_mask) + p.post_bias) >> p.shift);
+        v0 = __vimin_s32_relu(v0, 255);
+        v1 = __vimin_s32_relu(v1, 255);
+        return __byte_perm((uint32_t)v0, (uint32_t)v1, 0x5410u);
+    } else {
+        return post_pair<POST == POST_HI16>(a0, a1, p.shift);
+    }
 }
 
 // One thread's chunk, step 1: raw staged words (left halo | 16 bytes | right
@@ -359,25 +387,47 @@ __device__ __forceinline__ void pack_chunk(uint32_t (&raw)[Geo<InT, L, DIL>::NR]
 }
 
 // Step 2: byte-packed streams x tap set f -> output words in memory order.
-template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+// ENDS (flattened batches only): the chunk's window straddles a row boundary; `cut_s` samples of each stream's
+// window belong to the row on the left.  Every row is zero-padded on its own, so the sums are formed twice — once
+// with the right row's samples zeroed, once with the left row's — and each output takes the sum of its own row.
+template <typename InT, typename OutT, int L, int DIL, int POST, int MAC, bool ENDS>
 __device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int f, const uint32_t (&B)[DIL][Geo<InT, L, DIL>::NB],
-                                               uint32_t (&O)[Geo<InT, L, DIL>::SC * sizeof(OutT) / 4])
+                                               const int cut_s, uint32_t (&O)[Geo<InT, L, DIL>::SC * sizeof(OutT) / 4])
 {
     using G = Geo<InT, L, DIL>;
     constexpr int OS = sizeof(OutT);
     constexpr int NOUT = G::SC * OS / 4;
     int acc[DIL][G::S];
+    if constexpr (!ENDS) {
 #pragma unroll
-    for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, f, B[d], acc[d]);
+        for (int d = 0; d < DIL; ++d) mac_stream<G, L, MAC>(p, f, B[d], acc[d]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIL; ++d) {
+            uint32_t BL[G::NB], BR[G::NB];
+#pragma unroll
+            for (int j = 0; j < G::NB; ++j) {
+                const int m = cut_s - 4 * j;                 // leading bytes of this quad that lie in the left row
+                const uint32_t ml = m <= 0 ? 0u : (m >= 4 ? 0xffffffffu : (1u << (8 * m)) - 1u);
+                BL[j] = B[d][j] & ml;
+                BR[j] = B[d][j] & ~ml;
+            }
+            int aL[G::S], aR[G::S];
+            mac_stream<G, L, MAC>(p, f, BL, aL);
+            mac_stream<G, L, MAC>(p, f, BR, aR);
+#pragma unroll
+            for (int i = 0; i < G::S; ++i) acc[d][i] = (G::HL4 + i < cut_s) ? aL[i] : aR[i];
+        }
+    }
 
     // accumulators -> saturated 16-bit lanes in memory order
     uint32_t V[G::SC / 2];
     if constexpr (DIL == 1) {
 #pragma unroll
-        for (int j = 0; j < G::S / 2; ++j) V[j] = post_pair<HI16>(acc[0][2 * j], acc[0][2 * j + 1], p.shift);
+        for (int j = 0; j < G::S / 2; ++j) V[j] = post_pair_mode<POST>(acc[0][2 * j], acc[0][2 * j + 1], p);
     } else {
 #pragma unroll
-        for (int j = 0; j < G::S; ++j) V[j] = post_pair<HI16>(acc[0][j], acc[1][j], p.shift);
+        for (int j = 0; j < G::S; ++j) V[j] = post_pair_mode<POST>(acc[0][j], acc[1][j], p);
     }
     if constexpr (OS == 2) {
 #pragma unroll
@@ -386,6 +436,19 @@ __device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int 
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) O[j] = __byte_perm(V[2 * j], V[2 * j + 1], 0x6420u);
     }
+}
+
+// Flattened batches: how many scalars of the window of the chunk that starts `off` scalars into the tile belong to
+// the row on the left of a row boundary (0 = the window lies inside one row).  `tile_rem` = tile origin modulo the
+// row length.  The host guarantees period >= window, so a window meets at most one boundary.
+template <typename G, int DIL>
+__device__ __forceinline__ int row_cut(uint32_t tile_rem, uint32_t off, uint32_t period)
+{
+    constexpr uint32_t HLS = G::HL4 * DIL, HRS = G::HR4 * DIL;
+    const uint32_t r = (tile_rem + off) % period;          // position of the chunk's first scalar inside its row
+    if (r < HLS) return (int)(HLS - r);                    // the row starts inside the left halo
+    if (r + G::SC + HRS > period) return (int)(period - r + HLS);   // the row ends inside the chunk or its right halo
+    return 0;
 }
 
 // Wide datapath (MAC == 2): int16 samples used at full width — the signed int16
@@ -452,7 +515,7 @@ __device__ __forceinline__ void store_chunk(OutT *dst, const uint32_t (&O)[SC * 
     }
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC, int NF>
+template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF>
 __global__ void __launch_bounds__(C::kThreads, C::kMinBlocks)
 fir1d_staged_kernel(const __grid_constant__ StagedParams p)
 {
@@ -479,6 +542,11 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (this
+    // kernel's input, e.g. the uint8 copy of a float container) are visible from here on.  Our own dependents may
+    // start their prologue now; their griddepcontrol.wait still waits for this grid to finish.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Producer cursor (thread 0 only): the tile whose bulk copy is issued next.
     long long p_row = 0;
@@ -546,46 +614,56 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         if (tid == 0 && i + kStages < n_my) issue();
 
         OutT *ythread = reinterpret_cast<OutT *>(p.y) + t.row * p.ld_y + t.col0 + tid * G::SC;
+        // row boundaries inside a flattened batch: short filters only (the long-filter buckets do not take such batches)
+        constexpr bool kRowEnds = MAC != 2 && L <= kMaxWideTaps;
+        const uint32_t period = kRowEnds ? (uint32_t)p.period : 0u;
+        uint32_t tile_rem = 0;
+        if constexpr (kRowEnds) {
+            if (period) tile_rem = (uint32_t)((unsigned long long)t.col0 % (unsigned long long)period);
+        }
+        // one chunk: pack, then per tap set accumulate + post-process + store
+        auto do_chunk = [&](const int u, const bool vec, const long long room) {
+            if constexpr (MAC == 2) {
+                uint32_t O[NOUT];
+                wide_chunk<L, DIL, POST != 0>(p, raw[u], O);           // POST slot = "clamp ranges are not the full int16 range"
+                store_chunk<OutT, G::SC>(ythread + u * (kThreads * G::SC), O, vec, room);
+            } else {
+                uint32_t B[DIL][G::NB];
+                pack_chunk<InT, L, DIL>(raw[u], B);
+                int cut = 0;
+                bool ends = false;
+                if constexpr (kRowEnds) {
+                    if (period) {
+                        cut = row_cut<G, DIL>(tile_rem, (uint32_t)(tid * G::SC + u * (kThreads * G::SC)), period);
+                        ends = __any_sync(0xffffffffu, cut != 0);                 // warp-uniform: no divergent double work
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    uint32_t O[NOUT];
+                    if constexpr (kRowEnds) {
+                        if (ends) mac_post_chunk<InT, OutT, L, DIL, POST, MAC, true>(p, f, B, cut / DIL, O);
+                        else mac_post_chunk<InT, OutT, L, DIL, POST, MAC, false>(p, f, B, 0, O);
+                    } else {
+                        mac_post_chunk<InT, OutT, L, DIL, POST, MAC, false>(p, f, B, 0, O);
+                    }
+                    if (room > 0) store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O, vec, room);
+                }
+            }
+        };
         if (p.y_vec_ok && t.col0 + TS <= p.cols) {
             // whole tile inside the row: no per-chunk bounds logic at all
 #pragma unroll
-            for (int u = 0; u < kSub; ++u) {
-                if constexpr (MAC == 2) {
-                    uint32_t O[NOUT];
-                    wide_chunk<L, DIL, HI16>(p, raw[u], O);           // HI16 slot = "clamp ranges are not the full int16 range"
-                    store_chunk<OutT, G::SC>(ythread + u * (kThreads * G::SC), O, true, G::SC);
-                } else {
-                    uint32_t B[DIL][G::NB];
-                    pack_chunk<InT, L, DIL>(raw[u], B);
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        uint32_t O[NOUT];
-                        mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
-                        store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O, true, G::SC);
-                    }
-                }
-            }
+            for (int u = 0; u < kSub; ++u) do_chunk(u, true, G::SC);
         } else {
             const long long left = p.cols - t.col0 - tid * G::SC;      // scalars from this thread's first chunk to the row end
 #pragma unroll
             for (int u = 0; u < kSub; ++u) {
                 const long long room = left - u * (kThreads * G::SC);
-                if (room <= 0) continue;
                 if constexpr (MAC == 2) {
-                    uint32_t O[NOUT];
-                    wide_chunk<L, DIL, HI16>(p, raw[u], O);
-                    store_chunk<OutT, G::SC>(ythread + u * (kThreads * G::SC), O, p.y_vec_ok && room >= G::SC, room);
-                } else {
-                    uint32_t B[DIL][G::NB];
-                    pack_chunk<InT, L, DIL>(raw[u], B);
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        uint32_t O[NOUT];
-                        mac_post_chunk<InT, OutT, L, DIL, HI16, MAC>(p, f, B, O);
-                        store_chunk<OutT, G::SC>(ythread + f * p.filter_stride_y + u * (kThreads * G::SC), O,
-                                                 p.y_vec_ok && room >= G::SC, room);
-                    }
+                    if (room <= 0) continue;
                 }
+                do_chunk(u, p.y_vec_ok && room >= G::SC, room);         // (lanes past the row end compute and store nothing)
             }
         }
         advance_tile(c_row, c_tcol, gridDim.x, tpr);
@@ -593,16 +671,63 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
     }
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, bool HI16, int MAC, int NF = 1>
+// Per-process launch knobs, read once (getenv walks the whole environment; a launch should not).
+struct LaunchEnv {
+    int ctas_per_sm = 0;       // FIRGPU_CTAS_PER_SM: cap on resident CTAs per SM (profiling runs)
+    bool pdl = true;           // FIRGPU_NO_PDL=1 launches without programmatic stream serialisation (A/B runs)
+    LaunchEnv()
+    {
+        if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) ctas_per_sm = atoi(e);
+        if (const char *e = getenv("FIRGPU_NO_PDL")) pdl = !(e[0] == '1');
+    }
+};
+inline const LaunchEnv &launch_env()
+{
+    static const LaunchEnv env;
+    return env;
+}
+// SM count per device, cached (cudaDeviceGetAttribute is a driver round trip).
+inline int sm_count(int dev)
+{
+    static int sms[64] = {0};
+    if (dev >= 0 && dev < 64 && sms[dev]) return sms[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 1;
+    if (dev >= 0 && dev < 64) sms[dev] = n;
+    return n;
+}
+// Launch with (optionally) the programmatic-stream-serialisation attribute: the kernel may become resident while
+// its predecessor in the stream drains; it executes griddepcontrol.wait before it touches global memory.
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl, const Args &...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF = 1>
 int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
 {
-    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, HI16, MAC, NF>;
-    constexpr int kSmem = C::smem_bytes(Geo<InT, L, DIL>::PADB);
+    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, POST, MAC, NF>;
+    using G = Geo<InT, L, DIL>;
+    constexpr int kSmem = C::smem_bytes(G::PADB);
+    // a flattened batch needs every chunk window to meet at most one row boundary
+    if (p_in.period && (MAC == 2 || L > kMaxWideTaps || p_in.period < (long long)(G::HL4 * DIL + G::SC + G::HR4 * DIL) || p_in.period >= (1LL << 31) || p_in.rows != 1))
+        return 0;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
     FIRGPU_CUDA(cudaGetDevice(&dev));
-    int per_sm, sms;
+    int per_sm;
     {
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 64 && ctas_per_sm[dev] == 0) {
@@ -614,116 +739,117 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
         }
         per_sm = dev < 64 ? ctas_per_sm[dev] : 1;
     }
-    if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {      // tuning knob for profiling runs
-        const int forced = atoi(e);
-        if (forced >= 1 && forced < per_sm) per_sm = forced;
-    }
-    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const LaunchEnv &env = launch_env();
+    if (env.ctas_per_sm >= 1 && env.ctas_per_sm < per_sm) per_sm = env.ctas_per_sm;
     StagedParams p = p_in;
     const long long ts = C::kTileBytes / (int)sizeof(InT);
     p.tiles_per_row = (p.cols + ts - 1) / ts;
     if (p.tiles_per_row >= (1LL << 31)) return 0;
     p.total_tiles = p.tiles_per_row * p.rows;
-    long long grid = (long long)sms * per_sm;
+    long long grid = (long long)sm_count(dev) * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, C::kThreads, kSmem, stream>>>(p);
-    FIRGPU_CUDA(cudaGetLastError());
+    FIRGPU_CUDA(launch_pdl(kern, (unsigned)grid, C::kThreads, kSmem, stream, env.pdl && p.pdl, p));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
 }
 
-template <typename InT, typename OutT, int L, int DIL, bool HI16, int MAC>
+template <typename InT, typename OutT, int L, int DIL, int POST, int MAC>
 int launch_one(const StagedParams &p, cudaStream_t stream)
 {
     // four tap sets over one staged input (the generators' coefficient loop):
     // uint8 images, 3 / 5 taps only
     if constexpr (sizeof(InT) == 1 && sizeof(OutT) == 1 && (L == 3 || L == 5) && DIL == 1 && MAC == 0) {
-        if (p.n_filters == kMaxFilters) return launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, HI16, MAC, kMaxFilters>(p, stream);
+        if (p.n_filters == kMaxFilters) return launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, POST, MAC, kMaxFilters>(p, stream);
     }
     if (p.n_filters != 1) return 0;
     using Big = typename TuneFor<InT, OutT>::type;
 #ifndef FIRGPU_K_THREADS
     if (p.cols * (long long)sizeof(InT) < 2LL * Big::kTileBytes)
-        return launch_cfg<SmallRowCfg, InT, OutT, L, DIL, HI16, MAC>(p, stream);
+        return launch_cfg<SmallRowCfg, InT, OutT, L, DIL, POST, MAC>(p, stream);
 #endif
-    return launch_cfg<Big, InT, OutT, L, DIL, HI16, MAC>(p, stream);
+    return launch_cfg<Big, InT, OutT, L, DIL, POST, MAC>(p, stream);
 }
 
+// post: POST_SHIFT / POST_HI16 / POST_WRAP (wide TU: 0 / 1 = clamp flag).  mac: 0 = dp2a (signed 16-bit taps),
+// 1 = IMAD with full int32 taps — built for the WRAP post mode only, which is exact for any taps.
 template <typename InT, typename OutT, int L, int DIL>
-int launch_modes(const StagedParams &p, bool hi16, int mac, cudaStream_t s)
+int launch_modes(const StagedParams &p, int post, int mac, cudaStream_t s)
 {
 #ifdef FIRGPU_STAGED_WIDE_TU             // fir1d_staged_wide.cu: the wide (signed int16) datapath only
     static_assert(sizeof(InT) == 2 && sizeof(OutT) == 2, "wide datapath is int16 -> int16");
-    (void)mac;                           // "hi16" carries the clamp flag
-    return hi16 ? launch_one<InT, OutT, L, DIL, true, 2>(p, s) : launch_one<InT, OutT, L, DIL, false, 2>(p, s);
+    (void)mac;
+    return post ? launch_one<InT, OutT, L, DIL, 1, 2>(p, s) : launch_one<InT, OutT, L, DIL, 0, 2>(p, s);
 #else
-    if (mac == 0) {
-        return hi16 ? launch_one<InT, OutT, L, DIL, true, 0>(p, s) : launch_one<InT, OutT, L, DIL, false, 0>(p, s);
-    }
-    // The IMAD datapath is kept for the 5-tap headline shapes only (A/B evidence
-    // for the dp2a choice, profiles/); everything else is dp2a.
-    if constexpr (L == 5 && DIL == 1) {
-        return hi16 ? launch_one<InT, OutT, L, DIL, true, 1>(p, s) : launch_one<InT, OutT, L, DIL, false, 1>(p, s);
-    } else {
-        return 0;
+    if (mac == 1) return post == POST_WRAP ? launch_one<InT, OutT, L, DIL, POST_WRAP, 1>(p, s) : 0;
+    switch (post) {
+    case POST_SHIFT: return launch_one<InT, OutT, L, DIL, POST_SHIFT, 0>(p, s);
+    case POST_HI16: return launch_one<InT, OutT, L, DIL, POST_HI16, 0>(p, s);
+    case POST_WRAP: return launch_one<InT, OutT, L, DIL, POST_WRAP, 0>(p, s);
+    default: return 0;
     }
 #endif
 }
 
 template <typename InT, typename OutT, int DIL>
-int launch_taps(const StagedParams &p, int n_taps, bool hi16, int mac, cudaStream_t s)
+int launch_taps(const StagedParams &p, int n_taps, int post, int mac, cudaStream_t s)
 {
     switch (n_taps) {
-    case 1: return launch_modes<InT, OutT, 1, DIL>(p, hi16, mac, s);
-    case 2: return launch_modes<InT, OutT, 2, DIL>(p, hi16, mac, s);
-    case 3: return launch_modes<InT, OutT, 3, DIL>(p, hi16, mac, s);
-    case 4: return launch_modes<InT, OutT, 4, DIL>(p, hi16, mac, s);
-    case 5: return launch_modes<InT, OutT, 5, DIL>(p, hi16, mac, s);
-    case 6: return launch_modes<InT, OutT, 6, DIL>(p, hi16, mac, s);
-    case 7: return launch_modes<InT, OutT, 7, DIL>(p, hi16, mac, s);
-    case 8: return launch_modes<InT, OutT, 8, DIL>(p, hi16, mac, s);
-    case 9: return launch_modes<InT, OutT, 9, DIL>(p, hi16, mac, s);
+    case 1: return launch_modes<InT, OutT, 1, DIL>(p, post, mac, s);
+    case 2: return launch_modes<InT, OutT, 2, DIL>(p, post, mac, s);
+    case 3: return launch_modes<InT, OutT, 3, DIL>(p, post, mac, s);
+    case 4: return launch_modes<InT, OutT, 4, DIL>(p, post, mac, s);
+    case 5: return launch_modes<InT, OutT, 5, DIL>(p, post, mac, s);
+    case 6: return launch_modes<InT, OutT, 6, DIL>(p, post, mac, s);
+    case 7: return launch_modes<InT, OutT, 7, DIL>(p, post, mac, s);
+    case 8: return launch_modes<InT, OutT, 8, DIL>(p, post, mac, s);
+    case 9: return launch_modes<InT, OutT, 9, DIL>(p, post, mac, s);
     default: return 0;
     }
 }
-
-template <typename InT, typename OutT>
-int launch_dil(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s)
-{
-    if (dilation == 1) return launch_taps<InT, OutT, 1>(p, n_taps, hi16, mac, s);
-    if (dilation == 2) return launch_taps<InT, OutT, 2>(p, n_taps, hi16, mac, s);
-    return 0;
-}
-
 
 // Long filters (10..65 taps): the same kernel, instantiated for a few tap-count
 // buckets; the host zero-pads the taps to the bucket (keeping the centre) —
 // zero taps cost dp2a slots but no accuracy.  8 KiB tiles, two CTAs per SM.
 using LongTapCfg = Cfg<256, 2, 2, 1, 2>;
 constexpr int kLongBuckets[] = {13, 17, 25, 33, 49, 65};
-template <typename T, typename OutT = T>
-int launch_long(const StagedParams &p, int bucket, bool hi16, cudaStream_t s)
+template <typename T, typename OutT, int LB>
+int launch_long_bucket(const StagedParams &p, int post, cudaStream_t s)
 {
-    switch (bucket) {
-    case 13: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 13, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 13, 1, false, 0>(p, s);
-    case 17: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 17, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 17, 1, false, 0>(p, s);
-    case 25: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 25, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 25, 1, false, 0>(p, s);
-    case 33: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 33, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 33, 1, false, 0>(p, s);
-    case 49: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 49, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 49, 1, false, 0>(p, s);
-    case 65: return hi16 ? launch_cfg<LongTapCfg, T, OutT, 65, 1, true, 0>(p, s) : launch_cfg<LongTapCfg, T, OutT, 65, 1, false, 0>(p, s);
+    switch (post) {
+    case POST_SHIFT: return launch_cfg<LongTapCfg, T, OutT, LB, 1, POST_SHIFT, 0>(p, s);
+    case POST_HI16: return launch_cfg<LongTapCfg, T, OutT, LB, 1, POST_HI16, 0>(p, s);
+    case POST_WRAP: return launch_cfg<LongTapCfg, T, OutT, LB, 1, POST_WRAP, 0>(p, s);
     default: return 0;
     }
 }
-int launch_staged_long_u8(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
-int launch_staged_long_i16(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);
-int launch_staged_long_i16u8(const StagedParams &p, int bucket, bool hi16, cudaStream_t s);   // int16 samples in, uint8 out
+template <typename T, typename OutT = T>
+int launch_long(const StagedParams &p, int bucket, int post, cudaStream_t s)
+{
+    switch (bucket) {
+    case 13: return launch_long_bucket<T, OutT, 13>(p, post, s);
+    case 17: return launch_long_bucket<T, OutT, 17>(p, post, s);
+    case 25: return launch_long_bucket<T, OutT, 25>(p, post, s);
+    case 33: return launch_long_bucket<T, OutT, 33>(p, post, s);
+    case 49: return launch_long_bucket<T, OutT, 49>(p, post, s);
+    case 65: return launch_long_bucket<T, OutT, 65>(p, post, s);
+    default: return 0;
+    }
+}
+int launch_staged_long_u8(const StagedParams &p, int bucket, int post, cudaStream_t s);
+int launch_staged_long_i16(const StagedParams &p, int bucket, int post, cudaStream_t s);
+int launch_staged_long_i16u8(const StagedParams &p, int bucket, int post, cudaStream_t s);   // int16 samples in, uint8 out
 
-// One translation unit per (input, output) container pair instantiates these
-// (fir1d_staged_inst.cu compiled four times), which keeps the build parallel.
-int launch_staged_u8_u8(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
-int launch_staged_u8_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
-int launch_staged_i16_u8(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
-int launch_staged_i16_i16(const StagedParams &p, int n_taps, int dilation, bool hi16, int mac, cudaStream_t s);
+// One translation unit per (input, output, dilation) combination instantiates these
+// (fir1d_staged_inst.cu compiled eight times), which keeps the build parallel.
+#define FIRGPU_DECLARE_STAGED(name) int name(const StagedParams &p, int n_taps, int post, int mac, cudaStream_t s)
+FIRGPU_DECLARE_STAGED(launch_staged_u8_u8_d1);
+FIRGPU_DECLARE_STAGED(launch_staged_u8_u8_d2);
+FIRGPU_DECLARE_STAGED(launch_staged_u8_i16_d1);
+FIRGPU_DECLARE_STAGED(launch_staged_u8_i16_d2);
+FIRGPU_DECLARE_STAGED(launch_staged_i16_u8_d1);
+FIRGPU_DECLARE_STAGED(launch_staged_i16_u8_d2);
+FIRGPU_DECLARE_STAGED(launch_staged_i16_i16_d1);
+FIRGPU_DECLARE_STAGED(launch_staged_i16_i16_d2);
 int launch_staged_wide(const StagedParams &p, int n_taps, int dilation, bool clamp, cudaStream_t s);
 
 }  // namespace staged

@@ -9,9 +9,9 @@
 namespace firgpu {
 namespace staged {
 
-int FIRGPU_LONG_NAME(const StagedParams &p, int bucket, bool hi16, cudaStream_t s)
+int FIRGPU_LONG_NAME(const StagedParams &p, int bucket, int post, cudaStream_t s)
 {
-    return launch_long<FIRGPU_LONG_T, FIRGPU_LONG_OUT>(p, bucket, hi16, s);
+    return launch_long<FIRGPU_LONG_T, FIRGPU_LONG_OUT>(p, bucket, post, s);
 }
 
 }  // namespace staged

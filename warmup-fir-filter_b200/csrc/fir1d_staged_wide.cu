@@ -8,7 +8,9 @@ namespace staged {
 
 int launch_staged_wide(const StagedParams &p, int n_taps, int dilation, bool clamp, cudaStream_t s)
 {
-    return launch_dil<int16_t, int16_t>(p, n_taps, dilation, clamp, 2, s);
+    if (dilation == 1) return launch_taps<int16_t, int16_t, 1>(p, n_taps, clamp ? 1 : 0, 2, s);
+    if (dilation == 2) return launch_taps<int16_t, int16_t, 2>(p, n_taps, clamp ? 1 : 0, 2, s);
+    return 0;
 }
 
 }  // namespace staged

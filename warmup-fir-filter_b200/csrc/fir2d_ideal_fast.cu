@@ -179,8 +179,7 @@ int by_window(const Fir2dArgs &a, const double *h)
 // 1 = served, 0 = not eligible (caller uses the generic kernel), else error.
 int try_launch_fir2d_ideal_fast(const Fir2dArgs &a, const double *h_host)
 {
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (force && force[0] == '1') return 0;
+    if (force_generic()) return 0;
     if (a.in_dtype == FIRGPU_U8) {
         if (a.out_dtype == FIRGPU_F64) return by_window<uint8_t, double>(a, h_host);
         if (a.out_dtype == FIRGPU_F32) return by_window<uint8_t, float>(a, h_host);

@@ -75,8 +75,7 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     const bool narrowing = a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8;       // int16 pixels in, uint8 out
     if ((a.in_dtype != a.out_dtype && !narrowing) || (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16)) return 0;
     if (!shape_supported(a.kh, a.kw)) return 0;
-    const char *force = getenv("FIRGPU_FORCE_GENERIC");
-    if (force && force[0] == '1') return 0;
+    if (force_generic()) return 0;
     const int es = dtype_size(a.in_dtype);
     // TMA needs a 16-byte aligned base and 16-byte multiples for every pitch.
     if ((uintptr_t)a.x % 16 != 0 || (a.ld_x * es) % 16 != 0) return 0;

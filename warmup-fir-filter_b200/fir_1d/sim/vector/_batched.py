@@ -17,6 +17,21 @@ import numpy as np
 INPUT_SUFFIX = "_x_u8.npy"
 
 
+def vector_root() -> Path:
+    """The directory that holds ``input/`` and ``output/`` for every pipeline stage.  The reference resolves them
+    next to its own ``fir_1d/sim/vector`` modules (gen_input_vectors.py:15, gen_fixed_output.py:16-17,
+    gen_3tap_compare_report.py:18, restore_images.py:27); in an overlay (``FIR_REFERENCE_ROOT``) the reference's
+    untouched stages still do, so the GPU-backed generators must use the same place or the stages would read and
+    write different trees.  ``FIR_VECTOR_ROOT`` overrides it for all stages (a read-only reference checkout)."""
+    import os
+    if os.environ.get("FIR_VECTOR_ROOT"):
+        return Path(os.environ["FIR_VECTOR_ROOT"]).resolve()
+    ref = os.environ.get("FIR_REFERENCE_ROOT")
+    if ref and (Path(ref) / "fir_1d" / "sim" / "vector").is_dir():
+        return (Path(ref) / "fir_1d" / "sim" / "vector").resolve()
+    return Path(__file__).resolve().parent
+
+
 def list_input_files(input_dir: Path) -> list[Path]:
     found = [p for p in Path(input_dir).glob("*.npy") if p.name.endswith(INPUT_SUFFIX)]
     found.sort(key=lambda p: p.name.lower())

@@ -16,8 +16,8 @@ from fir_1d.sim.vector import _batched
 from fir_1d.sim.vector.h_coeff import h_coeff_3tap_map, h_coeff_5tap_map
 
 THIS_FILE = Path(__file__).resolve()
-DEFAULT_INPUT_DIR = THIS_FILE.parent / "input"
-DEFAULT_OUTPUT_DIR = THIS_FILE.parent / "output"
+DEFAULT_INPUT_DIR = _batched.vector_root() / "input"      # the same tree as the reference's other stages (see vector_root)
+DEFAULT_OUTPUT_DIR = _batched.vector_root() / "output"
 
 _iter_input_npy_files = _batched.list_input_files
 _load_input_image_u8 = _batched.load_image_u8

@@ -43,6 +43,22 @@ SIGNATURES = {
     "firgpu_fir1d_ideal_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci]),
     "firgpu_fir2d_fixed_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, _ci]),
     "firgpu_fir2d_ideal_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _vp, _ci, _ci, _ci]),
+    "firgpu_stream_create_fixed": (_ci, [C.POINTER(_vp), _ci, _ci, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci]),
+    "firgpu_stream_create_ideal": (_ci, [C.POINTER(_vp), _ci, _ci, _vp, _ci, _ci, _ci, _ci, _ci, _ci]),
+    "firgpu_stream_process": (_ci, [_vp, _vp, _vp, _i64, _vp]),
+    "firgpu_stream_process_host": (_ci, [_vp, _vp, _vp, _i64]),
+    "firgpu_stream_reset": (_ci, [_vp, _vp]),
+    "firgpu_stream_history": (_ci, [_vp, C.POINTER(_i64)]),
+    "firgpu_stream_destroy": (_ci, [_vp]),
+    "firgpu_record_begin": (_ci, [_vp]),
+    "firgpu_record_end": (_ci, [_vp, C.POINTER(_vp)]),
+    "firgpu_record_abort": (_ci, [_vp]),
+    "firgpu_graph_launch": (_ci, [_vp, _vp]),
+    "firgpu_graph_nodes": (_ci, [_vp, C.POINTER(_i64)]),
+    "firgpu_graph_destroy": (_ci, [_vp]),
+    "firgpu_get_device": (_ci, [C.POINTER(_ci)]),
+    "firgpu_set_device": (_ci, [_ci]),
+    "firgpu_fir1d_fixed_host_multi": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _ci, _ci, _ci, _ci, C.POINTER(_ci), _ci]),
     "firgpu_pinned_alloc": (_ci, [C.POINTER(_vp), C.c_size_t]),
     "firgpu_pinned_free": (_ci, [_vp]),
     "firgpu_release_cache": (_ci, []),

@@ -185,6 +185,39 @@ def _cuda_imgs(t, what: str):
     return n, hgt, wid, ld, img_stride
 
 
+def _cuda_out(out, x, out_dtype):
+    """The caller's ``out`` (or a fresh tensor) for a device call.  The kernels write through the raw pointer with
+    the element size of ``out_dtype``, so a tensor of another dtype, on the host, or on another GPU must never get
+    that far (it would be overrun, or fault)."""
+    import torch
+    want = _torch_dtype(out_dtype)
+    if out is None:
+        return torch.empty(x.shape, dtype=want, device=x.device)
+    if not (_is_torch(out) and out.is_cuda and out.device == x.device and out.dtype == want):
+        raise ValueError(f"out must be a {want} tensor on {x.device} (got "
+                         f"{getattr(out, 'dtype', type(out).__name__)} on {getattr(out, 'device', 'host')})")
+    return out
+
+
+class _device_scope:
+    """Make ``device`` current for a raw-pointer call (no torch involved)."""
+
+    def __init__(self, device: int):
+        self.device, self.prev = int(device), None
+
+    def __enter__(self):
+        L = _lib.lib()
+        cur = C.c_int(0)
+        _lib.check(L.firgpu_get_device(C.byref(cur)))
+        if cur.value != self.device:
+            _lib.check(L.firgpu_set_device(self.device))
+            self.prev = cur.value
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            _lib.lib().firgpu_set_device(self.prev)
+
+
 def _host_out(out, shape, dtype):
     """The caller's ``out`` (or a fresh array) for a host-buffer call: must be a
     C-contiguous array / CPU tensor of exactly the expected shape and dtype,
@@ -280,16 +313,22 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
     out_code = _OUT_FIXED[np.dtype(out_dtype)]
     if isinstance(x, DeviceArray):
         rows, cols = _rows_cols(x.shape)
-        if out is None:
+        if not isinstance(out, DeviceArray):
             raise ValueError("DeviceArray inputs need an explicit out=DeviceArray")
-        _lib.check(L.firgpu_fir1d_fixed(x.ptr, out.ptr, _NP_CODE[np.dtype(x.dtype)], _OUT_FIXED[np.dtype(out.dtype)],
-                                        rows, cols, cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits,
-                                        halo_left_valid, halo_right_valid, x.stream))
+        if np.dtype(out.dtype) not in _OUT_FIXED or tuple(out.shape) != tuple(x.shape) or out.device != x.device:
+            raise ValueError(f"out must be a uint8 / int16 DeviceArray of shape {tuple(x.shape)} on device {x.device}")
+        args = (x.ptr, out.ptr, _NP_CODE[np.dtype(x.dtype)], _OUT_FIXED[np.dtype(out.dtype)], rows, cols, cols, cols,
+                _taps_ptr(hq), hq.size, dilation, frac_bits, acc_bits, halo_left_valid, halo_right_valid)
+        with _device_scope(x.device):
+            if ex is None:
+                _lib.check(L.firgpu_fir1d_fixed(*args, x.stream))
+            else:
+                _lib.check(L.firgpu_fir1d_fixed_ex(*args, *ex, x.stream))
         return out
     if _is_torch(x) and x.is_cuda:
         import torch
         t, rows, cols, ld = _cuda_rows(x, not (halo_left_valid or halo_right_valid), *((ex[1], ex[2]) if ex else (0, 255)))
-        y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        y = _cuda_out(out, x, out_dtype)
         _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
         if (y_rows, y_cols) != (rows, cols):
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
@@ -348,7 +387,7 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
         if raw and x.dtype not in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64):
             x = x.to(torch.float64)              # raw samples of an exotic dtype: exact in float64, never clamped
         t, rows, cols, ld = _cuda_rows(x, not (halo_left_valid or halo_right_valid), *in_range)
-        y = out if out is not None else torch.empty(x.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        y = _cuda_out(out, x, out_dtype)
         _, y_rows, y_cols, ld_y = _cuda_rows(y, allow_copy=False)
         if (y_rows, y_cols) != (rows, cols):
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
@@ -474,7 +513,7 @@ def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8,
         n, hgt, wid = _imgs(t.shape)
         ld = t.stride(-2) if t.dim() >= 2 else wid
         img_stride = t.stride(-3) if t.dim() >= 3 else hgt * ld
-        y = out if out is not None else torch.empty(t.shape, dtype=_torch_dtype(out_dtype), device=x.device)
+        y = _cuda_out(out, t, out_dtype)
         if not y.is_contiguous() or tuple(y.shape) != tuple(t.shape):
             raise ValueError("out must be a contiguous tensor of the input's shape")
         with _on_device(torch, x.device):
@@ -598,6 +637,187 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
         import torch
         return torch.from_numpy(y)
     return y
+
+
+# ---------------------------------------------------------------------------
+# several devices, one host array
+# ---------------------------------------------------------------------------
+def fir1d_fixed_multi_gpu(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *, devices, dilation: int = 1,
+                          out_dtype=np.uint8, out=None, validate: bool = True):
+    """:func:`fir1d_fixed` on a HOST array, spread over ``devices`` (CUDA ordinals) by one call of
+    ``firgpu_fir1d_fixed_host_multi``: rows split evenly, a single long row cut into segments that read the taps'
+    reach from the neighbouring host samples.  No collective, no device-to-device traffic."""
+    quant.validate_taps(h)
+    a = _np_container(x.numpy() if _is_torch(x) else x)
+    if validate:
+        quant.check_samples_finite(a)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = np.ascontiguousarray(quant.quantize_taps(h, frac_bits, coeff_bits), dtype=np.int32)
+    rows, cols = _rows_cols(a.shape)
+    y = _host_out(out, a.shape, out_dtype)
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    _lib.check(_lib.lib().firgpu_fir1d_fixed_host_multi(a.ctypes.data, y.ctypes.data, _NP_CODE[a.dtype], _OUT_FIXED[np.dtype(out_dtype)],
+                                                       rows, cols, cols, cols, _taps_ptr(hq), hq.size, dilation, frac_bits,
+                                                       acc_bits, devs, len(devices)))
+    return y
+
+
+# ---------------------------------------------------------------------------
+# streaming with the history on the device
+# ---------------------------------------------------------------------------
+class FirStream:
+    """The causal filter ``y[n] = sum_k h[k] x[n - k*dilation]`` over a signal delivered in blocks; the
+    ``(len(h) - 1) * dilation`` most recent samples stay in HBM between calls (``firgpu_stream_*``; the reference's
+    C++ ``Fir1D`` keeps them in ``reg_``, fir_1d/model/cpp/fir_1d_ref.cpp:16-33).
+
+    ``model="fixed"``: the fixed-point model with integer taps ``hq`` (quantise with :mod:`firgpu.quant`);
+    ``model="ideal"``: the floating-point model with real taps.  ``process`` takes a CUDA tensor (device in, device
+    out, stream-ordered on torch's current stream) or a host array (pipelined copies)."""
+
+    def __init__(self, taps, *, model: str = "fixed", in_dtype=np.int16, out_dtype=None, dilation: int = 1, frac_bits: int = 12,
+                 acc_bits: int = 32, in_range=(0, 255), out_range=(0, 255), raw: bool = False, device: int = -1):
+        L = _lib.lib()
+        self._h = C.c_void_p()
+        self.model, self.in_dtype, self.dilation = model, np.dtype(in_dtype), int(dilation)
+        in_code = _NP_CODE[self.in_dtype]
+        if model == "fixed":
+            self.out_dtype = np.dtype(out_dtype or (np.uint8 if (out_range[0] >= 0 and out_range[1] <= 255) else np.int16))
+            self.taps = np.ascontiguousarray(taps, dtype=np.int32).reshape(-1)
+            _lib.check(L.firgpu_stream_create_fixed(C.byref(self._h), in_code, _OUT_FIXED[self.out_dtype], _taps_ptr(self.taps),
+                                                    self.taps.size, self.dilation, frac_bits, acc_bits, int(in_range[0]),
+                                                    int(in_range[1]), int(out_range[0]), int(out_range[1]), device))
+        elif model == "ideal":
+            self.out_dtype = np.dtype(out_dtype or np.float64)
+            self.taps = np.ascontiguousarray([float(v) for v in taps], dtype=np.float64)
+            _lib.check(L.firgpu_stream_create_ideal(C.byref(self._h), in_code, _OUT_IDEAL[self.out_dtype], _taps_ptr(self.taps),
+                                                    self.taps.size, self.dilation, int(in_range[0]), int(in_range[1]),
+                                                    1 if raw else 0, device))
+        else:
+            raise ValueError("model must be 'fixed' or 'ideal'")
+
+    @property
+    def history(self) -> int:
+        n = C.c_int64(0)
+        _lib.check(_lib.lib().firgpu_stream_history(self._h, C.byref(n)))
+        return n.value
+
+    def process(self, x, out=None):
+        """Filter the next block.  CUDA tensor in -> CUDA tensor out (asynchronous); host array in -> host array out."""
+        L = _lib.lib()
+        if _is_torch(x) and x.is_cuda:
+            import torch
+            if x.dim() != 1 or not x.is_contiguous() or x.dtype != _torch_dtype_any(self.in_dtype):
+                raise ValueError(f"a block must be a contiguous 1-D {self.in_dtype} tensor")
+            y = _cuda_out(out, x, self.out_dtype)
+            if tuple(y.shape) != tuple(x.shape) or not y.is_contiguous():
+                raise ValueError("out must be a contiguous tensor of the block's shape")
+            with _on_device(torch, x.device):
+                _lib.check(L.firgpu_stream_process(self._h, x.data_ptr(), y.data_ptr(), x.numel(),
+                                                   torch.cuda.current_stream(x.device).cuda_stream))
+            return y
+        a = np.ascontiguousarray(x.numpy() if _is_torch(x) else x, dtype=self.in_dtype).reshape(-1)
+        y = _host_out(out, a.shape, self.out_dtype)
+        _lib.check(L.firgpu_stream_process_host(self._h, a.ctypes.data, y.ctypes.data, a.size))
+        return y
+
+    def reset(self, stream: int = 0) -> None:
+        _lib.check(_lib.lib().firgpu_stream_reset(self._h, stream))
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            _lib.lib().firgpu_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _torch_dtype_any(np_dtype):
+    import torch
+    return {np.dtype(np.uint8): torch.uint8, np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32,
+            np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(np_dtype)]
+
+
+# ---------------------------------------------------------------------------
+# recorded launch sequences
+# ---------------------------------------------------------------------------
+class record:
+    """Context manager over ``firgpu_record_begin`` / ``firgpu_record_end``: the firgpu device calls issued inside the
+    block on ``stream`` (a raw ``cudaStream_t`` handle, not the NULL stream) by this thread are recorded, not executed;
+    ``replay()`` then submits the whole sequence at once (a CUDA graph).  For callers that manage device memory
+    themselves (``DeviceArray``, or CUDA tensors with every ``out=`` preallocated): nothing inside the block may
+    allocate, and each distinct call must have run once eagerly before.
+
+        with firgpu.record(stream) as rec:
+            firgpu.fir1d_fixed_q(x, hq, 15, 32, out_dtype=np.int16, out=y)
+        rec.replay()
+    """
+
+    def __init__(self, stream: int):
+        self.stream = int(stream)
+        self._g = C.c_void_p()
+        self.kernels = 0
+
+    def __enter__(self):
+        _lib.check(_lib.lib().firgpu_record_begin(self.stream))
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        L = _lib.lib()
+        if exc_type is not None:
+            L.firgpu_record_abort(self.stream)
+            return False
+        _lib.check(L.firgpu_record_end(self.stream, C.byref(self._g)))
+        n = C.c_int64(0)
+        _lib.check(L.firgpu_graph_nodes(self._g, C.byref(n)))
+        self.kernels = n.value
+        return False
+
+    def replay(self, stream: int | None = None) -> None:
+        _lib.check(_lib.lib().firgpu_graph_launch(self._g, self.stream if stream is None else int(stream)))
+
+    def close(self) -> None:
+        if self._g is not None and self._g.value:
+            _lib.lib().firgpu_graph_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Recording:
+    """The same for torch users, with torch's graph-safe allocator: ``fn`` (a callable issuing firgpu device calls
+    on CUDA tensors; it may allocate its outputs) runs once eagerly, once under ``torch.cuda.graph``, and never
+    again — ``replay()`` resubmits what it launched and returns the tensors the recorded pass produced, refreshed
+    from the inputs' current contents.
+
+        rec = firgpu.Recording(lambda: [firgpu.fir1d_fixed_multi(img, taps) for img in images])
+        outs = rec.replay()
+    """
+
+    def __init__(self, fn):
+        import torch
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            fn()                                             # first use configures kernels; not recorded
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+        self.kernels = _lib.launch_count() - before
+
+    def replay(self):
+        self.graph.replay()
+        return self.result
 
 
 # ---------------------------------------------------------------------------

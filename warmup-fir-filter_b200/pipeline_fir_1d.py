@@ -17,7 +17,7 @@ from pathlib import Path
 from time import perf_counter
 from typing import Any
 
-from fir_1d.sim.vector import gen_fixed_output, gen_ideal_output
+from fir_1d.sim.vector import _batched, gen_fixed_output, gen_ideal_output
 
 STAGE_FLAGS = ("skip_input", "skip_ideal", "skip_fixed", "skip_report", "skip_restore")
 
@@ -44,34 +44,42 @@ def run_pipeline(*, tap: str, overwrite_vectors: bool, skip_input: bool, skip_id
                  strict_report: bool, strict_restore: bool, top_k: int) -> dict[str, Any]:
     taps = _selected_taps(tap)
     results: dict[str, Any] = {"selected_taps": taps}
+    # ONE vector tree for all five stages, passed explicitly: the reference's own stages default to directories next
+    # to their source files, the GPU-backed ones must not default to somewhere else (see _batched.vector_root).
+    root = _batched.vector_root()
+    input_dir, output_dir = root / "input", root / "output"
 
     if not skip_input:
         _log_stage("Generate input vectors")
         make_inputs = _reference_stage("gen_input_vectors", "generate_input_vector_jsons")
-        results["input_manifest"] = make_inputs(overwrite=overwrite_vectors)
+        results["input_manifest"] = make_inputs(output_dir=input_dir, overwrite=overwrite_vectors)
 
     if not skip_ideal:
         _log_stage("Generate ideal outputs (GPU)")
         results["ideal_counts"] = {
-            f"ideal_{t}tap": getattr(gen_ideal_output, f"generate_ideal_{t}tap_output_vector")(overwrite=overwrite_vectors)
+            f"ideal_{t}tap": getattr(gen_ideal_output, f"generate_ideal_{t}tap_output_vector")(
+                input_dir=input_dir, output_dir=output_dir, overwrite=overwrite_vectors)
             for t in taps}
 
     if not skip_fixed:
         _log_stage("Generate fixed outputs (GPU)")
         results["fixed_counts"] = {
-            f"fixed_{t}tap": getattr(gen_fixed_output, f"generate_fixed_{t}tap_output_vector")(overwrite=overwrite_vectors)
+            f"fixed_{t}tap": getattr(gen_fixed_output, f"generate_fixed_{t}tap_output_vector")(
+                input_dir=input_dir, output_dir=output_dir, overwrite=overwrite_vectors)
             for t in taps}
 
     if not skip_report:
         _log_stage("Generate compare reports")
         results["report_results"] = {
             f"report_{t}tap": _reference_stage(f"gen_{t}tap_compare_report", f"generate_{t}tap_compare_report")(
-                top_k=top_k, strict=strict_report)
+                ideal_dir=output_dir / f"ideal_{t}tap", fixed_dir=output_dir / f"fixed_{t}tap",
+                report_dir=output_dir / f"report_{t}tap", top_k=top_k, strict=strict_report)
             for t in taps}
 
     if not skip_restore:
         _log_stage("Restore output images")
         summary = _reference_stage("restore_images", "restore_images")(
+            vector_output_dir=output_dir, output_img_dir=root.parent / "output_img",
             kind=restore_kind, tap=tap, ideal_policy=ideal_policy, overwrite=overwrite_images, strict=strict_restore)
         results["restore_summary"] = {k: summary[k] for k in ("num_converted", "num_skipped")}
 
@@ -97,7 +105,7 @@ def main(argv=None) -> None:
     args = _build_argparser().parse_args(argv)
     t0 = perf_counter()
     skipped = sum(int(getattr(args, f)) for f in STAGE_FLAGS)
-    out = Path(gen_fixed_output.DEFAULT_OUTPUT_DIR).resolve()
+    out = (_batched.vector_root() / "output").resolve()
     try:
         summary = run_pipeline(**{k: v for k, v in vars(args).items()})
     except Exception as exc:
