@@ -154,11 +154,7 @@ def test_pipeline_driver_model_stages(tmp_path, monkeypatch):
     inp, out = tmp_path / "input", tmp_path / "output"
     inp.mkdir()
     np.save(inp / "case_000_small_x_u8.npy", SMALL)
-    for mod in (gf, gi):
-        for name in dir(mod):
-            fn = getattr(mod, name)
-            if name.startswith("generate_") and callable(fn):
-                monkeypatch.setattr(mod, name, (lambda f: lambda **kw: f(input_dir=inp, output_dir=out, **kw))(fn))
+    monkeypatch.setenv("FIR_VECTOR_ROOT", str(tmp_path))          # one vector tree for every stage (_batched.vector_root)
     res = pipe.run_pipeline(tap="all", overwrite_vectors=True, skip_input=True, skip_ideal=False, skip_fixed=False,
                             skip_report=True, skip_restore=True, restore_kind="all", ideal_policy="clip",
                             overwrite_images=False, strict_report=False, strict_restore=False, top_k=5)

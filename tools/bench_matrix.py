@@ -28,7 +28,13 @@ LP3 = [0.25, 0.5, 0.25]
 PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 
 
+REPLAY = False      # --replay: time a recorded sequence (firgpu.Recording, a CUDA graph of the same launches) instead of Python calls
+
+
 def timed(fn, reps, warm=3):
+    if REPLAY:
+        rec = firgpu.Recording(fn)
+        fn = rec.replay
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -57,7 +63,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="stream,signed,u8,iq,taps,batched,images,ideal,2d")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--replay", action="store_true", help="submit each case as a recorded sequence (device time without per-call Python)")
     args = ap.parse_args()
+    global REPLAY
+    REPLAY = args.replay
     cases = args.cases.split(",")
     n = 1 << 28
     if "stream" in cases:
@@ -82,6 +91,20 @@ def main():
         s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], LP5, 15, 48, 16, centre=0, in_range=full, out_range=full, out=y[: 1 << 26], validate=False), 5)
         report("signed int16 causal 2^26 5tap (centred 9-tap form, wide datapath)", s, 1 << 26, 4)
         del x, y
+    if "wrap" in cases:
+        # live acc_bits wrap (WRAP post mode) and taps beyond int16 (IMAD datapath) on the staged kernel
+        x = rand_i16(n)
+        y = torch.empty_like(x)
+        hw = [0.9, -0.7, 0.8, 0.3, -0.2]
+        for frac, acc, cb, tag in ((12, 16, 16, "acc_bits 16"), (12, 20, 16, "acc_bits 20"), (12, 24, 16, "acc_bits 24"),
+                                   (28, 32, 32, "coeff_bits 32, frac 28 (IMAD)")):
+            s = timed(lambda: firgpu.fir1d_fixed(x, hw, frac, acc, cb, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^28 i16->i16 5tap wrap-live {tag}", s, n, 4)
+        xu = x.clamp(0, 255).to(torch.uint8)
+        yu = torch.empty_like(xu)
+        s = timed(lambda: firgpu.fir1d_fixed(xu, hw, 12, 16, 16, out=yu, validate=False), args.reps)
+        report("stream 2^28 u8->u8 5tap wrap-live acc_bits 16", s, n, 2)
+        del x, y, xu, yu
     if "u8" in cases:
         x = rand_i16(n).clamp(0, 255).to(torch.uint8)
         y = torch.empty_like(x)
