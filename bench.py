@@ -259,11 +259,12 @@ def device_signal(torch, shape, seed, device):
 
 
 def other_configs(args, torch, dist, rank: int, world: int, device, peak: float) -> dict:
-    """One step = one pass over this rank's shard, submitted as a recorded sequence (firgpu.Recording: the library's
-    batch entry, a CUDA graph of the same launches the public call makes) so that a 20-microsecond kernel is not
-    timed behind 25 microseconds of Python.  Timing: barrier + synchronize, CUDA events on the launching stream,
-    max over ranks.  `consistent` is a self-consistency check between two different kernel paths of the library
-    (parity against the oracle is the job of tests/, which cover these configs at full size)."""
+    """One step = one pass over this rank's shard.  The `reps` timed steps are recorded once (firgpu.Recording: the
+    library's batch entry, a CUDA graph of exactly the launches the public calls make) and submitted together, so
+    that a 20-microsecond kernel is not timed behind 25 microseconds of Python per call.  Timing: barrier +
+    synchronize, CUDA events on the launching stream around the submission, max over ranks.  `consistent` is a
+    self-consistency check between two different kernel paths of the library (parity against the oracle is the job
+    of tests/, which cover these configs at full size)."""
     import firgpu
     from firgpu import _lib, quant, shard
 
@@ -271,22 +272,23 @@ def other_configs(args, torch, dist, rank: int, world: int, device, peak: float)
     out = {}
 
     def timed(step):
-        rec = firgpu.Recording(step)
-        for _ in range(3):
-            rec.replay()
+        def steps():
+            for _ in range(reps):
+                step()
+        rec = firgpu.Recording(steps)          # runs `steps` once eagerly (warm-up), then records it
+        rec.replay()                           # second warm-up pass, as a replay
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(reps):
-            rec.replay()
+        rec.replay()
         b.record()
         torch.cuda.synchronize()
         ms = torch.tensor([a.elapsed_time(b) / reps], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), rec.kernels
+        return float(ms.item()), rec.kernels // reps
 
     def all_ok(flag: bool) -> bool:
         t = torch.tensor([1 if flag else 0], device=device, dtype=torch.int32)

@@ -105,6 +105,18 @@ def main():
         s = timed(lambda: firgpu.fir1d_fixed(xu, hw, 12, 16, 16, out=yu, validate=False), args.reps)
         report("stream 2^28 u8->u8 5tap wrap-live acc_bits 16", s, n, 2)
         del x, y, xu, yu
+    if "small" in cases:
+        # back-to-back small launches (a strong-scaled shard, a streaming block): 16 passes per recorded sequence, so
+        # that programmatic dependent launch between them is visible (compare with FIRGPU_NO_PDL=1)
+        for m in (1 << 20, 1 << 22, 1 << 24, 1 << 25):
+            x = rand_i16(m)
+            y = torch.empty_like(x)
+            s = timed(lambda: [firgpu.fir1d_fixed(x, LP5, 15, 32, 16, out_dtype=np.int16, out=y, validate=False) for _ in range(16)], args.reps)
+            report(f"16 x stream {m} i16->i16 5tap q1.15 back to back (per pass)", s / 16, m, 4)
+            xz = x.view(-1)
+            s = timed(lambda: [firgpu.fir1d_fixed(xz, LP5, 15, 32, 16, dilation=2, out_dtype=np.int16, out=y, validate=False) for _ in range(16)], args.reps)
+            report(f"16 x iq {m} scalars i16 5tap q1.15 back to back (per pass)", s / 16, m, 4)
+            del x, y
     if "u8" in cases:
         x = rand_i16(n).clamp(0, 255).to(torch.uint8)
         y = torch.empty_like(x)

@@ -513,9 +513,11 @@ int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtyp
 // the reference's 2999 x 4499 image) and no tile is left mostly empty by a short row.  The kernel is told the row
 // length (`period`) and forms the sums of the few chunks whose window straddles a row boundary once per side, so each
 // row keeps its own zero padding (fir_1d/sim/vector/gen_fixed_output.py:44-59).  One launch.
-// Rows wider than kFlattenMaxBytes with a 16-byte aligned pitch stay on the per-row tile walk (whole tiles per row,
-// no per-chunk boundary test).
-constexpr long kFlattenMaxBytes = 64 << 10;
+// Rows wider than kFlattenMaxBytes with a 16-byte aligned pitch stay on the per-row paths (row-streaming tensor-map
+// kernel up to 8 KiB, per-row tile walk beyond), which carry no per-chunk boundary test.  Measured, int16, 2^27 samples,
+// fraction of the HBM peak, flattened / per-row: 128 B rows 0.66 / 0.15, 256 B 0.66 / 0.30, 512 B 0.66 / 0.55,
+// 1 KiB 0.66 / 0.79, 2 KiB 0.69 / 0.70, 4 KiB 0.83 / 0.85, 8 KiB 0.89 / 0.92, 2 MiB 0.98 / 1.02 (profiles/README.md).
+constexpr long kFlattenMaxBytes = 512;
 
 bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                 int n_taps, int dilation)

@@ -17,6 +17,8 @@ struct FastPlan {
     bool wrap = false;                       // live acc_bits wrap evaluated in the post stage (plan_wrap)
     int shift = 0, bias = 0;
     int wrap_sh = 0;                         // wrap: 32 - acc_bits
+    bool wrap_split = false;                 // wrap: general split-shift post form (the multiply-add form does not apply)
+    int wrap_mul = 0;                        // wrap: 2^(acc_bits - frac_bits)
     uint32_t post_bias = 0, frac_mask = 0;   // wrap: 2^(frac-1), 2^frac - 1
     int32_t taps[kFastPlanMaxTaps] = {0};    // possibly pre-scaled
 };
@@ -83,6 +85,9 @@ inline FastPlan plan_wrap(const int32_t *hq, int n_taps, int frac_bits, int acc_
     f.shift = frac_bits;
     f.bias = 0;
     f.wrap_sh = 32 - acc_bits;
+    // multiply-add post form: (a << wrap_sh) * 2^(acc_bits - frac_bits) + 2^31, upper word (see post_pair_mode)
+    f.wrap_split = !(frac_bits <= acc_bits && acc_bits - frac_bits <= 30);
+    f.wrap_mul = f.wrap_split ? 0 : (int)(1u << (acc_bits - frac_bits));
     f.post_bias = 1u << (frac_bits - 1);
     f.frac_mask = (1u << frac_bits) - 1u;
     for (int k = 0; k < n_taps; ++k) f.taps[k] = hq[k];

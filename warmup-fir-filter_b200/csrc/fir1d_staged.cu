@@ -96,6 +96,8 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     p.wrap_sh = f0.wrap_sh;
     p.post_bias = f0.post_bias;
     p.frac_mask = f0.frac_mask;
+    p.wrap_split = f0.wrap_split ? 1 : 0;
+    p.wrap_mul = f0.wrap_mul;
     p.period = a.period;
     p.pdl = 1;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * es) % 16 == 0);

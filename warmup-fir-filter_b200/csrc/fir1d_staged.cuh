@@ -33,6 +33,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 namespace firgpu {
 namespace staged {
@@ -74,6 +75,18 @@ template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<256, 4, 2, 2, 2>
 #endif
 // Rows shorter than two long-row tiles: 8 KiB tiles, three CTAs per SM.
 using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
+// Flattened batches (row ends inside the kernel, RE = true).
+#ifndef FIRGPU_FLAT_CFG
+#define FIRGPU_FLAT_CFG 256, 4, 2, 2, 2
+#endif
+using FlatCfg = Cfg<FIRGPU_FLAT_CFG>;
+// WRAP post mode on long rows: the post stage costs about four more instructions per sample, and with the eight
+// warps per SM of the int16 long-row configuration the kernel becomes latency-bound (ncu: issue 41 %, DRAM 62 %);
+// the same 64 KiB in flight per SM as two CTAs of 16 KiB tiles.
+#ifndef FIRGPU_WRAP_CFG
+#define FIRGPU_WRAP_CFG 256, 4, 2, 2, 2
+#endif
+using WrapCfg = Cfg<FIRGPU_WRAP_CFG>;
 
 constexpr int kMaxFastTaps = 65;                // dp2a datapath (taps > 9 run in zero-padded buckets, see launch_long)
 constexpr int kMaxWideTaps = 9;                 // IMAD / wide datapaths
@@ -103,6 +116,9 @@ struct StagedParams {
     // flattened batch: the one long row is really rows of `period` scalars, each zero-padded on its own
     // (gen_fixed_output.py:44-59); 0 = rows are what rows / cols say
     long long period;
+    uint32_t rem_tile_step, rem_sub_step;      // (grid * tile scalars) % period, (threads * chunk scalars) % period (launch_cfg)
+    int wrap_split;                            // WRAP: use the general split-shift form (frac_bits > acc_bits, or frac + 32 - acc_bits < 2)
+    int wrap_mul;                              // WRAP: 2^(acc_bits - frac_bits) (multiply-add form)
     int pdl;                                   // launch with programmatic stream serialisation
 };
 
@@ -341,9 +357,21 @@ template <int POST>
 __device__ __forceinline__ uint32_t post_pair_mode(int a0, int a1, const StagedParams &p)
 {
     if constexpr (POST == POST_WRAP) {
-        const int w0 = (a0 << p.wrap_sh) >> p.wrap_sh, w1 = (a1 << p.wrap_sh) >> p.wrap_sh;
-        int v0 = (w0 >> p.shift) + (int)((((uint32_t)w0 & p.frac_mask) + p.post_bias) >> p.shift);
-        int v1 = (w1 >> p.shift) + (int)((((uint32_t)w1 & p.frac_mask) + p.post_bias) >> p.shift);
+        int v0, v1;
+        if (!p.wrap_split) {
+            // t = a << (32 - acc_bits) = w * 2^(32-acc_bits) exactly (w = the wrapped accumulator); one 32 x 32 -> 64
+            // multiply-add then gives (w + 2^(frac-1)) >> frac in its upper word:
+            //   t * 2^(acc_bits-frac) + 2^31 = (w + 2^(frac-1)) * 2^(32-frac)       (needs 2 <= frac + 32 - acc_bits <= 32)
+            const long long r0 = (long long)(a0 << p.wrap_sh) * (long long)p.wrap_mul + 0x80000000LL;
+            const long long r1 = (long long)(a1 << p.wrap_sh) * (long long)p.wrap_mul + 0x80000000LL;
+            v0 = (int)(r0 >> 32);
+            v1 = (int)(r1 >> 32);
+        } else {
+            // general form: sign-extend, then (w + bias) >> frac as (w >> frac) + (((w mod 2^frac) + bias) >> frac)
+            const int w0 = (a0 << p.wrap_sh) >> p.wrap_sh, w1 = (a1 << p.wrap_sh) >> p.wrap_sh;
+            v0 = (w0 >> p.shift) + (int)((((uint32_t)w0 & p.frac_mask) + p.post_bias) >> p.shift);
+            v1 = (w1 >> p.shift) + (int)((((uint32_t)w1 & p.frac_mask) + p.post_bias) >> p.shift);
+        }
         v0 = __vimin_s32_relu(v0, 255);
         v1 = __vimin_s32_relu(v1, 255);
         return __byte_perm((uint32_t)v0, (uint32_t)v1, 0x5410u);
@@ -407,10 +435,13 @@ __device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int 
             uint32_t BL[G::NB], BR[G::NB];
 #pragma unroll
             for (int j = 0; j < G::NB; ++j) {
-                const int m = cut_s - 4 * j;                 // leading bytes of this quad that lie in the left row
-                const uint32_t ml = m <= 0 ? 0u : (m >= 4 ? 0xffffffffu : (1u << (8 * m)) - 1u);
-                BL[j] = B[d][j] & ml;
-                BR[j] = B[d][j] & ~ml;
+                // bits of this quad that lie in the RIGHT row: all ones shifted up by 8 x (bytes of the quad in the left
+                // row, clamped to 0..4) — shl.b32 yields 0 for a shift of 32, which plain C++ does not promise
+                const int mb = __vimin_s32_relu(8 * cut_s - 32 * j, 32);
+                uint32_t mr;
+                asm("shl.b32 %0, %1, %2;" : "=r"(mr) : "r"(0xffffffffu), "r"(mb));
+                BL[j] = B[d][j] & ~mr;
+                BR[j] = B[d][j] & mr;
             }
             int aL[G::S], aR[G::S];
             mac_stream<G, L, MAC>(p, f, BL, aL);
@@ -438,14 +469,13 @@ __device__ __forceinline__ void mac_post_chunk(const StagedParams &p, const int 
     }
 }
 
-// Flattened batches: how many scalars of the window of the chunk that starts `off` scalars into the tile belong to
-// the row on the left of a row boundary (0 = the window lies inside one row).  `tile_rem` = tile origin modulo the
-// row length.  The host guarantees period >= window, so a window meets at most one boundary.
+// Flattened batches: how many scalars of the window of a chunk whose first scalar sits at position r of its row
+// belong to the row on the LEFT of a row boundary (0 = the window lies inside one row).  The host guarantees
+// period >= window, so a window meets at most one boundary.
 template <typename G, int DIL>
-__device__ __forceinline__ int row_cut(uint32_t tile_rem, uint32_t off, uint32_t period)
+__device__ __forceinline__ int row_cut(uint32_t r, uint32_t period)
 {
     constexpr uint32_t HLS = G::HL4 * DIL, HRS = G::HR4 * DIL;
-    const uint32_t r = (tile_rem + off) % period;          // position of the chunk's first scalar inside its row
     if (r < HLS) return (int)(HLS - r);                    // the row starts inside the left halo
     if (r + G::SC + HRS > period) return (int)(period - r + HLS);   // the row ends inside the chunk or its right halo
     return 0;
@@ -515,7 +545,9 @@ __device__ __forceinline__ void store_chunk(OutT *dst, const uint32_t (&O)[SC * 
     }
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF>
+// RE ("row ends"): this instantiation takes flattened batches (p.period = row length) and zero-pads every row
+// on its own; the others carry no code for it.
+template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF, bool RE = false>
 __global__ void __launch_bounds__(C::kThreads, C::kMinBlocks)
 fir1d_staged_kernel(const __grid_constant__ StagedParams p)
 {
@@ -543,9 +575,12 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
     }
     __syncthreads();
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (this
-    // kernel's input, e.g. the uint8 copy of a float container) are visible from here on.  Our own dependents may
-    // start their prologue now; their griddepcontrol.wait still waits for this grid to finish.
+    // kernel's input, e.g. the uint8 copy of a float container) are visible from here on.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Our dependents (the next kernel in the stream) may become resident from now on: every CTA of this grid is
+    // resident at this point (one wave), so theirs spread evenly over the SMs; their prologue overlaps our run and
+    // their own griddepcontrol.wait still waits for this whole grid.  (Triggering at a CTA's last tile instead was
+    // measured 22 % slower back to back: SMs whose CTA had already exited took two CTAs of the next grid.)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Producer cursor (thread 0 only): the tile whose bulk copy is issued next.
@@ -576,6 +611,17 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
     int stage = 0;
     uint32_t phase_bits = 0;
     const uint32_t lane_off = G::PADB + tid * kChunk;
+    // flattened batch: position of this thread's first chunk inside its row, kept up to date with adds only
+    constexpr bool kRowEnds = RE;
+    static_assert(!RE || (MAC != 2 && L <= kMaxWideTaps), "row ends: short filters on the packed datapaths only");
+    const uint32_t period = kRowEnds ? (uint32_t)p.period : 0u;
+    uint32_t tile_rem = 0, lane_rem = 0;
+    if constexpr (kRowEnds) {
+        if (period) {
+            tile_rem = (uint32_t)(((unsigned long long)blockIdx.x * TS) % period);
+            lane_rem = (uint32_t)(tid * G::SC) % period;
+        }
+    }
     for (long long i = 0; i < n_my; ++i) {
         const TilePlan t = plan_tile<G, TS>(p, c_row, c_tcol);
         const long long g0 = t.col0 - G::PADS;
@@ -614,12 +660,10 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         if (tid == 0 && i + kStages < n_my) issue();
 
         OutT *ythread = reinterpret_cast<OutT *>(p.y) + t.row * p.ld_y + t.col0 + tid * G::SC;
-        // row boundaries inside a flattened batch: short filters only (the long-filter buckets do not take such batches)
-        constexpr bool kRowEnds = MAC != 2 && L <= kMaxWideTaps;
-        const uint32_t period = kRowEnds ? (uint32_t)p.period : 0u;
-        uint32_t tile_rem = 0;
+        uint32_t r_chunk = 0;                              // row position of chunk u = 0; advanced per chunk below
         if constexpr (kRowEnds) {
-            if (period) tile_rem = (uint32_t)((unsigned long long)t.col0 % (unsigned long long)period);
+            r_chunk = tile_rem + lane_rem;
+            if (r_chunk >= period) r_chunk -= period;
         }
         // one chunk: pack, then per tap set accumulate + post-process + store
         auto do_chunk = [&](const int u, const bool vec, const long long room) {
@@ -634,8 +678,10 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
                 bool ends = false;
                 if constexpr (kRowEnds) {
                     if (period) {
-                        cut = row_cut<G, DIL>(tile_rem, (uint32_t)(tid * G::SC + u * (kThreads * G::SC)), period);
+                        cut = row_cut<G, DIL>(r_chunk, period);
                         ends = __any_sync(0xffffffffu, cut != 0);                 // warp-uniform: no divergent double work
+                        r_chunk += p.rem_sub_step;
+                        if (r_chunk >= period) r_chunk -= period;
                     }
                 }
 #pragma unroll
@@ -668,6 +714,10 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         }
         advance_tile(c_row, c_tcol, gridDim.x, tpr);
         stage = stage + 1 == kStages ? 0 : stage + 1;
+        if constexpr (kRowEnds) {
+            tile_rem += p.rem_tile_step;
+            if (tile_rem >= period) tile_rem -= period;
+        }
     }
 }
 
@@ -714,14 +764,14 @@ inline cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t s
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF = 1>
+template <typename C, typename InT, typename OutT, int L, int DIL, int POST, int MAC, int NF = 1, bool RE = false>
 int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
 {
-    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, POST, MAC, NF>;
+    auto kern = fir1d_staged_kernel<C, InT, OutT, L, DIL, POST, MAC, NF, RE>;
     using G = Geo<InT, L, DIL>;
     constexpr int kSmem = C::smem_bytes(G::PADB);
     // a flattened batch needs every chunk window to meet at most one row boundary
-    if (p_in.period && (MAC == 2 || L > kMaxWideTaps || p_in.period < (long long)(G::HL4 * DIL + G::SC + G::HR4 * DIL) || p_in.period >= (1LL << 31) || p_in.rows != 1))
+    if (p_in.period && (!RE || p_in.period < (long long)(G::HL4 * DIL + G::SC + G::HR4 * DIL) || p_in.period >= (1LL << 31) || p_in.rows != 1))
         return 0;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
@@ -748,7 +798,14 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
     p.total_tiles = p.tiles_per_row * p.rows;
     long long grid = (long long)sm_count(dev) * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    FIRGPU_CUDA(launch_pdl(kern, (unsigned)grid, C::kThreads, kSmem, stream, env.pdl && p.pdl, p));
+    if (p.period) {
+        p.rem_tile_step = (uint32_t)((unsigned long long)(grid * ts) % (unsigned long long)p.period);
+        p.rem_sub_step = (uint32_t)((unsigned long long)(C::kThreads * G::SC) % (unsigned long long)p.period);
+    }
+    // Programmatic stream serialisation only for launches of a few tiles per CTA (about 20 microseconds or less), where
+    // the launch latency it hides is a visible share; long kernels measured 1 % slower with it.
+    const bool pdl = env.pdl && p.pdl && p.total_tiles <= 4 * grid;
+    FIRGPU_CUDA(launch_pdl(kern, (unsigned)grid, C::kThreads, kSmem, stream, pdl, p));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
 }
@@ -759,15 +816,24 @@ int launch_one(const StagedParams &p, cudaStream_t stream)
     // four tap sets over one staged input (the generators' coefficient loop):
     // uint8 images, 3 / 5 taps only
     if constexpr (sizeof(InT) == 1 && sizeof(OutT) == 1 && (L == 3 || L == 5) && DIL == 1 && MAC == 0) {
-        if (p.n_filters == kMaxFilters) return launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, POST, MAC, kMaxFilters>(p, stream);
+        if (p.n_filters == kMaxFilters)
+            return p.period ? launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, POST, MAC, kMaxFilters, true>(p, stream)
+                            : launch_cfg<Cfg<256, 2, 2, 2, 2>, InT, OutT, L, DIL, POST, MAC, kMaxFilters>(p, stream);
     }
     if (p.n_filters != 1) return 0;
+    // flattened batches (dense rows filtered as one long row, row ends inside the kernel): one configuration,
+    // 8 KiB tiles and three CTAs per SM — the row-end path is latency-bound and wants the warps
+    if constexpr (MAC != 2 && L <= kMaxWideTaps) {
+        if (p.period) return launch_cfg<FlatCfg, InT, OutT, L, DIL, POST, MAC, 1, true>(p, stream);
+    }
+    if (p.period) return 0;
     using Big = typename TuneFor<InT, OutT>::type;
+    using Long = typename std::conditional<POST == POST_WRAP, WrapCfg, Big>::type;
 #ifndef FIRGPU_K_THREADS
     if (p.cols * (long long)sizeof(InT) < 2LL * Big::kTileBytes)
         return launch_cfg<SmallRowCfg, InT, OutT, L, DIL, POST, MAC>(p, stream);
 #endif
-    return launch_cfg<Big, InT, OutT, L, DIL, POST, MAC>(p, stream);
+    return launch_cfg<Long, InT, OutT, L, DIL, POST, MAC>(p, stream);
 }
 
 // post: POST_SHIFT / POST_HI16 / POST_WRAP (wide TU: 0 / 1 = clamp flag).  mac: 0 = dp2a (signed 16-bit taps),
@@ -794,15 +860,17 @@ template <typename InT, typename OutT, int DIL>
 int launch_taps(const StagedParams &p, int n_taps, int post, int mac, cudaStream_t s)
 {
     switch (n_taps) {
+#ifndef FIRGPU_QUICK                     // (make QUICK=1: experiment builds carry 3 and 5 taps only)
     case 1: return launch_modes<InT, OutT, 1, DIL>(p, post, mac, s);
     case 2: return launch_modes<InT, OutT, 2, DIL>(p, post, mac, s);
-    case 3: return launch_modes<InT, OutT, 3, DIL>(p, post, mac, s);
     case 4: return launch_modes<InT, OutT, 4, DIL>(p, post, mac, s);
-    case 5: return launch_modes<InT, OutT, 5, DIL>(p, post, mac, s);
     case 6: return launch_modes<InT, OutT, 6, DIL>(p, post, mac, s);
     case 7: return launch_modes<InT, OutT, 7, DIL>(p, post, mac, s);
     case 8: return launch_modes<InT, OutT, 8, DIL>(p, post, mac, s);
     case 9: return launch_modes<InT, OutT, 9, DIL>(p, post, mac, s);
+#endif
+    case 3: return launch_modes<InT, OutT, 3, DIL>(p, post, mac, s);
+    case 5: return launch_modes<InT, OutT, 5, DIL>(p, post, mac, s);
     default: return 0;
     }
 }
@@ -827,11 +895,13 @@ int launch_long(const StagedParams &p, int bucket, int post, cudaStream_t s)
 {
     switch (bucket) {
     case 13: return launch_long_bucket<T, OutT, 13>(p, post, s);
+#ifndef FIRGPU_QUICK
     case 17: return launch_long_bucket<T, OutT, 17>(p, post, s);
     case 25: return launch_long_bucket<T, OutT, 25>(p, post, s);
     case 33: return launch_long_bucket<T, OutT, 33>(p, post, s);
     case 49: return launch_long_bucket<T, OutT, 49>(p, post, s);
     case 65: return launch_long_bucket<T, OutT, 65>(p, post, s);
+#endif
     default: return 0;
     }
 }

@@ -114,6 +114,15 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
         for (int m = 0; m < a.kh; ++m) p.col_taps[m] = (int32_t)(fa[m] * scale);
     } else {
         for (int m = 0; m < a.kh; ++m) build_pairs(f.taps + m * a.kw, a.kw, kMaxPairs2, p.cp_even[m], p.cp_odd[m]);
+        if (a.kh == 5 && a.kw == 5) {
+            // the tap of a 5-wide kernel row that has no partner in its row: offset +2 (taps[0]) for windows that start on
+            // an even sample, offset -2 (taps[4]) for odd ones; rows (0,1) and (2,3) share a dp2a (fir2d_tiled.cuh, mac_cross)
+            for (int j = 0; j < 2; ++j) {
+                const int32_t *r0 = f.taps + (2 * j) * a.kw, *r1 = f.taps + (2 * j + 1) * a.kw;
+                p.xp_even[j] = pack_pair(tap_at(r0, 5, 2), tap_at(r1, 5, 2));
+                p.xp_odd[j] = pack_pair(tap_at(r0, 5, -2), tap_at(r1, 5, -2));
+            }
+        }
     }
 
     const int bh = rows_per_stage(a.kh);                     // Geo2::BH

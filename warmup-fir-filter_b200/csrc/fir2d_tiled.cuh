@@ -80,6 +80,7 @@ struct TiledParams {
     int total_items;
     uint32_t cp_even[kMaxKH][kMaxPairs2];        // general: dp2a tap pairs of kernel row m
     uint32_t cp_odd[kMaxKH][kMaxPairs2];
+    uint32_t xp_even[2], xp_odd[2];              // general 5x5: the odd tap of kernel rows (0,1) and (2,3) paired ACROSS rows
     uint32_t rp_even[kMaxPairs2], rp_odd[kMaxPairs2];   // separable: row-pass pairs (vector b)
     int32_t col_taps[kMaxKH];                    // separable: column taps (vector a, pre-scaled)
 };
@@ -137,6 +138,51 @@ __device__ __forceinline__ void mac_row(const uint32_t (&cpe)[kMaxPairs2], const
             }
         }
         acc[i] = a;
+    }
+}
+
+// The same without the tap that has no partner inside its kernel row (5-wide rows: the last tap of a window that
+// starts on an even sample, the first tap of one that starts on an odd sample): two dp2a per pixel instead of three.
+template <typename G1, int L>
+__device__ __forceinline__ void mac_row_pairs(const uint32_t (&cpe)[kMaxPairs2], const uint32_t (&cpo)[kMaxPairs2],
+                                              const uint32_t (&B)[G1::NB], int (&acc)[G1::S])
+{
+    static_assert(L == 5, "cross-row pairing is built for 5-wide kernel rows");
+#pragma unroll
+    for (int i = 0; i < G1::S; ++i) {
+        int a = acc[i];
+        const int s0 = G1::HL4 + i - G1::lo;
+        if ((s0 & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int q = s0 / 2 + k;
+                a = (q & 1) ? dp2a_hi(cpe[k], B[q >> 1], a) : dp2a_lo(cpe[k], B[q >> 1], a);
+            }
+        } else {
+#pragma unroll
+            for (int k = 1; k < 3; ++k) {
+                const int q = (s0 - 1) / 2 + k;
+                a = (q & 1) ? dp2a_hi(cpo[k], B[q >> 1], a) : dp2a_lo(cpo[k], B[q >> 1], a);
+            }
+        }
+        acc[i] = a;
+    }
+}
+
+// ... and those left-over taps of TWO vertically adjacent kernel rows in one dp2a: V holds the two input rows'
+// bytes interleaved (V[2q] = [x.b0, y.b0, x.b1, y.b1], V[2q+1] = [x.b2, y.b2, x.b3, y.b3] of byte-quad q, x = the newer
+// row), `even` / `odd` the two rows' left-over taps for windows starting on an even / odd sample.  25 taps then cost
+// 13 dp2a per pixel instead of 15 — the dp2a pipe is what bounds a general 5x5 kernel.
+template <typename G1>
+__device__ __forceinline__ void mac_cross(uint32_t even, uint32_t odd, const uint32_t (&V)[2 * G1::NB], int (&acc)[G1::S])
+{
+#pragma unroll
+    for (int i = 0; i < G1::S; ++i) {
+        const int s0 = G1::HL4 + i - G1::lo;
+        const bool ev = (s0 & 1) == 0;
+        const int sg = ev ? s0 + 4 : s0;                 // the sample that left-over tap multiplies
+        const uint32_t x = V[2 * (sg >> 2) + ((sg & 3) >> 1)];
+        acc[i] = (sg & 1) ? dp2a_hi(ev ? even : odd, x, acc[i]) : dp2a_lo(ev ? even : odd, x, acc[i]);
     }
 }
 
@@ -251,6 +297,8 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // rolling window of the last KH input rows
     uint32_t Bw[SEP ? 1 : KH][G1::NB];            // general: byte-packed samples
     int Rw[SEP ? KH : 1][G1::S];                  // separable: horizontal sums
+    constexpr bool kCross = !SEP && KH == 5 && KW == 5;      // general 5x5: left-over taps paired across kernel rows
+    uint32_t Vw[kCross ? KH : 1][2 * G1::NB];     // ... row rr interleaved bytewise with the row before it
 
     int stage = 0;
     uint32_t phase_bits = 0;
@@ -296,6 +344,14 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         } else {
 #pragma unroll
                             for (int q = 0; q < G1::NB; ++q) Bw[rr][q] = Bnew[q];
+                            if constexpr (kCross) {
+                                const int prev = (rr + KH - 1) % KH;
+#pragma unroll
+                                for (int q = 0; q < G1::NB; ++q) {
+                                    Vw[rr][2 * q] = __byte_perm(Bnew[q], Bw[prev][q], 0x5140u);
+                                    Vw[rr][2 * q + 1] = __byte_perm(Bnew[q], Bw[prev][q], 0x7362u);
+                                }
+                            }
                         }
                         if (o >= 0 && o < rows_here) {
                             int acc[G1::S];
@@ -307,9 +363,16 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 if constexpr (SEP) {
 #pragma unroll
                                     for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
+                                } else if constexpr (kCross) {
+                                    if (m < 4) mac_row_pairs<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
+                                    else mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                 } else {
                                     mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                 }
+                            }
+                            if constexpr (kCross) {       // kernel rows (0,1) <-> input rows (rr, rr-1); (2,3) <-> (rr-2, rr-3)
+                                mac_cross<G1>(p.xp_even[0], p.xp_odd[0], Vw[rr], acc);
+                                mac_cross<G1>(p.xp_even[1], p.xp_odd[1], Vw[(rr + KH - 2) % KH], acc);
                             }
                             uint32_t V[G1::S / 2];
 #pragma unroll

@@ -10,8 +10,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libfirgpu.so"
+LIB_PATH = Path(os.environ.get("FIRGPU_LIB") or HERE / "libfirgpu.so")      # FIRGPU_LIB: another build of the same library (kernel experiments)
 
 # enum firgpu_dtype
 U8, I16, I32, F32, F64 = 0, 1, 2, 3, 4

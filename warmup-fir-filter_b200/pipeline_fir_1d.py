@@ -48,6 +48,8 @@ def run_pipeline(*, tap: str, overwrite_vectors: bool, skip_input: bool, skip_id
     # to their source files, the GPU-backed ones must not default to somewhere else (see _batched.vector_root).
     root = _batched.vector_root()
     input_dir, output_dir = root / "input", root / "output"
+    if not skip_input:
+        input_dir.mkdir(parents=True, exist_ok=True)       # (the reference's stage creates the leaf only)
 
     if not skip_input:
         _log_stage("Generate input vectors")
