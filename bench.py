@@ -427,7 +427,11 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         dist.barrier()
     ms_total = torch.tensor([start.elapsed_time(end)], device=device, dtype=torch.float64)
+    ms_ranks = [float(ms_total.item()) / args.steps]
     if world > 1:
+        gathered = [torch.zeros_like(ms_total) for _ in range(world)]
+        dist.all_gather(gathered, ms_total)
+        ms_ranks = [float(t.item()) / args.steps for t in gathered]
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_total = float(ms_total.item())
     ms_per_step = ms_total / args.steps
@@ -496,6 +500,7 @@ def gpu_arm(args, rank: int, local_rank: int, world: int) -> None:
                     "d2h_bytes_per_step": 2 * n_host * world, "steps": e2e_steps,
                     "api": "firgpu.fir1d_fixed(host int16 ndarray, pinned) -> firgpu_fir1d_fixed_host", "matches_device_run": e2e_ok},
             "gpu_launches": int(launches), "clocks": clock_summary,
+            "ms_per_step_by_rank": [round(v, 6) for v in ms_ranks],      # the headline takes the slowest
         }
         if configs is not None:
             line["configs"] = configs

@@ -117,6 +117,32 @@ def main():
             s = timed(lambda: [firgpu.fir1d_fixed(xz, LP5, 15, 32, 16, dilation=2, out_dtype=np.int16, out=y, validate=False) for _ in range(16)], args.reps)
             report(f"16 x iq {m} scalars i16 5tap q1.15 back to back (per pass)", s / 16, m, 4)
             del x, y
+    if "streamblocks" in cases:
+        # device-resident streaming (firgpu_stream_*): a 2^28-sample int16 signal delivered in blocks, against one call
+        from firgpu import quant as _q
+        x = rand_i16(n)
+        y = torch.empty_like(x)
+        hq = _q.quantize_taps(LP5, 15, 16)
+        s = timed(lambda: firgpu.fir1d_fixed(x, LP5, 15, 32, 16, centre=0, out_dtype=np.int16, out=y, validate=False), args.reps)
+        report("causal one call 2^28 i16->i16 5tap q1.15", s, n, 4)
+        for lg in (20, 22, 24, 26, 28):
+            blk = 1 << lg
+            st = firgpu.FirStream(hq, model="fixed", in_dtype=np.int16, out_dtype=np.int16, frac_bits=15)
+            s = timed(lambda: [st.process(x[b:b + blk], out=y[b:b + blk]) for b in range(0, n, blk)], max(3, args.reps // 4))
+            report(f"stream object, 2^28 samples in device blocks of 2^{lg} (main + history kernel per block)", s, n, 4)
+            st.close()
+        g = torch.Generator(device="cuda").manual_seed(9)
+        xf = torch.randn(1 << 26, generator=g, device="cuda", dtype=torch.float64)
+        yf = torch.empty_like(xf)
+        s = timed(lambda: firgpu.fir1d_ideal(xf, LP5, centre=0, raw=True, out=yf, validate=False), 5)
+        report("C++ Fir1D model, one call 2^26 f64->f64 5tap", s, 1 << 26, 16)
+        for lg in (20, 22, 24):
+            blk = 1 << lg
+            st = firgpu.FirStream(LP5, model="ideal", in_dtype=np.float64, out_dtype=np.float64, raw=True)
+            s = timed(lambda: [st.process(xf[b:b + blk], out=yf[b:b + blk]) for b in range(0, 1 << 26, blk)], 5)
+            report(f"C++ Fir1D model as a stream object, 2^26 samples in device blocks of 2^{lg}", s, 1 << 26, 16)
+            st.close()
+        del x, y, xf, yf
     if "u8" in cases:
         x = rand_i16(n).clamp(0, 255).to(torch.uint8)
         y = torch.empty_like(x)

@@ -215,6 +215,10 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch (small launches only, see launch_tiled_one): the prologue above overlapped the
+    // previous kernel's tail; nothing below may touch global memory before that kernel has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // item -> (image, band, strip); consecutive items are neighbouring strips of
     // one band, so bands that share halo rows are processed at the same time
@@ -439,15 +443,17 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     // int16 kernels are fastest with 3 resident CTAs per SM; 5-row and all uint8 kernels
     // (twice the arithmetic per byte) with all that fit.
     if (KH <= 3 && sizeof(T) == 2 && per_sm > 3) per_sm = 3;
-    if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {
+    if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) {       // (tools/sweep_tiled.cu changes it between launches: not cached)
         const int forced = atoi(e);
         if (forced >= 1 && forced < per_sm) per_sm = forced;
     }
-    FIRGPU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = staged::sm_count(dev);
     long long grid = (long long)sms * per_sm;
     if (grid > p.total_items) grid = p.total_items;
-    kern<<<(unsigned)grid, kBlock2, G::SMEM, stream>>>(map, p);
-    FIRGPU_CUDA(cudaGetLastError());
+    // a few items per CTA (a row-band shard of an 8-GPU plan, a small image): hide the launch latency behind the
+    // previous kernel's tail; long launches gain nothing from it
+    const bool pdl = staged::launch_env().pdl && p.total_items <= 8 * grid;
+    FIRGPU_CUDA(staged::launch_pdl(kern, (unsigned)grid, kBlock2, G::SMEM, stream, pdl, map, p));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
 }
