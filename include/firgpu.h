@@ -108,6 +108,16 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype,
                        int64_t halo_left_valid, int64_t halo_right_valid,
                        void *stream);
 
+/* Which datapath firgpu_fir1d_fixed would use for these integer taps on uint8 /
+ * int16 containers.  Host-only (no device needed): the exactness proof of the
+ * packed int32 kernels is made from the taps alone.
+ *   *path  FIRGPU_PATH_STAGED (a fast kernel) or FIRGPU_PATH_GENERIC (int64 kernel)
+ *   *post  0 = shift, 1 = taps pre-scaled to a 16-bit shift, 2 = live acc_bits
+ *          wrap evaluated in the post stage (fir_1d_fixed_ref.py:110-118)
+ *   *mac   0 = dp2a (taps fit int16), 1 = IMAD with 32-bit taps */
+int firgpu_fir1d_fixed_plan(const int32_t *hq, int n_taps, int frac_bits, int acc_bits,
+                            int *path, int *post, int *mac);
+
 /* Same filter applied with n_filters tap sets to one input, reading x once:
  * hq is [n_filters][n_taps] row-major (host), y is [n_filters] outputs
  * separated by filter_stride_y elements.  Stands behind the coefficient loop

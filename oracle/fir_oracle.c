@@ -51,7 +51,15 @@ static inline int64_t load_sample(const void *base, int dtype, int64_t idx)
     case FIRO_U8:  return ((const uint8_t *)base)[idx];
     case FIRO_I16: { int64_t v = ((const int16_t *)base)[idx]; return v < 0 ? 0 : v > 255 ? 255 : v; }
     case FIRO_I32: { int64_t v = ((const int32_t *)base)[idx]; return v < 0 ? 0 : v > 255 ? 255 : v; }
-    case FIRO_F32: return prep_from_double((double)((const float *)base)[idx]);
+    case FIRO_F32: {
+        /* float32 containers: the reference's `sample + 0.5` is a float32 add (NumPy 2 scalar promotion,
+         * fir_1d_ref.py:37); volatile keeps the compiler from evaluating it in a wider type */
+        volatile float sum = ((const float *)base)[idx] + 0.5f;
+        double r = floor((double)sum);
+        if (r < 0.0) return 0;
+        if (r > 255.0) return 255;
+        return (int64_t)r;
+    }
     default:       return prep_from_double(((const double *)base)[idx]);
     }
 }

@@ -20,7 +20,7 @@ PIXEL_LO, PIXEL_HI = 0, 255          # fir_1d_fixed_ref.py:50-51
 
 
 def prep_samples(x, lo: int = PIXEL_LO, hi: int = PIXEL_HI) -> np.ndarray:
-    """round-half-up (floor(x + 0.5) in float64) then clamp to [lo, hi]
+    """round-half-up (floor(x + 0.5) in the precision of the container: float64 for lists and float64 arrays) then clamp to [lo, hi]
     (fir_1d/model/python/fir_1d_ref.py:35-41; the reference's range is
     [0, 255]).  Integer inputs skip the rounding, which is the identity on
     them.  Returns uint8 for the reference range, int64 otherwise."""
@@ -30,7 +30,13 @@ def prep_samples(x, lo: int = PIXEL_LO, hi: int = PIXEL_HI) -> np.ndarray:
         return a
     if a.dtype.kind in "iub":
         return np.clip(a.astype(np.int64), lo, hi).astype(out_t)
-    r = np.floor(a.astype(np.float64) + 0.5)
+    if a.dtype.kind == "f" and a.dtype.itemsize < 8:
+        # the reference adds 0.5 to the array's own scalars: `np.float32 + 0.5` is a float32 add under NumPy 2 promotion
+        # (fir_1d_ref.py:37, `math.floor(sample + 0.5)`), which differs from float64 at one value per format, the largest
+        # one below 0.5 (it ties up to 1.0)
+        r = np.floor(a + a.dtype.type(0.5)).astype(np.float64)
+    else:
+        r = np.floor(a.astype(np.float64) + 0.5)
     return np.clip(r, lo, hi).astype(out_t)
 
 

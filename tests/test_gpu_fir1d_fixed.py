@@ -458,6 +458,8 @@ def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):
         [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e300, -1e300, 0.49999999999999994, 0.5, 0.25, 2.0 ** -30, 255.49999999999997, 1.7e308],
         np.exp(rng.uniform(-40, 40, size=500)), -np.exp(rng.uniform(-40, 40, size=100))])
     assert onp.fir1d_fixed(np.array([0.49999999999999994]), [1.0])[0] == 1          # the reference's own behaviour
+    assert onp.fir1d_fixed(np.array([0.49999997], np.float32), [1.0])[0] == 1       # ... and on a float32 array (float32 add)
+    assert onp.fir1d_fixed([0.49999997017860413], [1.0])[0] == 0                    # ... the same value in a list: float64 add
     i32 = np.arange(-3, 260, dtype=np.float32)
     special32 = np.concatenate([
         i32, i32 + np.float32(0.5), np.nextafter(i32 + np.float32(0.5), np.float32(-np.inf)), np.nextafter(i32 + np.float32(0.5), np.float32(np.inf)),
@@ -466,7 +468,9 @@ def test_sample_rounding_matches_float64_floor_at_every_boundary(fg, torch):
     for base in (special, special32):
         for reps in (1, 8):                                   # 1: generic kernel; 8: > 4096 samples, conversion pass
             x = np.tile(base, reps)
-            want = np.clip(np.floor(x.astype(np.float64) + 0.5), 0, 255).astype(np.uint8)
+            # the add is evaluated in the container's precision (np.float32 + 0.5 stays float32: fir_1d_ref.py:37)
+            with np.errstate(over="ignore"):
+                want = np.clip(np.floor(x + x.dtype.type(0.5)).astype(np.float64), 0, 255).astype(np.uint8)
             for src in (x, torch.from_numpy(x).cuda()):
                 y = fg.fir1d_fixed(src, [1.0])
                 y = y.cpu().numpy() if hasattr(y, "cpu") else y

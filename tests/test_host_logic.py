@@ -293,3 +293,55 @@ def test_image_view_addressing():
     for bad in (base[:, :, ::2], base.transpose(1, 2), four[:, :, :, 2:9]):
         with pytest.raises(ValueError):
             ops._cuda_imgs(bad, "x")
+
+
+# ---- round 2: host-side decisions that need no device -------------------------------------------------------------
+@pytest.mark.parametrize("h, frac, acc, cb, want", [
+    ([1 / 16, 4 / 16, 6 / 16, 4 / 16, 1 / 16], 15, 32, 16, ("staged", "hi16", "dp2a")),      # the headline taps: pre-scaled by 2, one byte permute
+    ([-0.125, 1.25, -0.125], 12, 32, 16, ("staged", "shift", "dp2a")),                        # sharpen: 5120 * 16 does not fit int16
+    ([0.9, -0.7, 0.8, 0.3, -0.2], 12, 16, 16, ("staged", "wrap", "dp2a")),                    # 255 * sum|hq| >= 2^15: the wrap is live
+    ([1.0], 12, 20, 16, ("staged", "wrap", "dp2a")),
+    ([0.9, -0.7, 0.8, 0.3, -0.2], 12, 24, 16, ("staged", "shift", "dp2a")),                   # same taps, wrap provably idle
+    ([7.5, -7.5, 0.001], 28, 32, 32, ("staged", "wrap", "imad")),                             # 32-bit taps
+    ([0.001, 0.002], 28, 40, 32, ("staged", "wrap", "imad")),                                 # wider accumulator, sums fit int32
+    ([0.4, 0.3], 30, 64, 32, ("generic", None, None)),                                        # sums beyond int32 in a 64-bit accumulator
+    ([0.01] * 21, 12, 18, 16, ("staged", "wrap", "dp2a")),                                    # long-filter bucket under a live wrap
+    ([0.01] * 70, 12, 32, 16, ("generic", None, None)),                                       # beyond the largest bucket
+])
+def test_fixed_point_datapath_is_chosen_from_the_taps_alone(h, frac, acc, cb, want):
+    import firgpu
+    got = firgpu.fir1d_fixed_plan(h, frac, acc, cb)
+    assert (got["path"], got["post"], got["mac"]) == want
+
+
+def test_vector_root_is_one_tree_for_all_pipeline_stages(monkeypatch, tmp_path):
+    """The GPU-backed generators default to the SAME input / output tree as the reference's untouched stages
+    (advisor finding, round 1): FIR_VECTOR_ROOT, else the reference's fir_1d/sim/vector, else next to the drop-in."""
+    from pathlib import Path
+    from fir_1d.sim.vector import _batched
+    monkeypatch.delenv("FIR_VECTOR_ROOT", raising=False)
+    monkeypatch.delenv("FIR_REFERENCE_ROOT", raising=False)
+    assert _batched.vector_root() == Path(_batched.__file__).resolve().parent
+    ref = tmp_path / "ref"
+    (ref / "fir_1d" / "sim" / "vector").mkdir(parents=True)
+    monkeypatch.setenv("FIR_REFERENCE_ROOT", str(ref))
+    assert _batched.vector_root() == (ref / "fir_1d" / "sim" / "vector").resolve()
+    monkeypatch.setenv("FIR_VECTOR_ROOT", str(tmp_path / "elsewhere"))
+    assert _batched.vector_root() == (tmp_path / "elsewhere").resolve()
+
+
+def test_stream_and_record_entry_points_reject_bad_arguments_without_a_device():
+    import ctypes as C
+    from firgpu import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    taps = (C.c_int32 * 3)(1, 2, 1)
+    assert L.firgpu_stream_create_fixed(C.byref(h), 9, _lib.U8, taps, 3, 1, 12, 32, 0, 255, 0, 255, 0) == -1       # dtype
+    assert L.firgpu_stream_create_fixed(C.byref(h), _lib.U8, _lib.U8, taps, 0, 1, 12, 32, 0, 255, 0, 255, 0) == -3  # taps
+    assert L.firgpu_stream_create_fixed(C.byref(h), _lib.U8, _lib.F64, taps, 3, 1, 12, 32, 0, 255, 0, 255, 0) == -1
+    assert L.firgpu_stream_create_fixed(C.byref(h), _lib.U8, _lib.U8, taps, 3, 0, 12, 32, 0, 255, 0, 255, 0) == -5  # dilation
+    assert L.firgpu_stream_create_fixed(C.byref(h), _lib.U8, _lib.U8, taps, 3, 1, 0, 32, 0, 255, 0, 255, 0) == -4   # bits
+    assert L.firgpu_stream_process(None, None, None, 5, None) == -6
+    assert L.firgpu_record_begin(None) == -6                      # the NULL stream cannot record
+    assert L.firgpu_graph_launch(None, None) == -6
+    assert b"NULL" in L.firgpu_last_error()

@@ -89,3 +89,23 @@ def test_reference_complex_times_real_tap_is_componentwise():
     re, im = c_oracle.ref_complex_real_tap_mac(z, h)
     assert re == pytest.approx(float(np.dot(z[0::2], h)), abs=1e-9)
     assert im == pytest.approx(float(np.dot(z[1::2], h)), abs=1e-9)
+
+
+def test_half_up_rounding_follows_the_container_precision(ref):
+    """`math.floor(sample + 0.5)` (fir_1d_ref.py:37) runs on the container's own scalars: float64 for lists and float64
+    arrays, float32 / float16 for such arrays (NumPy 2 promotion).  The three oracles agree with the reference on every
+    x.5 tie, its neighbours and the one value per format where the precisions differ (the largest below 0.5)."""
+    fixed, ideal = ref
+    for dt in (np.float64, np.float32, np.float16):
+        ints = np.arange(-2, 258).astype(dt)
+        half = ints + dt(0.5)
+        x = np.concatenate([ints, half, np.nextafter(half, dt(-np.inf)), np.nextafter(half, dt(np.inf)),
+                            np.array([0.49999999999999994, 0.49999997, 0.49975586, 0.5, 255.49999], dtype=np.float64).astype(dt)])
+        x = x[np.isfinite(x)]
+        want = fixed(x, [1.0])
+        assert np.array_equal(onp.fir1d_fixed(x, [1.0]), want), dt
+        assert list(opy.fir1d_fixed(list(x), [1.0])) == want.tolist(), dt
+        if dt != np.float16:                          # (the C oracle reads float32 / float64 containers)
+            assert np.array_equal(c_oracle.fir1d_fixed(x, onp.quantize_taps([1.0], 12, 16), 12, 32), want), dt
+        assert np.array_equal(np.asarray(ideal(x, [1.0])), onp.fir1d_ideal(x, [1.0])), dt
+    assert fixed(np.array([0.49999997], np.float32), [1.0])[0] == 1 and fixed([0.49999997017860413], [1.0])[0] == 0

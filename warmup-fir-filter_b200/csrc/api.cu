@@ -1282,6 +1282,15 @@ int firgpu_fir1d_fixed_host_multi(const void *x, void *y, int in_dtype, int out_
     return rc;
 }
 
+int firgpu_fir1d_fixed_plan(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int *path, int *post, int *mac)
+{
+    if (!hq || !path || !post || !mac) return set_error(FIRGPU_E_NULL, "firgpu_fir1d_fixed_plan: NULL");
+    if (n_taps < 1 || n_taps > FIRGPU_MAX_TAPS) return set_error(FIRGPU_E_TAPS, "firgpu_fir1d_fixed_plan: n_taps=%d outside [1,%d]", n_taps, FIRGPU_MAX_TAPS);
+    int rc = check_bits("firgpu_fir1d_fixed_plan", frac_bits, acc_bits);
+    if (rc) return rc;
+    return plan_fir1d_fixed(hq, n_taps, frac_bits, acc_bits, path, post, mac);
+}
+
 int firgpu_get_device(int *device)
 {
     if (!device) return set_error(FIRGPU_E_NULL, "firgpu_get_device: NULL");

@@ -86,11 +86,17 @@ __device__ __forceinline__ int prep_sample(double v)
     if (hi >> 31) r = 0;                                       // x < 0 or -0.0
     return r;
 }
-__device__ __forceinline__ int prep_sample(float v)              // == prep_sample((double)v): the float64 add never changes the floor here
+// float32 containers: the reference evaluates `sample + 0.5` on the array's own scalars (NumPy 2: np.float32 + 0.5 stays
+// float32, fir_1d_ref.py:37), so the add is a FLOAT32 add.  Like the float64 one it is exact on [0, 256) except for one
+// value, the largest float32 below 0.5 (0x3effffff): 0.5 - 2^-25 + 0.5 is a tie that rounds to 1.0, and the reference
+// returns 1 for it (a Python list of the same values is float64 arithmetic and returns 0: the container decides).
+__device__ __forceinline__ int prep_sample(float v)
 {
     // floor(2x) with one saturating conversion (2x is exact; +-inf-sized products saturate), then (q + 1) >> 1.
     const int q = min(__float2int_rd(v * 2.0f), 2 * kPixelMax + 1);
-    return min(max((q + 1) >> 1, 0), kPixelMax);
+    int r = min(max((q + 1) >> 1, 0), kPixelMax);
+    if (__float_as_uint(v) == 0x3effffffu) r = 1;              // the float32 tie described above
+    return r;
 }
 
 // Parametrised forms (extended entry points): sample clamp range [lo, hi] and
@@ -104,7 +110,12 @@ __device__ __forceinline__ int prep_sample_range(double v, int lo, int hi)
     r = fmin(fmax(r, (double)lo), (double)hi);
     return (int)r;
 }
-__device__ __forceinline__ int prep_sample_range(float v, int lo, int hi) { return prep_sample_range((double)v, lo, hi); }
+__device__ __forceinline__ int prep_sample_range(float v, int lo, int hi)
+{
+    double r = floor((double)__fadd_rn(v, 0.5f));              // the reference's add is a float32 add for float32 containers
+    r = fmin(fmax(r, (double)lo), (double)hi);
+    return (int)r;
+}
 
 // wrap -> bias -> shift -> saturate on a 64-bit accumulator.  |acc| < 2^50 for
 // every supported tap count, so int64 itself never overflows and the only
@@ -174,6 +185,8 @@ int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
 // taps are outside the staged kernel's domain (caller falls to generic), <0 / >0 on error.
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
+// host-only: the datapath that would serve these taps (firgpu_fir1d_fixed_plan)
+int plan_fir1d_fixed(const int32_t *hq_host, int n_taps, int frac_bits, int acc_bits, int *path, int *post, int *mac);
 // wide datapath of the extended entry point (signed int16 ranges); 1 = served, 0 = not eligible
 int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_host);
 // n_filters tap sets ([n_filters][n_taps]) over one pass of the input; outputs filter_stride_y elements apart.

@@ -21,6 +21,41 @@ int mac_mode()
     return g_mac_mode;
 }
 
+// Every tap set must be provably exact in int32, and all of them share one post mode: the 16-bit-shift form when every
+// set can be pre-scaled, else the plain shift, else — wrap live, taps beyond int16, a shifted result beyond 16 bits — the
+// WRAP form (dp2a while the taps fit int16, IMAD with full int32 taps otherwise; IMAD exists for single tap sets of at most
+// nine taps).
+bool select_plan(const int32_t *taps_in, int n_taps, int n_filters, int frac_bits, int acc_bits, bool long_bucket, bool force_imad,
+                 FastPlan *plans, int *post_out, int *mac_out)
+{
+    int post = POST_HI16, mac = 0;
+    auto plan_all = [&](auto &&make) {
+        for (int f = 0; f < n_filters; ++f) {
+            plans[f] = make(taps_in + (size_t)f * n_taps);
+            if (!plans[f].ok) return false;
+        }
+        return true;
+    };
+    bool ok = !force_imad && plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, frac_bits, acc_bits, 32767); });
+    if (ok) {
+        for (int f = 0; f < n_filters; ++f)
+            if (!plans[f].hi16) post = POST_SHIFT;
+        if (post == POST_SHIFT)
+            ok = plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, frac_bits, acc_bits, 32767, false); });
+    }
+    if (!ok) {
+        post = POST_WRAP;
+        ok = !force_imad && plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, frac_bits, acc_bits, 32767); });
+        if (!ok && !long_bucket && n_filters == 1) {
+            mac = 1;
+            ok = plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, frac_bits, acc_bits, 0x7fffffff); });
+        }
+    }
+    *post_out = post;
+    *mac_out = mac;
+    return ok;
+}
+
 }  // namespace
 
 int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_host, int n_filters, int64_t filter_stride_y)
@@ -49,33 +84,9 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
         taps_in = padded;
         n_taps = bucket;
     }
-    // Every tap set must be provably exact in int32, and all of them share one post mode: the 16-bit-shift form
-    // when every set can be pre-scaled, else the plain shift, else — wrap live, taps beyond int16, a shifted
-    // result beyond 16 bits — the WRAP form (dp2a while the taps fit int16, IMAD with full int32 taps otherwise).
     FastPlan plans[kMaxFilters];
     int post = POST_HI16, mac = 0;
-    auto plan_all = [&](auto &&make) {
-        for (int f = 0; f < n_filters; ++f) {
-            plans[f] = make(taps_in + (size_t)f * n_taps);
-            if (!plans[f].ok) return false;
-        }
-        return true;
-    };
-    bool ok = !force_imad && plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, a.frac_bits, a.acc_bits, 32767); });
-    if (ok) {
-        for (int f = 0; f < n_filters; ++f)
-            if (!plans[f].hi16) post = POST_SHIFT;
-        if (post == POST_SHIFT)
-            ok = plan_all([&](const int32_t *t) { return plan_fast(t, n_taps, a.frac_bits, a.acc_bits, 32767, false); });
-    }
-    if (!ok) {
-        post = POST_WRAP;
-        ok = !force_imad && plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, a.frac_bits, a.acc_bits, 32767); });
-        if (!ok && !bucket && n_filters == 1) {
-            mac = 1;
-            ok = plan_all([&](const int32_t *t) { return plan_wrap(t, n_taps, a.frac_bits, a.acc_bits, 0x7fffffff); });
-        }
-    }
+    const bool ok = select_plan(taps_in, n_taps, n_filters, a.frac_bits, a.acc_bits, bucket != 0, force_imad, plans, &post, &mac);
     if (!ok) return 0;
     const FastPlan &f0 = plans[0];
 
@@ -121,6 +132,28 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     if (a.out_dtype == FIRGPU_U8)
         return d2 ? launch_staged_i16_u8_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_i16_u8_d1(p, a.n_taps, post, mac, a.stream);
     return d2 ? launch_staged_i16_i16_d2(p, a.n_taps, post, mac, a.stream) : launch_staged_i16_i16_d1(p, a.n_taps, post, mac, a.stream);
+}
+
+// Host-only query behind firgpu_fir1d_fixed_plan: which datapath would serve these taps on uint8 / int16 containers.
+int plan_fir1d_fixed(const int32_t *hq_host, int n_taps_in, int frac_bits, int acc_bits, int *path, int *post, int *mac)
+{
+    *path = FIRGPU_PATH_GENERIC;
+    *post = *mac = 0;
+    if (n_taps_in < 1 || n_taps_in > kMaxFastTaps || force_generic()) return 0;
+    int n_taps = n_taps_in, bucket = 0;
+    int32_t padded[kMaxFastTaps];
+    const int32_t *taps_in = hq_host;
+    if (n_taps_in > kMaxWideTaps) {
+        for (int b : kLongBuckets)
+            if (!bucket && b >= n_taps_in) bucket = b;
+        const int off = bucket / 2 - n_taps_in / 2;
+        for (int k = 0; k < bucket; ++k) padded[k] = (k >= off && k < off + n_taps_in) ? hq_host[k - off] : 0;
+        taps_in = padded;
+        n_taps = bucket;
+    }
+    FastPlan plans[kMaxFilters];
+    if (select_plan(taps_in, n_taps, 1, frac_bits, acc_bits, bucket != 0, false, plans, post, mac)) *path = FIRGPU_PATH_STAGED;
+    return 0;
 }
 
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host)

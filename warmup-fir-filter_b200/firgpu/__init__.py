@@ -8,7 +8,7 @@ paths (``fir_1d.model.python...``, ``fir_2d...``, ``pipeline_fir_1d``) live next
 package and call into it.  No CPU fallback exists.
 """
 from .ops import (DeviceArray, FirStream, PinnedArray, Recording, compare_metrics, fir1d_fixed, fir1d_fixed_iq,  # noqa: F401
-                  fir1d_fixed_multi, fir1d_fixed_multi_gpu, fir1d_fixed_q, fir1d_ideal, fir2d_fixed, fir2d_fixed_q, fir2d_ideal, record)
+                  fir1d_fixed_multi, fir1d_fixed_multi_gpu, fir1d_fixed_plan, fir1d_fixed_q, fir1d_ideal, fir2d_fixed, fir2d_fixed_q, fir2d_ideal, record)
 
 __all__ = ["DeviceArray", "FirStream", "PinnedArray", "Recording", "compare_metrics", "fir1d_fixed", "fir1d_fixed_q", "fir1d_fixed_iq",
-           "fir1d_fixed_multi", "fir1d_fixed_multi_gpu", "fir1d_ideal", "fir2d_fixed_q", "fir2d_fixed", "fir2d_ideal", "record"]
+           "fir1d_fixed_multi", "fir1d_fixed_multi_gpu", "fir1d_fixed_plan", "fir1d_ideal", "fir2d_fixed_q", "fir2d_fixed", "fir2d_ideal", "record"]

@@ -102,7 +102,12 @@ def _np_container(x, lo: int = 0, hi: int = 255, raw: bool = False) -> np.ndarra
     elif a.dtype.kind in "iu":
         a = np.clip(a, lo, hi).astype(np.uint8 if (lo >= 0 and hi <= 255) else np.int16)
     elif a.dtype.kind == "f":
-        a = a.astype(np.float32 if a.dtype.itemsize < 4 else np.float64)
+        if a.dtype == np.float16 and not raw:
+            # the reference adds 0.5 in the array's own precision (fir_1d_ref.py:37 on np.float16 scalars); the only
+            # value where that differs from exact arithmetic is the largest float16 below 0.5, which ties up to 1.0
+            a = np.where(a == np.float16(0.49975586), np.float32(0.5), a.astype(np.float32))
+        else:
+            a = a.astype(np.float32 if a.dtype.itemsize < 4 else np.float64)
     else:
         raise TypeError(f"unsupported sample dtype {a.dtype}")
     return np.ascontiguousarray(a)
@@ -118,7 +123,10 @@ def _torch_container(t, lo: int = 0, hi: int = 255):
         t = t.to(torch.int16)
     elif t.dtype in (torch.int64,):
         t = t.clamp(lo, hi).to(torch.uint8 if (lo >= 0 and hi <= 255) else torch.int16)
-    elif t.dtype in (torch.float16, torch.bfloat16):
+    elif t.dtype == torch.float16:
+        wide = t.to(torch.float32)                       # (the float16 tie below 0.5, see _np_container)
+        t = torch.where(t == 0.49975586, torch.full_like(wide, 0.5), wide)
+    elif t.dtype == torch.bfloat16:
         t = t.to(torch.float32)
     else:
         raise TypeError(f"unsupported sample dtype {t.dtype}")
@@ -301,6 +309,20 @@ def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int =
         ex = (len(hq) // 2 if centre is None else int(centre),) + in_range + out_range
     return fir1d_fixed_q(x, hq, frac_bits, acc_bits, dilation=dilation, out_dtype=out_dtype, out=out,
                          device=device, halo_left_valid=halo_left_valid, halo_right_valid=halo_right_valid, ex=ex)
+
+
+def fir1d_fixed_plan(h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16) -> dict:
+    """Which datapath would serve these taps on uint8 / int16 samples — answered on the host from the quantised taps
+    alone (``firgpu_fir1d_fixed_plan``): ``{"path": "staged" | "generic", "post": "shift" | "hi16" | "wrap", "mac":
+    "dp2a" | "imad"}``."""
+    quant.validate_taps(h)
+    quant.check_bits(frac_bits, acc_bits, coeff_bits)
+    hq = np.ascontiguousarray(quant.quantize_taps(h, frac_bits, coeff_bits), dtype=np.int32)
+    path, post, mac = C.c_int(0), C.c_int(0), C.c_int(0)
+    _lib.check(_lib.lib().firgpu_fir1d_fixed_plan(_taps_ptr(hq), hq.size, frac_bits, acc_bits, C.byref(path), C.byref(post), C.byref(mac)))
+    staged = path.value == _lib.PATH_STAGED
+    return {"path": "staged" if staged else "generic", "post": ("shift", "hi16", "wrap")[post.value] if staged else None,
+            "mac": ("dp2a", "imad")[mac.value] if staged else None}
 
 
 def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, out_dtype=np.uint8, out=None,
