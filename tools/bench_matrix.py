@@ -31,8 +31,8 @@ PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROO
 REPLAY = False      # --replay: time a recorded sequence (firgpu.Recording, a CUDA graph of the same launches) instead of Python calls
 
 
-def timed(fn, reps, warm=3):
-    if REPLAY:
+def timed(fn, reps, warm=3, recordable=True):
+    if REPLAY and recordable:
         rec = firgpu.Recording(fn)
         fn = rec.replay
     for _ in range(warm):
@@ -250,7 +250,7 @@ def main():
         # fused fixed-vs-ideal metrics: 1 B read per sample, seven numbers out (the call synchronises to return them)
         for hgt, wid in ((64, 64), (2999, 4499), (8192, 16384)):
             x = rand_i16(hgt * wid).clamp(0, 255).to(torch.uint8).view(hgt, wid)
-            s = timed(lambda: firgpu.compare_metrics(x, LP5, validate=False), 5)
+            s = timed(lambda: firgpu.compare_metrics(x, LP5, validate=False), 5, recordable=False)    # (the call synchronises to return its numbers)
             report(f"compare metrics {hgt}x{wid} u8 5tap q4.12 (fixed + ideal + 7 reductions)", s, hgt * wid, 1)
     if "iqideal" in cases:
         z = rand_i16(1 << 27)                      # 2^26 complex samples interleaved
