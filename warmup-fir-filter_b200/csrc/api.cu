@@ -574,6 +574,35 @@ int scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream)
     return 0;
 }
 
+// Extended fixed-point call on device memory (arguments already checked).
+int fir1d_fixed_ex_device(const Fir1dArgs &a, const int32_t *hq, bool fast_only)
+{
+    // Any alignment is the centred filter with zero taps in front of / behind the real ones (a zero tap adds nothing
+    // to the integer sum), so causal and other off-centre filters run on the centred fast kernels too.
+    Fir1dArgs fast = a;
+    int32_t padded[kFastPlanMaxTaps];
+    const int32_t *fast_taps = hq;
+    const int n_taps = a.n_taps, c = a.centre < 0 ? n_taps / 2 : a.centre;
+    if (c != n_taps / 2) {
+        const int reach = std::max(c, n_taps - 1 - c), wide_taps = 2 * reach + 1, off = reach - c;
+        if (wide_taps <= kFastPlanMaxTaps) {
+            for (int k = 0; k < wide_taps; ++k) padded[k] = (k >= off && k < off + n_taps) ? hq[k - off] : 0;
+            fast.n_taps = wide_taps;
+            fast.centre = -1;
+            fast_taps = padded;
+        }
+    }
+    int rc;
+    if (fast.is_reference_model()) {        // the reference's own parameters: the fast kernels apply
+        rc = try_launch_fir1d_fixed_staged(fast, fast_taps);
+    } else {                                // other clamp ranges on int16 containers: wide datapath
+        rc = try_launch_fir1d_fixed_staged_wide(fast, fast_taps);
+    }
+    if (rc != 0 || fast_only) return rc;    // served (1), error, or "no fast kernel applies" for a caller that has its own fallback
+    rc = launch_fir1d_fixed_generic(a, hq);
+    return rc ? rc : 1;
+}
+
 }  // namespace firgpu
 
 using namespace firgpu;
@@ -1126,29 +1155,8 @@ int firgpu_fir1d_fixed_ex(const void *x, void *y, int in_dtype, int out_dtype, i
     a.in_hi = in_hi;
     a.out_lo = out_lo;
     a.out_hi = out_hi;
-    // Any alignment is the centred filter with zero taps in front of / behind the real ones (a zero tap adds nothing
-    // to the integer sum), so causal and other off-centre filters run on the centred fast kernels too.
-    Fir1dArgs fast = a;
-    int32_t padded[kFastPlanMaxTaps];
-    const int32_t *fast_taps = hq;
-    const int c = centre < 0 ? n_taps / 2 : centre;
-    if (c != n_taps / 2) {
-        const int reach = std::max(c, n_taps - 1 - c), wide_taps = 2 * reach + 1, off = reach - c;
-        if (wide_taps <= kFastPlanMaxTaps) {
-            for (int k = 0; k < wide_taps; ++k) padded[k] = (k >= off && k < off + n_taps) ? hq[k - off] : 0;
-            fast.n_taps = wide_taps;
-            fast.centre = -1;
-            fast_taps = padded;
-        }
-    }
-    if (fast.is_reference_model()) {        // the reference's own parameters: the fast kernels apply
-        rc = try_launch_fir1d_fixed_staged(fast, fast_taps);
-    } else {                                // other clamp ranges on int16 containers: wide datapath
-        rc = try_launch_fir1d_fixed_staged_wide(fast, fast_taps);
-    }
-    if (rc == 1) return 0;
-    if (rc != 0) return rc;
-    return launch_fir1d_fixed_generic(a, hq);
+    rc = fir1d_fixed_ex_device(a, hq, false);
+    return rc == 1 ? 0 : rc;
 }
 
 int firgpu_fir1d_ideal_ex(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,

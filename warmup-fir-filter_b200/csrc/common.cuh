@@ -158,6 +158,10 @@ struct Fir1dArgs {
     int in_lo = 0, in_hi = 255;      // sample clamp range
     int out_lo = 0, out_hi = 255;    // output saturation range
     int raw = 0;                     // ideal model only: use samples as they are (no round / clamp)
+    // streaming (rows == 1, fast kernels only): the halo_left scalars in front of x live in `hist`, not in memory before
+    // x; the kernel writes the row's last halo_left scalars to `hist_out` (a different buffer)
+    const void *hist = nullptr;
+    void *hist_out = nullptr;
     int64_t period = 0;              // staged kernel only: this one row is really rows of `period` scalars, each zero-padded
                                      // on its own (a dense row batch filtered in one flattened pass)
     bool is_reference_model() const
@@ -185,6 +189,9 @@ int try_launch_fir1d_ideal_fast(const Fir1dArgs &a, const double *h_host);
 // fir1d_staged.cu — returns 1 when the call was served, 0 when the shape /
 // taps are outside the staged kernel's domain (caller falls to generic), <0 / >0 on error.
 int try_launch_fir1d_fixed_staged(const Fir1dArgs &a, const int32_t *hq_host);
+// the body of firgpu_fir1d_fixed_ex after its argument checks; fast_only: do not fall back to the generic kernel
+// (returns 1 when a fast kernel served the call, 0 when none applies, else an error code)
+int fir1d_fixed_ex_device(const Fir1dArgs &a, const int32_t *hq, bool fast_only);
 // host-only: the datapath that would serve these taps (firgpu_fir1d_fixed_plan)
 int plan_fir1d_fixed(const int32_t *hq_host, int n_taps, int frac_bits, int acc_bits, int *path, int *post, int *mac);
 // wide datapath of the extended entry point (signed int16 ranges); 1 = served, 0 = not eligible

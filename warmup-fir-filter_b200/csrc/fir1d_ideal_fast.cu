@@ -49,8 +49,10 @@ template <typename InT, typename F, int L, int kGroups, bool CAUSAL, int DIL>   
 __global__ void __launch_bounds__(kThreadsI)
 fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t rows, int64_t cols, int64_t ld_x,
                         int64_t ld_y, int64_t tiles_per_row, int64_t total_tiles, TapsF64<L> h, int64_t halo_left,
-                        int64_t halo_right)
+                        int64_t halo_right, const InT *__restrict__ hist, InT *__restrict__ hist_out)
 {
+    // hist (streaming, rows == 1): the halo_left samples in front of column 0 come from this buffer instead of the
+    // memory before x; the warp of the last tile copies the row's tail to hist_out for the next block.
     const int kWarps = (int)(blockDim.x >> 5);           // block size is a launch-time choice (<= kThreadsI)
     constexpr int OP = 16 / (2 * (int)sizeof(F));        // output pairs per group: one 16-byte store (2 doubles / 4 floats)
     constexpr int G = 2 * OP;                            // outputs per group
@@ -61,6 +63,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
     using P2 = typename PairOf<InT>::type;
     const int lane = threadIdx.x & 31;
     const int64_t vlo = -halo_left, vhi = cols + halo_right;
+    const int64_t plo = hist ? 0 : vlo;                  // lowest column that may be loaded from x itself
 
     // w[i] is sample base - 2 PL + i; output base + e reads samples base + e + hi - k, k = 0 .. L-1
     auto filter_group = [&](const F (&w)[2 * NP], F (&a)[G]) {
@@ -110,7 +113,7 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
         const int pad = (int)((reinterpret_cast<uintptr_t>(yr) / sizeof(F)) % G);
         const int64_t col0 = tcol * kTileI - pad;
         const bool x_pairs = (reinterpret_cast<uintptr_t>(xr + col0) & (2 * sizeof(InT) - 1)) == 0;
-        const bool interior = col0 >= 0 && col0 - 2 * PL >= vlo && col0 + kTileI + 2 * PR <= vhi && col0 + kTileI <= cols && x_pairs;
+        const bool interior = col0 >= 0 && col0 - 2 * PL >= plo && col0 + kTileI + 2 * PR <= vhi && col0 + kTileI <= cols && x_pairs;
         if (interior) {
             P2 raw[kGroups][NP];
 #pragma unroll
@@ -140,11 +143,15 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     const int64_t g = n - 2 * PL + 2 * p;
-                    if (x_pairs && g >= vlo && g + 1 < vhi) {
+                    if (x_pairs && g >= plo && g + 1 < vhi) {
                         widen(*reinterpret_cast<const P2 *>(xr + g), w[2 * p], w[2 * p + 1]);
                     } else {
-                        w[2 * p] = (g >= vlo && g < vhi) ? one(xr[g]) : (F)0;
-                        w[2 * p + 1] = (g + 1 >= vlo && g + 1 < vhi) ? one(xr[g + 1]) : (F)0;
+                        auto at = [&](int64_t c) -> F {
+                            if (c < vlo || c >= vhi) return (F)0;
+                            return one((c < 0 && hist) ? hist[c - vlo] : xr[c]);
+                        };
+                        w[2 * p] = at(g);
+                        w[2 * p + 1] = at(g + 1);
                     }
                 }
                 F a[G];
@@ -159,6 +166,8 @@ fir1d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t ro
                 }
             }
         }
+        if (hist_out && tile + 1 == (uint32_t)total_tiles)
+            for (int64_t j = lane; j < halo_left; j += 32) hist_out[j] = xr[cols - halo_left + j];
     }
 }
 
@@ -183,8 +192,10 @@ int run_groups(const Fir1dArgs &a, const double *h_host)
     if (total >= 0xffffffffLL) return 0;                  // (2^41 outputs: not a real case; the generic kernel takes it)
     const int64_t grid = (total + kWarps - 1) / kWarps;
     if (grid > 0x7fffffffLL) return 0;
+    if (a.hist && (a.rows != 1 || a.halo_left < 1 || a.cols < a.halo_left)) return 0;
     fir1d_ideal_fast_kernel<InT, F, L, kGroups, CAUSAL, DIL><<<(unsigned)grid, threads, 0, a.stream>>>(
-        (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right);
+        (const InT *)a.x, (F *)a.y, a.rows, a.cols, a.ld_x, a.ld_y, tiles_per_row, total, h, a.halo_left, a.halo_right,
+        (const InT *)a.hist, (InT *)a.hist_out);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_STAGED);
     return 1;

@@ -111,6 +111,11 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     p.wrap_mul = f0.wrap_mul;
     p.period = a.period;
     p.pdl = 1;
+    if (a.hist) {                              // streaming block: single row, single tap set, history of halo_left scalars
+        if (a.rows != 1 || n_filters != 1 || a.period || a.halo_left < 1 || a.cols < a.halo_left) return 0;
+        p.hist = (const unsigned char *)a.hist;
+        p.hist_out = (unsigned char *)a.hist_out;
+    }
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * es) % 16 == 0);
     const int out_vec = (int)((kChunk / es) * os);           // bytes per vector store: 8, 16 or 32
     const int out_align = out_vec > 16 ? 16 : out_vec;
@@ -193,6 +198,11 @@ int try_launch_fir1d_fixed_staged_wide(const Fir1dArgs &a, const int32_t *hq_hos
     p.halo_right = a.halo_right;
     p.n_filters = 1;
     p.pdl = 1;
+    if (a.hist) {
+        if (a.rows != 1 || a.halo_left < 1 || a.cols < a.halo_left) return 0;
+        p.hist = (const unsigned char *)a.hist;
+        p.hist_out = (unsigned char *)a.hist_out;
+    }
     p.shift = a.frac_bits;
     p.bias = (int)bias;
     p.x_bulk_ok = ((uintptr_t)a.x % 16 == 0) && (a.rows == 1 || (a.ld_x * 2) % 16 == 0);

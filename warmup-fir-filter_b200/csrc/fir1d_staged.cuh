@@ -120,6 +120,10 @@ struct StagedParams {
     int wrap_split;                            // WRAP: use the general split-shift form (frac_bits > acc_bits, or frac + 32 - acc_bits < 2)
     int wrap_mul;                              // WRAP: 2^(acc_bits - frac_bits) (multiply-add form)
     int pdl;                                   // launch with programmatic stream serialisation
+    // streaming (rows == 1): the halo_left scalars in front of column 0 are not in memory before x but in `hist`
+    // (hist[j] is column j - halo_left); the CTA of the last tile copies the row's last halo_left scalars to hist_out
+    const unsigned char *hist;
+    unsigned char *hist_out;
 };
 
 enum { POST_SHIFT = 0, POST_HI16 = 1, POST_WRAP = 2 };
@@ -281,7 +285,7 @@ __device__ __forceinline__ TilePlan plan_tile(const StagedParams &p, long long r
     t.need_hi = t.col0 + (in_tile + G::SC - 1) / G::SC * G::SC + G::PADS;
     if (t.need_hi > g1) t.need_hi = g1;
     constexpr int Q = 16 / G::ES;                 // scalars per 16 bytes
-    long long lo = floor_div(vlo + Q - 1, Q) * Q, hi = floor_div(vhi, Q) * Q;
+    long long lo = floor_div((p.hist ? 0 : vlo) + Q - 1, Q) * Q, hi = floor_div(vhi, Q) * Q;   // (a history buffer is not in front of x)
     if (lo < g0) lo = g0;
     if (hi > t.need_hi) hi = t.need_hi;
     if (!p.x_bulk_ok || hi <= lo) lo = hi = g0;
@@ -635,11 +639,14 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         if (left_end > g0 || t.need_hi > right_begin) {
             const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
             const InT *xrow = reinterpret_cast<const InT *>(p.x) + t.row * p.ld_x;
+            const InT *hist = reinterpret_cast<const InT *>(p.hist);
             InT *sts = reinterpret_cast<InT *>(smem + stage * kStageBytes);
-            for (long long g = g0 + tid; g < left_end; g += kThreads)
-                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
-            for (long long g = right_begin + tid; g < t.need_hi; g += kThreads)
-                sts[g - g0] = (g >= vlo && g < vhi) ? xrow[g] : (InT)0;
+            auto sample = [&](long long g) -> InT {
+                if (g < vlo || g >= vhi) return (InT)0;
+                return (g < 0 && hist) ? hist[g - vlo] : xrow[g];
+            };
+            for (long long g = g0 + tid; g < left_end; g += kThreads) sts[g - g0] = sample(g);
+            for (long long g = right_begin + tid; g < t.need_hi; g += kThreads) sts[g - g0] = sample(g);
             __syncthreads();
         }
         if (has_bulk) {
@@ -719,16 +726,26 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             if (tile_rem >= period) tile_rem -= period;
         }
     }
+    // streaming: the next block's history = this block's tail (written to the OTHER history buffer: the CTA of the
+    // first tile may still be reading the current one)
+    if (p.hist_out && (long long)blockIdx.x == (p.total_tiles - 1) % gridDim.x) {
+        const InT *xrow = reinterpret_cast<const InT *>(p.x);
+        InT *out = reinterpret_cast<InT *>(p.hist_out);
+        for (long long j = tid; j < p.halo_left; j += kThreads) out[j] = xrow[p.cols - p.halo_left + j];
+    }
 }
 
 // Per-process launch knobs, read once (getenv walks the whole environment; a launch should not).
 struct LaunchEnv {
     int ctas_per_sm = 0;       // FIRGPU_CTAS_PER_SM: cap on resident CTAs per SM (profiling runs)
     bool pdl = true;           // FIRGPU_NO_PDL=1 launches without programmatic stream serialisation (A/B runs)
+    int pdl_max_tiles = 16;    // FIRGPU_PDL_MAX_TILES: largest launch (tiles per CTA) that carries the attribute (measured: 4 -> 16 tiles
+                               // lifts back-to-back 2^24 / 2^25-sample passes from 0.91 / 0.86 to 0.96 / 0.89 of the HBM peak; 110 tiles lose 1 %)
     LaunchEnv()
     {
         if (const char *e = getenv("FIRGPU_CTAS_PER_SM")) ctas_per_sm = atoi(e);
         if (const char *e = getenv("FIRGPU_NO_PDL")) pdl = !(e[0] == '1');
+        if (const char *e = getenv("FIRGPU_PDL_MAX_TILES")) pdl_max_tiles = atoi(e);
     }
 };
 inline const LaunchEnv &launch_env()
@@ -802,9 +819,9 @@ int launch_cfg(const StagedParams &p_in, cudaStream_t stream)
         p.rem_tile_step = (uint32_t)((unsigned long long)(grid * ts) % (unsigned long long)p.period);
         p.rem_sub_step = (uint32_t)((unsigned long long)(C::kThreads * G::SC) % (unsigned long long)p.period);
     }
-    // Programmatic stream serialisation only for launches of a few tiles per CTA (about 20 microseconds or less), where
+    // Programmatic stream serialisation only for launches of at most pdl_max_tiles tiles per CTA (about 30 microseconds), where
     // the launch latency it hides is a visible share; long kernels measured 1 % slower with it.
-    const bool pdl = env.pdl && p.pdl && p.total_tiles <= 4 * grid;
+    const bool pdl = env.pdl && p.pdl && p.total_tiles <= (long long)env.pdl_max_tiles * grid;
     FIRGPU_CUDA(launch_pdl(kern, (unsigned)grid, C::kThreads, kSmem, stream, pdl, p));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;

@@ -26,6 +26,8 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+
 namespace firgpu {
 namespace tiled {
 
@@ -452,8 +454,37 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     if (grid > p.total_items) grid = p.total_items;
     // a few items per CTA (a row-band shard of an 8-GPU plan, a small image): hide the launch latency behind the
     // previous kernel's tail; long launches gain nothing from it
-    const bool pdl = staged::launch_env().pdl && p.total_items <= 8 * grid;
-    FIRGPU_CUDA(staged::launch_pdl(kern, (unsigned)grid, kBlock2, G::SMEM, stream, pdl, map, p));
+    // Band height.  Items (band x strip x image) are dealt to the persistent CTAs in rounds; with only a few rounds —
+    // a row-band shard of an 8-GPU plan — a part-filled last round costs up to 20 %.  Choose the stages per item
+    // (band = stages * BH - (KH - 1) output rows) that loses least to a part-filled round, to the KH - 1 rows every item
+    // loads without producing output, and to a short last band; plenty of rounds keep the default (about 64 rows).
+    TiledParams q = p;
+    if (p.total_items < 16 * (long long)sms * per_sm) {
+        double best = -1.0;
+        for (int spi = 2; spi <= 16; ++spi) {
+            const int band = spi * G::BH - (KH - 1);
+            if (band < 1) continue;
+            const long long bands = (p.height + band - 1) / band;
+            const long long items = bands * p.n_strips * (long long)p.n_img;
+            const long long g = std::min<long long>((long long)sms * per_sm, items);
+            const double rounds = (double)((items + g - 1) / g);
+            // cost model: every item walks spi stages whatever it holds; useful work = output rows
+            const double useful = (double)p.height * p.n_strips * p.n_img / (double)G::BH;      // stages of output rows
+            const double spent = rounds * g * spi;
+            const double eff = useful / spent;
+            if (eff > best) {
+                best = eff;
+                q.stages_per_item = spi;
+                q.band_rows = band;
+                q.n_bands = (int)bands;
+                q.total_items = (int)items;
+            }
+        }
+        grid = (long long)sms * per_sm;
+        if (grid > q.total_items) grid = q.total_items;
+    }
+    const bool pdl = staged::launch_env().pdl && q.total_items <= 8 * grid;
+    FIRGPU_CUDA(staged::launch_pdl(kern, (unsigned)grid, kBlock2, G::SMEM, stream, pdl, map, q));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
 }

@@ -2,10 +2,14 @@
 // between blocks in HBM — what reg_ is in the reference's C++ class (fir_1d/model/cpp/fir_1d_ref.cpp:16-33,
 // Fir1D::process_sample shifts reg_ and sums h[k] * reg_[k], i.e. y[n] = sum_k h[k] x[n-k]).
 //
-// A block is filtered where it lies (device memory of the caller): one pass of the ordinary causal kernels with a
-// zero history computes every output, then ONE small kernel (a) rewrites the first (taps-1)*dilation outputs, whose
-// windows reach into the previous block, from the saved history and (b) replaces the history by the block's tail.
-// Nothing is concatenated or copied; blocks no longer than the history are served by the small kernel alone.
+// A block is filtered where it lies (device memory of the caller).  Fast kernels (staged fixed-point kernel, register
+// kernel of the raw float64 model) read the history themselves: the scalars in front of column 0 come from the history
+// buffer, and the CTA of the last tile writes the block's tail to the OTHER of two history buffers (the CTA of the
+// first tile may still be reading the current one) — ONE launch per block.  Everything else: one pass of the ordinary
+// causal kernels with a zero history computes every output, then one small kernel (a) rewrites the first
+// (taps-1)*dilation outputs, whose windows reach into the previous block, from the saved history and (b) replaces the
+// history by the block's tail.  Nothing is concatenated or copied; blocks no longer than the history are served by
+// the small kernel alone.
 // Host blocks travel through a chunked H2D -> filter -> D2H pipeline whose filter steps are chained by events
 // (the history makes consecutive chunks dependent; their copies still overlap).
 #include "common.cuh"
@@ -29,7 +33,10 @@ struct StreamState {
     std::vector<int32_t> hq;
     std::vector<double> h;
     int64_t hist = 0;                              // history scalars: (n_taps - 1) * dilation
-    void *d_state = nullptr, *d_taps = nullptr;
+    void *d_state = nullptr, *d_taps = nullptr;    // d_state: two history buffers of `hist` scalars; `cur` is the live one
+    int cur = 0;
+    size_t state_stride = 0;                       // bytes between the two buffers
+    void *state(int which) const { return (char *)d_state + (size_t)which * state_stride; }
     std::mutex mu;
     // host pipeline (created on first use)
     cudaStream_t hs[kHostSlots] = {};
@@ -92,7 +99,7 @@ int launch_head(StreamState *s, const void *x, void *y, int64_t n, cudaStream_t 
 {
     if (s->hist == 0) return 0;
     stream_head_kernel<InT, OutT, FIXED><<<1, kHeadThreads, (size_t)s->hist * sizeof(InT), stream>>>(
-        (const InT *)x, (OutT *)y, (InT *)s->d_state, (long long)n, (int)s->hist, s->d_taps, s->n_taps, s->dilation, s->frac_bits,
+        (const InT *)x, (OutT *)y, (InT *)s->state(s->cur), (long long)n, (int)s->hist, s->d_taps, s->n_taps, s->dilation, s->frac_bits,
         s->acc_bits, s->in_lo, s->in_hi, s->out_lo, s->out_hi, s->raw);
     FIRGPU_CUDA(cudaGetLastError());
     note_launch(FIRGPU_PATH_GENERIC);
@@ -142,7 +149,34 @@ struct DeviceScope {
 int process_device(StreamState *s, const void *x, void *y, int64_t n, cudaStream_t stream)
 {
     int rc = 0;
-    if (n > s->hist) {       // every output with a zero history; the first `hist` of them are rewritten below
+    if (n > s->hist) {
+        // one launch: a fast kernel that reads the history buffer and leaves the next one behind.  Not while the stream
+        // is being recorded: which of the two buffers is live is host state, and a replayed sequence must find the
+        // history where it left it — the two-launch form below keeps it in one buffer.
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) {
+            cudaGetLastError();
+            capturing = cudaStreamCaptureStatusNone;
+        }
+        if (s->hist > 0 && capturing == cudaStreamCaptureStatusNone) {
+            Fir1dArgs a{x, y, s->in_dtype, s->out_dtype, 1, n, n, n, s->n_taps, s->dilation, s->frac_bits, s->acc_bits,
+                        s->hist, 0, stream};
+            a.centre = 0;
+            a.in_lo = s->in_lo;
+            a.in_hi = s->in_hi;
+            a.out_lo = s->out_lo;
+            a.out_hi = s->out_hi;
+            a.raw = s->raw;
+            a.hist = s->state(s->cur);
+            a.hist_out = s->state(s->cur ^ 1);
+            rc = s->fixed ? fir1d_fixed_ex_device(a, s->hq.data(), true) : try_launch_fir1d_ideal_fast(a, s->h.data());
+            if (rc == 1) {
+                s->cur ^= 1;
+                return 0;
+            }
+            if (rc != 0) return rc;
+        }
+        // no fast kernel for these parameters: every output with a zero history; the first `hist` of them are rewritten below
         if (s->fixed)
             rc = firgpu_fir1d_fixed_ex(x, y, s->in_dtype, s->out_dtype, 1, n, n, n, s->hq.data(), s->n_taps, s->dilation, s->frac_bits,
                                        s->acc_bits, 0, 0, 0, s->in_lo, s->in_hi, s->out_lo, s->out_hi, (void *)stream);
@@ -210,7 +244,8 @@ int create_common(firgpu_stream_t *out, StreamState *s, const void *taps, size_t
         delete s;
         return rc;
     }
-    const size_t state_bytes = (size_t)std::max<int64_t>(s->hist, 1) * dtype_size(s->in_dtype);
+    s->state_stride = ((size_t)std::max<int64_t>(s->hist, 1) * dtype_size(s->in_dtype) + 255) / 256 * 256;
+    const size_t state_bytes = 2 * s->state_stride;
     cudaError_t e = cudaMalloc(&s->d_state, state_bytes);
     if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, state_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_taps, tap_bytes);
@@ -393,7 +428,7 @@ int firgpu_stream_reset(firgpu_stream_t handle, void *stream)
     DeviceScope scope;
     int rc = scope.enter(s->device);
     if (rc) return rc;
-    if (s->hist) FIRGPU_CUDA(cudaMemsetAsync(s->d_state, 0, (size_t)s->hist * dtype_size(s->in_dtype), (cudaStream_t)stream));
+    if (s->hist) FIRGPU_CUDA(cudaMemsetAsync(s->state(s->cur), 0, (size_t)s->hist * dtype_size(s->in_dtype), (cudaStream_t)stream));
     return 0;
 }
 
