@@ -217,10 +217,9 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // Programmatic dependent launch (small launches only, see launch_tiled_one): the prologue above overlapped the
-    // previous kernel's tail; nothing below may touch global memory before that kernel has completed.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (No programmatic dependent launch here: measured on row-band shards of the 8- and 4-GPU plans it changes nothing for
+    // the 5-row kernels and costs 15-20 % for 3x3 int16, whose resident CTAs per SM are capped below the occupancy limit —
+    // the next grid's CTAs then land unevenly in the free slots.  profiles/r2_shard2d_stages_per_item_{pdl,nopdl}.jsonl)
 
     // item -> (image, band, strip); consecutive items are neighbouring strips of
     // one band, so bands that share halo rows are processed at the same time
@@ -458,10 +457,14 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     // a row-band shard of an 8-GPU plan — a part-filled last round costs up to 20 %.  Choose the stages per item
     // (band = stages * BH - (KH - 1) output rows) that loses least to a part-filled round, to the KH - 1 rows every item
     // loads without producing output, and to a short last band; plenty of rounds keep the default (about 64 rows).
+    // Measured on the [4, 2048, 16384] int16 shard (config 4 at N = 8): 3x3 0.856 (default 8 stages) -> 0.917, rank-1 5x5
+    // 0.741 -> 0.774 of the HBM peak; the model is coarse (the best forced value reaches 0.93 / 0.82).
     TiledParams q = p;
-    if (p.total_items < 16 * (long long)sms * per_sm) {
+    int spi_lo = 2, spi_hi = 16;
+    if (const char *e = getenv("FIRGPU_T2_SPI")) spi_lo = spi_hi = atoi(e);      // experiments: force the stages per item
+    if (p.total_items < 16 * (long long)sms * per_sm || spi_lo == spi_hi) {
         double best = -1.0;
-        for (int spi = 2; spi <= 16; ++spi) {
+        for (int spi = spi_lo; spi <= spi_hi; ++spi) {
             const int band = spi * G::BH - (KH - 1);
             if (band < 1) continue;
             const long long bands = (p.height + band - 1) / band;
@@ -483,8 +486,7 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
         grid = (long long)sms * per_sm;
         if (grid > q.total_items) grid = q.total_items;
     }
-    const bool pdl = staged::launch_env().pdl && q.total_items <= 8 * grid;
-    FIRGPU_CUDA(staged::launch_pdl(kern, (unsigned)grid, kBlock2, G::SMEM, stream, pdl, map, q));
+    FIRGPU_CUDA(staged::launch_pdl(kern, (unsigned)grid, kBlock2, G::SMEM, stream, false, map, q));
     note_launch(FIRGPU_PATH_STAGED);
     return 1;
 }
