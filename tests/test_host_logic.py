@@ -245,7 +245,7 @@ def test_segment_plan_halos():
         shard.plan_segments(100, 2, 5, 2, align=3)
     bands = shard.plan_bands(16384, 8, 5)
     assert bands[0].before == 0 and bands[0].after == 2 and bands[7].after == 0 and bands[3].lo == 3 * 2048 - 2
-    assert shard.aligned_lead(2, 2) == 8 and shard.aligned_lead(0, 2) == 0 and shard.aligned_lead(4, 1) == 16
+    assert shard.aligned_lead(2, 2) == 128 and shard.aligned_lead(0, 2) == 0 and shard.aligned_lead(4, 1) == 256      # 256-byte boundaries
 
 
 def test_sharded_result_equals_whole_signal_on_cpu():
