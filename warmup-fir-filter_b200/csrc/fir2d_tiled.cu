@@ -16,18 +16,38 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 EncodeTiledFn encode_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!fn) {
+    static const EncodeTiledFn fn = [] {            // resolved once (thread-safe static initialisation)
         void *ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
+            return (EncodeTiledFn)ptr;
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
+
+// Encoded tensor maps, per host thread: a map depends only on (base, dims, strides, box rows), and callers filter the
+// same buffers again and again (a row-band shard per step, the same image with several kernels); encoding costs a
+// driver call per launch otherwise.  Eight entries, round robin.
+struct MapKey {
+    const void *base;
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box_rows;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && dims[0] == o.dims[0] && dims[1] == o.dims[1] && dims[2] == o.dims[2] && strides[0] == o.strides[0] &&
+               strides[1] == o.strides[1] && box_rows == o.box_rows;
+    }
+};
+struct MapCache {
+    static constexpr int kEntries = 8;
+    MapKey key[kEntries] = {};
+    CUtensorMap map[kEntries];
+    bool used[kEntries] = {};
+    int next = 0;
+};
+thread_local MapCache tl_maps;
 
 long long gcd_ll(long long a, long long b)
 {
@@ -149,17 +169,31 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     p.y_vec_ok = ((uintptr_t)a.y % va == 0) && (a.ld_y * os) % va == 0 && (a.n_img == 1 || (a.img_stride_y * os) % va == 0);
 
     const long long map_rows = a.halo_top + a.height + a.halo_bottom;
-    CUtensorMap map;
     cuuint64_t dims[3] = {(cuuint64_t)(map_w * es / kMapElemBytes), (cuuint64_t)map_rows, (cuuint64_t)a.n_img};
     cuuint64_t strides[2] = {(cuuint64_t)(a.ld_x * es),
                              (cuuint64_t)((a.n_img > 1 ? a.img_stride_x : map_rows * a.ld_x) * es)};
     cuuint32_t box[3] = {(cuuint32_t)kBoxElems, (cuuint32_t)bh, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     void *base = (void *)((const unsigned char *)a.x - a.halo_top * a.ld_x * es);
-    const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims,
-                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 0;                          // shape the TMA cannot describe: generic kernel
+    const MapKey key{base, {dims[0], dims[1], dims[2]}, {strides[0], strides[1]}, box[1]};
+    MapCache &cache = tl_maps;
+    int slot = -1;
+    for (int i = 0; i < MapCache::kEntries; ++i)
+        if (cache.used[i] && cache.key[i] == key) slot = i;
+    if (slot < 0) {
+        slot = cache.next;
+        const CUresult r = encode(&cache.map[slot], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims,
+                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {                              // shape the TMA cannot describe: generic kernel
+            cache.used[slot] = false;
+            return 0;
+        }
+        cache.key[slot] = key;
+        cache.used[slot] = true;
+        cache.next = (slot + 1) % MapCache::kEntries;
+    }
+    const CUtensorMap &map = cache.map[slot];
 
     if (narrowing) return launch_tiled_i16u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
     return es == 1 ? launch_tiled_u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream)

@@ -82,6 +82,15 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+def _raw_stream(torch, device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` as an integer.  torch.cuda.current_stream() builds a
+    Stream object per call (about 7 microseconds); the raw accessor is what launch-latency-sensitive callers use."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:                      # an older / newer torch without the private accessor
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 def _np_container(x, lo: int = 0, hi: int = 255, raw: bool = False) -> np.ndarray:
     """Any host input -> C-contiguous array in one of the five containers the
     kernels read.  Integer types the kernels do not read are clamped here to
@@ -161,6 +170,14 @@ def _cuda_rows(x, allow_copy: bool, lo: int = 0, hi: int = 255):
     anything else is made contiguous, which is only legal without halos."""
     import torch
     native = x.dtype in (torch.uint8, torch.int16, torch.int32, torch.float32, torch.float64)
+    if native and x.is_contiguous():                       # the common case first: no stride arithmetic
+        shape = x.shape
+        if len(shape) == 1:
+            return x, 1, int(shape[0]), int(shape[0])
+        if len(shape) == 2:
+            return x, int(shape[0]), int(shape[1]), int(shape[1])
+        rows, cols = _rows_cols(shape)
+        return x, rows, cols, cols
     if native and x.dim() == 1 and (x.stride(0) == 1 or x.shape[0] <= 1):
         return x, 1, int(x.shape[0]), int(x.shape[0])
     if native and x.dim() == 2 and (x.stride(1) == 1 or x.shape[1] <= 1) and (x.stride(0) >= x.shape[1] or x.shape[0] <= 1):
@@ -258,8 +275,9 @@ def _imgs(shape) -> tuple[int, int, int]:
     return n, int(shape[-2]), int(shape[-1])
 
 
-def _taps_ptr(arr: np.ndarray):
-    return arr.ctypes.data_as(C.c_void_p)
+def _taps_ptr(arr: np.ndarray) -> int:
+    """Address of a (contiguous, caller-kept-alive) tap array; ctypes converts the integer for a c_void_p argument."""
+    return arr.__array_interface__["data"][0]
 
 
 # ---------------------------------------------------------------------------
@@ -355,7 +373,7 @@ def fir1d_fixed_q(x, hq, frac_bits: int, acc_bits: int, *, dilation: int = 1, ou
         if (y_rows, y_cols) != (rows, cols):
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             if ex is None:
                 _lib.check(L.firgpu_fir1d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), _OUT_FIXED[np.dtype(out_dtype)],
                                                 rows, cols, ld, ld_y, _taps_ptr(hq), hq.size, dilation, frac_bits,
@@ -414,7 +432,7 @@ def fir1d_ideal(x, h, *, dilation: int = 1, out_dtype=np.float64, out=None, devi
         if (y_rows, y_cols) != (rows, cols):
             raise ValueError(f"out has shape {tuple(y.shape)}, expected {tuple(x.shape)}")
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             if ex is None:
                 _lib.check(L.firgpu_fir1d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, rows, cols, ld, ld_y,
                                                 _taps_ptr(hh), hh.size, dilation, halo_left_valid, halo_right_valid, stream))
@@ -480,7 +498,7 @@ def compare_metrics(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: i
         import torch
         t, rows, cols, ld = _cuda_rows(x, allow_copy=True)
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             _lib.check(L.firgpu_fir1d_compare(t.data_ptr(), _torch_code(t), rows, cols, ld, _taps_ptr(hq), _taps_ptr(hh),
                                               hq.size, frac_bits, acc_bits, out.ctypes.data, stream))
     else:
@@ -539,7 +557,7 @@ def fir2d_fixed_q(x, hq2d, frac_bits: int, acc_bits: int, *, out_dtype=np.uint8,
         if not y.is_contiguous() or tuple(y.shape) != tuple(t.shape):
             raise ValueError("out must be a contiguous tensor of the input's shape")
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             _lib.check(L.firgpu_fir2d_fixed(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, wid,
                                             img_stride, hgt * wid, _taps_ptr(hq), kh, kw, frac_bits, acc_bits,
                                             halo_top_valid, halo_bottom_valid, stream))
@@ -592,7 +610,7 @@ def fir1d_fixed_multi(x, h_sets, frac_bits: int = 12, acc_bits: int = 32, coeff_
         stride = -(-n // 256) * 256
         flat = torch.empty(nf * stride, dtype=_torch_dtype(out_dtype), device=x.device)
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             _lib.check(L.firgpu_fir1d_fixed_multi(t.data_ptr(), flat.data_ptr(), _torch_code(t), out_code, rows, cols, ld,
                                                   cols, stride, _taps_ptr(hq), nf, n_taps, 1, frac_bits, acc_bits,
                                                   stream))
@@ -640,7 +658,7 @@ def fir2d_ideal(x, h2d, *, out_dtype=np.float64, out=None, device: int = -1, val
             raise ValueError(f"out must be a CUDA {np.dtype(out_dtype)} tensor of the input's shape")
         _, _, _, ld_y, img_stride_y = _cuda_imgs(y, "out")
         with _on_device(torch, x.device):
-            stream = torch.cuda.current_stream(x.device).cuda_stream
+            stream = _raw_stream(torch, x.device)
             _lib.check(L.firgpu_fir2d_ideal(t.data_ptr(), y.data_ptr(), _torch_code(t), out_code, n, hgt, wid, ld, ld_y,
                                             img_stride, img_stride_y, _taps_ptr(hh), kh, kw, halo_top_valid,
                                             halo_bottom_valid, stream))
@@ -735,7 +753,7 @@ class FirStream:
                 raise ValueError("out must be a contiguous tensor of the block's shape")
             with _on_device(torch, x.device):
                 _lib.check(L.firgpu_stream_process(self._h, x.data_ptr(), y.data_ptr(), x.numel(),
-                                                   torch.cuda.current_stream(x.device).cuda_stream))
+                                                   _raw_stream(torch, x.device)))
             return y
         a = np.ascontiguousarray(x.numpy() if _is_torch(x) else x, dtype=self.in_dtype).reshape(-1)
         y = _host_out(out, a.shape, self.out_dtype)
