@@ -515,9 +515,9 @@ int out_size_fixed(int out_dtype) { return out_dtype == FIRGPU_U8 ? 1 : out_dtyp
 // row keeps its own zero padding (fir_1d/sim/vector/gen_fixed_output.py:44-59).  One launch.
 // Rows wider than kFlattenMaxBytes with a 16-byte aligned pitch stay on the per-row paths (row-streaming tensor-map
 // kernel up to 8 KiB, per-row tile walk beyond), which carry no per-chunk boundary test.  Measured, int16, 2^27 samples,
-// fraction of the HBM peak, flattened / per-row: 128 B rows 0.66 / 0.15, 256 B 0.66 / 0.30, 512 B 0.66 / 0.55,
-// 1 KiB 0.66 / 0.79, 2 KiB 0.69 / 0.70, 4 KiB 0.83 / 0.85, 8 KiB 0.89 / 0.92, 2 MiB 0.98 / 1.02 (profiles/README.md).
-constexpr long kFlattenMaxBytes = 512;
+// fraction of the HBM peak, in-kernel row ends / per-row paths: 128 B rows 0.81 / 0.15, 256 B 0.81 / 0.30, 512 B 0.81 / 0.55,
+// 1 KiB 0.81 / 0.81, 2 KiB 0.85 / 0.68, 4 KiB 0.88 / 0.85, 8 KiB 0.83 / 0.96, 2 MiB 0.98 / 1.02 (profiles/README.md R2.4).
+constexpr long kFlattenMaxBytes = 4096;
 
 bool flatten_ok(const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
                 int n_taps, int dilation)

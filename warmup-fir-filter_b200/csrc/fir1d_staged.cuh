@@ -76,10 +76,13 @@ template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<256, 4, 2, 2, 2>
 // Rows shorter than two long-row tiles: 8 KiB tiles, three CTAs per SM.
 using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
 // Flattened batches (row ends inside the kernel, RE = true).
-#ifndef FIRGPU_FLAT_CFG
-#define FIRGPU_FLAT_CFG 256, 4, 2, 2, 2
+#ifndef FIRGPU_FLAT_SUB
+#define FIRGPU_FLAT_SUB 6             // 16-byte sub-steps per thread per tile (tile = 4 KiB x this); measured 4 / 6 / 8: 0.77 / 0.81 / 0.80
 #endif
-using FlatCfg = Cfg<FIRGPU_FLAT_CFG>;
+#ifndef FIRGPU_FLAT_CTAS
+#define FIRGPU_FLAT_CTAS 2
+#endif
+using FlatCfg = Cfg<256, FIRGPU_FLAT_SUB, 2, FIRGPU_FLAT_CTAS, FIRGPU_FLAT_CTAS>;
 // WRAP post mode on long rows: the post stage costs about four more instructions per sample, and with the eight
 // warps per SM of the int16 long-row configuration the kernel becomes latency-bound (ncu: issue 41 %, DRAM 62 %);
 // the same 64 KiB in flight per SM as two CTAs of 16 KiB tiles.
@@ -626,19 +629,33 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             lane_rem = (uint32_t)(tid * G::SC) % period;
         }
     }
+    // Interior tiles — the bulk copy covers the whole stage and the tile lies wholly inside the row — need no plan: the
+    // two bounds below (first / last column a whole-stage bulk copy may touch) are loop invariants.  Everything else
+    // (row ends, shard seams, unaligned rows) takes the general plan.  Used where the per-tile plan is a visible share
+    // of the instruction stream (smaller tiles, heavier post stage): A/B on one box, fraction of the HBM peak with /
+    // without — WRAP post 0.986 / 0.936, IMAD 0.885 / 0.817, row ends 0.77 / 0.70, I/Q 0.978 / 0.961; the plain long-row
+    // kernels schedule worse with it (int16 -> int16 0.990 / 1.000, int16 -> uint8 0.938 / 0.995) and keep the plan.
+    constexpr bool kInteriorFast = RE || POST == POST_WRAP || MAC == 1 || DIL == 2;
+    constexpr int Q16 = 16 / G::ES;
+    const long long bulk_first = floor_div((p.hist ? 0 : -p.halo_left) + Q16 - 1, Q16) * Q16;
+    const long long bulk_last = floor_div(p.cols + p.halo_right, Q16) * Q16;
     for (long long i = 0; i < n_my; ++i) {
-        const TilePlan t = plan_tile<G, TS>(p, c_row, c_tcol);
-        const long long g0 = t.col0 - G::PADS;
+        const long long col0 = (long long)c_tcol * TS;
+        const long long g0 = col0 - G::PADS;
         const uint32_t st_base = smem_base + stage * kStageBytes;
+        const bool interior = kInteriorFast && p.x_bulk_ok && g0 >= bulk_first && col0 + TS + G::PADS <= bulk_last && col0 + TS <= p.cols;
+        bool has_bulk = true;
+        if (!interior) {
+        const TilePlan t = plan_tile<G, TS>(p, c_row, c_tcol);
 
         // Patch what the bulk copy does not cover: zero padding outside the
         // readable range, and everything when the row is not 16-byte aligned.
-        const bool has_bulk = t.bulk_hi > t.bulk_lo;
+        has_bulk = t.bulk_hi > t.bulk_lo;
         const long long left_end = has_bulk ? t.bulk_lo : t.need_hi;
         const long long right_begin = has_bulk ? t.bulk_hi : t.need_hi;
         if (left_end > g0 || t.need_hi > right_begin) {
             const long long vlo = -p.halo_left, vhi = p.cols + p.halo_right;
-            const InT *xrow = reinterpret_cast<const InT *>(p.x) + t.row * p.ld_x;
+            const InT *xrow = reinterpret_cast<const InT *>(p.x) + c_row * p.ld_x;
             const InT *hist = reinterpret_cast<const InT *>(p.hist);
             InT *sts = reinterpret_cast<InT *>(smem + stage * kStageBytes);
             auto sample = [&](long long g) -> InT {
@@ -648,6 +665,7 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
             for (long long g = g0 + tid; g < left_end; g += kThreads) sts[g - g0] = sample(g);
             for (long long g = right_begin + tid; g < t.need_hi; g += kThreads) sts[g - g0] = sample(g);
             __syncthreads();
+        }
         }
         if (has_bulk) {
             mbar_wait(bar_base + 8 * stage, (phase_bits >> stage) & 1u);
@@ -666,7 +684,7 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
         __syncthreads();
         if (tid == 0 && i + kStages < n_my) issue();
 
-        OutT *ythread = reinterpret_cast<OutT *>(p.y) + t.row * p.ld_y + t.col0 + tid * G::SC;
+        OutT *ythread = reinterpret_cast<OutT *>(p.y) + c_row * p.ld_y + col0 + tid * G::SC;
         uint32_t r_chunk = 0;                              // row position of chunk u = 0; advanced per chunk below
         if constexpr (kRowEnds) {
             r_chunk = tile_rem + lane_rem;
@@ -704,12 +722,12 @@ fir1d_staged_kernel(const __grid_constant__ StagedParams p)
                 }
             }
         };
-        if (p.y_vec_ok && t.col0 + TS <= p.cols) {
+        if (p.y_vec_ok && col0 + TS <= p.cols) {
             // whole tile inside the row: no per-chunk bounds logic at all
 #pragma unroll
             for (int u = 0; u < kSub; ++u) do_chunk(u, true, G::SC);
         } else {
-            const long long left = p.cols - t.col0 - tid * G::SC;      // scalars from this thread's first chunk to the row end
+            const long long left = p.cols - col0 - tid * G::SC;      // scalars from this thread's first chunk to the row end
 #pragma unroll
             for (int u = 0; u < kSub; ++u) {
                 const long long room = left - u * (kThreads * G::SC);
