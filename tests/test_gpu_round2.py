@@ -513,3 +513,43 @@ def test_mismatched_out_tensors_are_rejected_before_the_kernel_writes(fg, torch)
                                                             out_range=full, out_dtype=np.int16))
     with pytest.raises(ValueError, match="out must be"):
         fg.fir1d_fixed(fg.DeviceArray(xs.data_ptr(), (xs.numel(),), np.int16), [0.5], out=fg.DeviceArray(ys.data_ptr(), (5,), np.int16))
+
+
+def test_fir2d_live_wrap_runs_on_the_tensor_map_kernel(fg, torch):
+    """The 2-D model inherits the 1-D post stage (wrap to acc_bits once per pixel, bias not re-wrapped): narrow
+    accumulators are served by the tensor-map kernel's WRAP post mode — general, rank-1 and single-row / single-column
+    windows, uint8 / int16 pixels, both outputs, band shards with halo rows — bit-exact against the oracle."""
+    from firgpu import _lib, quant, shard
+    rng = np.random.default_rng(71)
+    kernels = {"3x3": rng.uniform(-0.9, 0.9, size=(3, 3)), "5x5": rng.uniform(-0.5, 0.5, size=(5, 5)),
+               "5x5 rank-1": np.outer([0.9, -0.7, 0.8, 0.3, -0.2], [0.5, 0.9, -0.8, 0.7, 0.4]), "3x5": rng.uniform(-0.6, 0.6, size=(3, 5)),
+               "5x1": rng.uniform(-0.9, 0.9, size=(5, 1)), "1x5": rng.uniform(-0.9, 0.9, size=(1, 5))}
+    n_live = 0
+    for dtype in (np.uint8, np.int16):
+        img = signal(rng, (2, 150, 1000), dtype, wild=0.03)
+        it = torch.from_numpy(img).cuda()
+        for name, k in kernels.items():
+            for acc_bits in (12, 16, 20):
+                hq = quant.quantize_taps(k, 12, 16)
+                n_live += 255 * int(np.abs(hq).sum()) >= 2 ** (acc_bits - 1)
+                for out_dtype in ((np.uint8, np.int16) if dtype == np.int16 else (np.uint8,)):
+                    got = fg.fir2d_fixed(it, k.tolist(), 12, acc_bits, 16, out_dtype=out_dtype)
+                    assert _lib.last_path() == _lib.PATH_STAGED, (dtype, name, acc_bits, out_dtype)
+                    assert np.array_equal(got.cpu().numpy(), onp.fir2d_fixed(img, k.tolist(), 12, acc_bits, 16, out_dtype=out_dtype)), (dtype, name, acc_bits)
+    assert n_live >= 20
+    k = kernels["5x5"]
+    hq = quant.quantize_taps(k, 12, 16)
+    img = signal(rng, (1, 300, 640), np.int16)
+    want = onp.fir2d_fixed(img, k.tolist(), 12, 16, 16, out_dtype=np.int16)
+    it = torch.from_numpy(img).cuda()
+    for band in shard.plan_bands(300, 3, 5):
+        got = fg.fir2d_fixed_q(it[:, band.lo:band.hi, :][:, band.before:band.before + band.size, :], hq, 12, 16, out_dtype=np.int16,
+                               halo_top_valid=band.before, halo_bottom_valid=band.after)
+        assert np.array_equal(got.cpu().numpy(), want[:, band.start:band.stop, :]), band.start
+    # short pitched rows of a 1-D batch under a live wrap: the row-streaming form of the same kernel
+    rows = signal(rng, (64, 3008), np.int16)
+    view = torch.from_numpy(rows).cuda()[:, :3000]
+    h = [0.9, -0.7, 0.8, 0.3, -0.2]
+    got = fg.fir1d_fixed(view, h, 12, 16, 16, out_dtype=np.int16)
+    assert _lib.last_path() == _lib.PATH_STAGED
+    assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(rows[:, :3000], h, 12, 16, 16, out_dtype=np.int16))

@@ -18,8 +18,8 @@ int check_cuda(cudaError_t e, const char *what)
 }
 void note_launch(int) {}
 namespace tiled {
-int launch_tiled_u8(const CUtensorMap &, const TiledParams &, int, int, bool, bool, cudaStream_t) { return 0; }
-int launch_tiled_i16u8(const CUtensorMap &, const TiledParams &, int, int, bool, bool, cudaStream_t) { return 0; }
+int launch_tiled_u8(const CUtensorMap &, const TiledParams &, int, int, int, bool, cudaStream_t) { return 0; }
+int launch_tiled_i16u8(const CUtensorMap &, const TiledParams &, int, int, int, bool, cudaStream_t) { return 0; }
 }
 }  // namespace firgpu
 

@@ -360,8 +360,8 @@ __device__ __forceinline__ uint32_t post_pair(int a0, int a1, int shift)
 // Same for the kernel's POST mode.  WRAP: the int32 sum is exact modulo 2^32 (dp2a and IMAD wrap), so its low
 // acc_bits bits are those of the reference's unbounded sum; (w + bias) >> frac is evaluated as
 // (w >> frac) + (((w mod 2^frac) + bias) >> frac), which cannot overflow for any acc_bits <= 32, frac <= 31.
-template <int POST>
-__device__ __forceinline__ uint32_t post_pair_mode(int a0, int a1, const StagedParams &p)
+template <int POST, typename Params>
+__device__ __forceinline__ uint32_t post_pair_mode(int a0, int a1, const Params &p)
 {
     if constexpr (POST == POST_WRAP) {
         int v0, v1;

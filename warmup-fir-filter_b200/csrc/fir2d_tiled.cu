@@ -113,19 +113,29 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     bool sep = false;
     FastPlan f;
     long long fa[kMaxKH], fb[8];
+    // Post stage as in the 1-D kernel (fir1d_staged.cu, select_plan): shift-by-16 with pre-scaled taps, plain shift, or —
+    // live acc_bits wrap, a shifted result beyond 16 bits — the WRAP form (exact modulo 2^32 for acc_bits <= 32).
+    auto plan = [&](int tap_limit) {
+        FastPlan g = plan_fast(hq, n_taps, a.frac_bits, a.acc_bits, tap_limit);
+        if (!g.ok) g = plan_wrap(hq, n_taps, a.frac_bits, a.acc_bits, tap_limit);
+        return g;
+    };
     if (shape_has_separable(a.kh, a.kw) && !(getenv("FIRGPU_NO_SEPARABLE")) && factor_rank1(hq, a.kh, a.kw, fa, fb)) {
         bool b_fits = true;
         for (int n = 0; n < a.kw; ++n)
             if (fb[n] > 32767 || fb[n] < -32768) b_fits = false;
+        for (int m = 0; m < a.kh; ++m)
+            if (fa[m] > 0x7fffffffLL || fa[m] < -0x80000000LL) b_fits = false;
         if (b_fits) {
-            f = plan_fast(hq, n_taps, a.frac_bits, a.acc_bits, 0x7fffffff);
+            f = plan(0x7fffffff);           // row pass: dp2a with vector b (int16); column pass: IMAD with vector a (int32)
             sep = f.ok;
         }
     }
     if (!sep) {
-        f = plan_fast(hq, n_taps, a.frac_bits, a.acc_bits, 32767);
+        f = plan(32767);
         if (!f.ok) return 0;
     }
+    const int post = f.wrap ? POST_WRAP : (f.hi16 ? POST_HI16 : POST_SHIFT);
     if (sep) {
         const long long scale = f.hi16 ? (1LL << (16 - a.frac_bits)) : 1;
         int32_t b32[8];
@@ -144,6 +154,11 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
             }
         }
     }
+    p.wrap_sh = f.wrap_sh;
+    p.wrap_split = f.wrap_split ? 1 : 0;
+    p.wrap_mul = f.wrap_mul;
+    p.post_bias = f.post_bias;
+    p.frac_mask = f.frac_mask;
 
     const int bh = rows_per_stage(a.kh);                     // Geo2::BH
     const int stages_per_item = (kBandTarget + a.kh - 1 + bh - 1) / bh;
@@ -195,9 +210,9 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     }
     const CUtensorMap &map = cache.map[slot];
 
-    if (narrowing) return launch_tiled_i16u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
-    return es == 1 ? launch_tiled_u8(map, p, a.kh, a.kw, f.hi16, sep, a.stream)
-                   : launch_tiled_i16(map, p, a.kh, a.kw, f.hi16, sep, a.stream);
+    if (narrowing) return launch_tiled_i16u8(map, p, a.kh, a.kw, post, sep, a.stream);
+    return es == 1 ? launch_tiled_u8(map, p, a.kh, a.kw, post, sep, a.stream)
+                   : launch_tiled_i16(map, p, a.kh, a.kw, post, sep, a.stream);
 }
 
 }  // namespace firgpu

@@ -38,6 +38,10 @@ using staged::mbar_expect_tx;
 using staged::mbar_init;
 using staged::mbar_wait;
 using staged::post_pair;
+using staged::post_pair_mode;
+using staged::POST_HI16;
+using staged::POST_SHIFT;
+using staged::POST_WRAP;
 using staged::smem_u32;
 using staged::store_v4;
 
@@ -80,6 +84,9 @@ struct TiledParams {
     int halo_top;                                // map row of image row 0
     int shift, bias, y_vec_ok;
     int total_items;
+    // WRAP post (live acc_bits wrap, see staged::post_pair_mode): same fields as StagedParams
+    int wrap_sh, wrap_split, wrap_mul;
+    uint32_t post_bias, frac_mask;
     uint32_t cp_even[kMaxKH][kMaxPairs2];        // general: dp2a tap pairs of kernel row m
     uint32_t cp_odd[kMaxKH][kMaxPairs2];
     uint32_t xp_even[2], xp_odd[2];              // general 5x5: the odd tap of kernel rows (0,1) and (2,3) paired ACROSS rows
@@ -188,7 +195,7 @@ __device__ __forceinline__ void mac_cross(uint32_t even, uint32_t odd, const uin
     }
 }
 
-template <typename T, int KH, int KW, bool HI16, bool SEP, typename OutT = T>
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T>
 __global__ void __launch_bounds__(kBlock2, FIRGPU_T2_MINBLOCKS)
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
@@ -381,7 +388,7 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             }
                             uint32_t V[G1::S / 2];
 #pragma unroll
-                            for (int q = 0; q < G1::S / 2; ++q) V[q] = post_pair<HI16>(acc[2 * q], acc[2 * q + 1], p.shift);
+                            for (int q = 0; q < G1::S / 2; ++q) V[q] = post_pair_mode<POST>(acc[2 * q], acc[2 * q + 1], p);
                             uint32_t O[NOUT];
                             if constexpr (OS == 2) {
 #pragma unroll
@@ -420,11 +427,11 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 
 // ---- launch helpers -------------------------------------------------------------
-template <typename T, int KH, int KW, bool HI16, bool SEP, typename OutT = T>
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T>
 int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t stream)
 {
     using G = Geo2<T, KH, KW>;
-    auto kern = fir2d_tiled_kernel<T, KH, KW, HI16, SEP, OutT>;
+    auto kern = fir2d_tiled_kernel<T, KH, KW, POST, SEP, OutT>;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -491,27 +498,37 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     return 1;
 }
 
+template <typename T, int KH, int KW, bool SEP, typename OutT>
+int launch_tiled_post(const CUtensorMap &map, const TiledParams &p, int post, cudaStream_t s)
+{
+    switch (post) {
+    case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT>(map, p, s);
+    case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT>(map, p, s);
+    case POST_WRAP: return launch_tiled_one<T, KH, KW, POST_WRAP, SEP, OutT>(map, p, s);
+    default: return 0;
+    }
+}
+
 template <typename T, int KH, int KW, typename OutT = T>
-int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, bool hi16, bool sep, cudaStream_t s)
+int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, int post, bool sep, cudaStream_t s)
 {
     if constexpr (KH > 1 && KW >= 3 && !(KH == 3 && KW == 3)) {
-        if (sep)
-            return hi16 ? launch_tiled_one<T, KH, KW, true, true, OutT>(map, p, s) : launch_tiled_one<T, KH, KW, false, true, OutT>(map, p, s);
+        if (sep) return launch_tiled_post<T, KH, KW, true, OutT>(map, p, post, s);
     }
-    return hi16 ? launch_tiled_one<T, KH, KW, true, false, OutT>(map, p, s) : launch_tiled_one<T, KH, KW, false, false, OutT>(map, p, s);
+    return launch_tiled_post<T, KH, KW, false, OutT>(map, p, post, s);
 }
 
 template <typename T, typename OutT = T>
-int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
+int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s)
 {
-    if (kh == 1 && kw == 3) return launch_tiled_modes<T, 1, 3, OutT>(map, p, hi16, sep, s);   // short-row batches of the 1-D filter
-    if (kh == 1 && kw == 5) return launch_tiled_modes<T, 1, 5, OutT>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1, OutT>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3, OutT>(map, p, hi16, sep, s);
-    if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5, OutT>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1, OutT>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3, OutT>(map, p, hi16, sep, s);
-    if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5, OutT>(map, p, hi16, sep, s);
+    if (kh == 1 && kw == 3) return launch_tiled_modes<T, 1, 3, OutT>(map, p, post, sep, s);   // short-row batches of the 1-D filter
+    if (kh == 1 && kw == 5) return launch_tiled_modes<T, 1, 5, OutT>(map, p, post, sep, s);
+    if (kh == 3 && kw == 1) return launch_tiled_modes<T, 3, 1, OutT>(map, p, post, sep, s);
+    if (kh == 3 && kw == 3) return launch_tiled_modes<T, 3, 3, OutT>(map, p, post, sep, s);
+    if (kh == 3 && kw == 5) return launch_tiled_modes<T, 3, 5, OutT>(map, p, post, sep, s);
+    if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1, OutT>(map, p, post, sep, s);
+    if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3, OutT>(map, p, post, sep, s);
+    if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5, OutT>(map, p, post, sep, s);
     return 0;
 }
 
@@ -521,9 +538,9 @@ inline bool shape_supported(int kh, int kw)
 {
     return ((kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5)) || (kh == 1 && (kw == 3 || kw == 5));
 }
-int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
-int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);
-int launch_tiled_i16u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s);   // int16 pixels in, uint8 out
+int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s);
+int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s);
+int launch_tiled_i16u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s);   // int16 pixels in, uint8 out
 
 }  // namespace tiled
 }  // namespace firgpu

@@ -9,9 +9,9 @@
 namespace firgpu {
 namespace tiled {
 
-int FIRGPU_TILED_NAME(const CUtensorMap &map, const TiledParams &p, int kh, int kw, bool hi16, bool sep, cudaStream_t s)
+int FIRGPU_TILED_NAME(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s)
 {
-    return launch_tiled_shape<FIRGPU_TILED_T, FIRGPU_TILED_OUT>(map, p, kh, kw, hi16, sep, s);
+    return launch_tiled_shape<FIRGPU_TILED_T, FIRGPU_TILED_OUT>(map, p, kh, kw, post, sep, s);
 }
 
 }  // namespace tiled
