@@ -190,6 +190,33 @@ int firgpu_fir1d_ideal_ex_host(const void *x, void *y, int in_dtype, int out_dty
                                int centre, int in_lo, int in_hi, int raw, int device);
 
 /* ------------------------------------------------------------------------
+ * Complex taps on interleaved I/Q  [I0,Q0,I1,Q1,...]  (cols, ld_*, halo_* count
+ * scalars and must be even).
+ *
+ * The reference stops at real taps: lib/mycomplex.h:10-41 defines complex +
+ * complex and complex * double only (that is the dilation == 2 mode above).
+ * This is the step SURVEY 8(f)4 lists after streaming; the specification is
+ * ours, parity unpinned except for hq_im == 0, where it equals
+ * the real-tap I/Q filter:
+ *   acc_re[n] = sum_k hq_re[k] * xs_re[m] - hq_im[k] * xs_im[m]    m = n - (k - n_taps/2)
+ *   acc_im[n] = sum_k hq_re[k] * xs_im[m] + hq_im[k] * xs_re[m]
+ *   each through the 1-D post stage (wrap to acc_bits once, + 2^(frac-1),
+ *   >> frac, saturate to [out_lo, out_hi]); samples clamped to [in_lo, in_hi]
+ *   ((0,255) twice = the reference's ranges, (-32768,32767) = signed baseband).
+ * ------------------------------------------------------------------------ */
+int firgpu_fir1d_fixed_complex(const void *x, void *y, int in_dtype, int out_dtype,
+                               int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                               const int32_t *hq_re, const int32_t *hq_im, int n_taps,
+                               int frac_bits, int acc_bits,
+                               int64_t halo_left_valid, int64_t halo_right_valid,
+                               int in_lo, int in_hi, int out_lo, int out_hi, void *stream);
+int firgpu_fir1d_fixed_complex_host(const void *x, void *y, int in_dtype, int out_dtype,
+                                    int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                                    const int32_t *hq_re, const int32_t *hq_im, int n_taps,
+                                    int frac_bits, int acc_bits,
+                                    int in_lo, int in_hi, int out_lo, int out_hi, int device);
+
+/* ------------------------------------------------------------------------
  * Fused fixed-vs-ideal comparison (row-batched, no outputs materialised).
  *
  * Stands behind _compute_metrics

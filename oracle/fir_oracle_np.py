@@ -143,6 +143,39 @@ def fir1d_fixed_iq(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: in
 # --------------------------------------------------------------------------
 # 2-D (parity unpinned — our spec; see fir_oracle_py.fir2d_fixed)
 # --------------------------------------------------------------------------
+def fir1d_fixed_complex(z, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16, *, out_dtype=np.int16,
+                        in_range=(PIXEL_LO, PIXEL_HI), out_range=(PIXEL_LO, PIXEL_HI)) -> np.ndarray:
+    """Interleaved I/Q [I0,Q0,I1,Q1,...] with COMPLEX taps — OUR specification (parity unpinned: lib/mycomplex.h:10-41
+    defines complex + complex and complex * double only, so the reference fixes how a real-scalar product and a sum
+    act per component, not a complex product).  Written directly from the definition, not as the two real filters the
+    product composes it from:
+
+        hq_re[k], hq_im[k] = the 1-D model's quantisation of Re h[k], Im h[k]          (fir_1d_fixed_ref.py:79-81)
+        xs = the 1-D model's sample preparation of every scalar                         (fir_1d_ref.py:35-41)
+        acc_re[n] = sum_k hq_re[k] * xs_re[m] - hq_im[k] * xs_im[m],   m = n - (k - L//2), zero outside [0, N)
+        acc_im[n] = sum_k hq_re[k] * xs_im[m] + hq_im[k] * xs_re[m]
+        y_re, y_im = the 1-D post stage on each accumulator (wrap once, + bias, >> frac, saturate)   (:110-126)
+
+    Imaginary taps of zero reduce it to ``fir1d_fixed_iq`` (real taps), which IS pinned by composition."""
+    z = np.asarray(z)
+    hc = np.asarray(h, dtype=np.complex128).reshape(-1)
+    hq_re = quantize_taps(hc.real, frac_bits, coeff_bits)
+    hq_im = quantize_taps(hc.imag, frac_bits, coeff_bits)
+    xs = prep_samples(z, *in_range).astype(np.int64)
+    xr, xi = xs[..., 0::2], xs[..., 1::2]
+    acc_re = np.zeros(xr.shape, dtype=np.int64)
+    acc_im = np.zeros(xr.shape, dtype=np.int64)
+    views_r = dict(_shifted_views(xr, hc.size, 1, None))
+    views_i = dict(_shifted_views(xi, hc.size, 1, None))
+    for k in range(hc.size):
+        acc_re += hq_re[k] * views_r[k] - hq_im[k] * views_i[k]
+        acc_im += hq_re[k] * views_i[k] + hq_im[k] * views_r[k]
+    out = np.empty(z.shape, dtype=out_dtype)
+    out[..., 0::2] = post_accumulate(acc_re, frac_bits, acc_bits, *out_range).astype(out_dtype)
+    out[..., 1::2] = post_accumulate(acc_im, frac_bits, acc_bits, *out_range).astype(out_dtype)
+    return out
+
+
 def _shifted_views_2d(xs: np.ndarray, kh: int, kw: int):
     ch, cw = kh // 2, kw // 2
     hgt, wid = xs.shape[-2:]

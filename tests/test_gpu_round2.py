@@ -553,3 +553,45 @@ def test_fir2d_live_wrap_runs_on_the_tensor_map_kernel(fg, torch):
     got = fg.fir1d_fixed(view, h, 12, 16, 16, out_dtype=np.int16)
     assert _lib.last_path() == _lib.PATH_STAGED
     assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(rows[:, :3000], h, 12, 16, 16, out_dtype=np.int16))
+
+
+def test_complex_taps_on_interleaved_iq(fg, torch):
+    """Complex taps (SURVEY 8(f)4's last step; specification ours, parity unpinned — the reference's MyComplex has no
+    complex product): the product composes them from two real filters over the interleaved stream, the oracle
+    evaluates the definition directly.  Anchors: purely real taps reduce to the real-tap I/Q filter (pinned by
+    composition), h = [j] rotates every sample by 90 degrees, 1 ... 8 complex taps, reference and signed ranges, live
+    wrap, several rows, the trailing-axis-of-2 layout, host arrays long enough to be cut into segments."""
+    from firgpu import _lib
+    rng = np.random.default_rng(81)
+    full = (-32768, 32767)
+    for n_taps in (1, 2, 3, 4, 5, 8):
+        h = (rng.uniform(-0.4, 0.4, size=n_taps) + 1j * rng.uniform(-0.4, 0.4, size=n_taps)).tolist()
+        for shape in ((2,), (10,), (16386,), (3, 5000), (70_002,)):
+            for in_r, out_r, dt in (((0, 255), (0, 255), np.uint8), ((0, 255), (0, 255), np.int16), (full, full, np.int16)):
+                z = signal(rng, shape, dt, wild=0.05) if in_r == (0, 255) else rng.integers(-3000, 3000, size=shape).astype(np.int16)
+                for acc_bits in (32, 18):
+                    got = fg.fir1d_fixed_complex(torch.from_numpy(z).cuda(), h, 12, acc_bits, 16, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                    want = onp.fir1d_fixed_complex(z, h, 12, acc_bits, 16, in_range=in_r, out_range=out_r, out_dtype=np.int16)
+                    assert np.array_equal(got.cpu().numpy(), want), (n_taps, shape, in_r, acc_bits)
+    # fast kernels serve it: up to four signed complex taps on the wide datapath, reference ranges through the buckets
+    z = rng.integers(-3000, 3000, size=1 << 20).astype(np.int16)
+    fg.fir1d_fixed_complex(torch.from_numpy(z).cuda(), [0.2 + 0.1j, 0.3 - 0.2j, 0.1 + 0.3j], 15, 32, 16, in_range=full, out_range=full)
+    assert _lib.last_path() == _lib.PATH_STAGED
+    # anchors
+    zr = signal(rng, 100_000, np.int16)
+    h_real = [0.1, 0.2, 0.4, 0.2, 0.1]
+    a = fg.fir1d_fixed_complex(torch.from_numpy(zr).cuda(), h_real, 12, 32, 16, out_dtype=np.int16).cpu().numpy()
+    b = fg.fir1d_fixed_iq(torch.from_numpy(zr).cuda(), h_real, 12, 32, 16, out_dtype=np.int16).cpu().numpy()
+    assert np.array_equal(a, b) and np.array_equal(a, onp.fir1d_fixed_iq(zr, h_real, 12, 32, 16, out_dtype=np.int16))
+    zs = rng.integers(-1000, 1000, size=20_000).astype(np.int16)
+    rot = fg.fir1d_fixed_complex(torch.from_numpy(zs).cuda(), [1j], 12, 32, 16, in_range=full, out_range=full).cpu().numpy()
+    assert np.array_equal(rot[0::2], -zs[1::2]) and np.array_equal(rot[1::2], zs[0::2])
+    # [N, 2] layout and the host entry point (long enough for column segments with halos)
+    pairs = zs.reshape(-1, 2)
+    h = [0.3 + 0.1j, -0.2 + 0.25j, 0.15 - 0.3j]
+    want = onp.fir1d_fixed_complex(zs, h, 12, 32, 16, in_range=full, out_range=full, out_dtype=np.int16)
+    got = fg.fir1d_fixed_complex(torch.from_numpy(pairs).cuda(), h, 12, 32, 16, in_range=full, out_range=full)
+    assert got.shape == pairs.shape and np.array_equal(got.cpu().numpy().reshape(-1), want)
+    big = rng.integers(-3000, 3000, size=40_000_000).astype(np.int16)
+    want = onp.fir1d_fixed_complex(big, h, 12, 32, 16, in_range=full, out_range=full, out_dtype=np.int16)
+    assert np.array_equal(fg.fir1d_fixed_complex(big, h, 12, 32, 16, in_range=full, out_range=full), want)

@@ -206,3 +206,36 @@ def test_reference_report_numbers_are_the_published_ones(compare_rows):
     assert s3["num_cases"] == s5["num_cases"] == 28 and s3["num_samples_total"] == 67_975_252
     assert (round(s3["avg_mae"], 4), round(s3["avg_rmse"], 4), round(s3["avg_mean_err"], 4), s3["max_max_abs_err"]) == (2.4078, 5.8063, 2.2903, 255.0)
     assert (round(s5["avg_mae"], 4), round(s5["avg_rmse"], 4), round(s5["avg_mean_err"], 4), s5["max_max_abs_err"]) == (1.1302, 2.9380, 0.8871, 118.0625)
+
+
+def test_complex_tap_oracle_anchors():
+    """oracle/fir_oracle_np.py::fir1d_fixed_complex is OUR specification (the reference has no complex product); what
+    can be anchored is anchored: purely real taps = the real-tap I/Q filter (two independent runs of the reference-pinned
+    1-D model), h = [j] is a rotation by 90 degrees, linearity in the taps before the rounding, and a scalar restatement."""
+    rng = np.random.default_rng(5)
+    z = rng.integers(-300, 600, size=2 * 257).astype(np.int16)
+    h = [0.1, 0.2, 0.4, 0.2, 0.1]
+    assert np.array_equal(onp.fir1d_fixed_complex(z, h, 12, 32, 16, out_dtype=np.uint8), onp.fir1d_fixed_iq(z, h, 12, 32, 16))
+    full = (-32768, 32767)
+    zs = rng.integers(-1000, 1000, size=200).astype(np.int16)
+    rot = onp.fir1d_fixed_complex(zs, [1j], 12, 32, 16, in_range=full, out_range=full)
+    assert np.array_equal(rot[0::2], -zs[1::2]) and np.array_equal(rot[1::2], zs[0::2])
+    # scalar restatement of the definition with unbounded Python ints
+    hc = [0.3 + 0.1j, -0.2 + 0.25j, 0.15 - 0.3j, 0.05 + 0.05j]
+    hr = onp.quantize_taps([v.real for v in hc], 12, 16).tolist()
+    hi = onp.quantize_taps([v.imag for v in hc], 12, 16).tolist()
+    n, L, c = zs.size // 2, len(hc), len(hc) // 2
+    want = np.empty(zs.size, dtype=np.int64)
+    for acc_bits in (32, 14):
+        for i in range(n):
+            ar = ai = 0
+            for k in range(L):
+                m = i - (k - c)
+                if 0 <= m < n:
+                    xr, xi = int(zs[2 * m]), int(zs[2 * m + 1])
+                    ar += hr[k] * xr - hi[k] * xi
+                    ai += hr[k] * xi + hi[k] * xr
+            want[2 * i] = onp.post_accumulate(np.array([ar], dtype=np.int64), 12, acc_bits, *full)[0]
+            want[2 * i + 1] = onp.post_accumulate(np.array([ai], dtype=np.int64), 12, acc_bits, *full)[0]
+        got = onp.fir1d_fixed_complex(zs, hc, 12, acc_bits, 16, in_range=full, out_range=full)
+        assert np.array_equal(got, want.astype(np.int16)), acc_bits

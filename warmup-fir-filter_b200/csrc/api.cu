@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1288,6 +1289,114 @@ int firgpu_fir1d_fixed_host_multi(const void *x, void *y, int in_dtype, int out_
         }
     }
     return rc;
+}
+
+// ---- complex taps on interleaved I/Q (fir1d_complex.cu explains the decomposition) -----------------------------
+namespace {
+// Real 2L-tap filters A (Re, centre 2c+1) and B (Im, centre 2c) of the complex taps (hq_re, hq_im).
+void complex_tap_filters(const int32_t *hq_re, const int32_t *hq_im, int n_taps, std::vector<int32_t> &ga, std::vector<int32_t> &gb)
+{
+    ga.assign(2 * (size_t)n_taps, 0);
+    gb.assign(2 * (size_t)n_taps, 0);
+    for (int k = 0; k < n_taps; ++k) {
+        ga[2 * k] = -hq_im[k];
+        ga[2 * k + 1] = hq_re[k];
+        gb[2 * k] = hq_re[k];
+        gb[2 * k + 1] = hq_im[k];
+    }
+}
+
+int complex_device(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y,
+                   const std::vector<int32_t> &ga, const std::vector<int32_t> &gb, int n_taps, int frac_bits, int acc_bits,
+                   int64_t halo_left, int64_t halo_right, int in_lo, int in_hi, int out_lo, int out_hi, cudaStream_t stream)
+{
+    const int os = out_size_fixed(out_dtype), c = n_taps / 2;
+    // scratch rows for the two real filters, 16-byte aligned pitch
+    const int64_t ld_t = round_up(cols, 16);
+    unsigned char *tmp = nullptr;
+    int rc = scratch_alloc((void **)&tmp, (size_t)(2 * ld_t * rows * os), stream);
+    if (rc) return rc;
+    unsigned char *ta = tmp, *tb = tmp + (size_t)ld_t * rows * os;
+    Fir1dArgs a{x, ta, in_dtype, out_dtype, rows, cols, ld_x, ld_t, 2 * n_taps, 1, frac_bits, acc_bits, halo_left, halo_right, stream};
+    a.in_lo = in_lo;
+    a.in_hi = in_hi;
+    a.out_lo = out_lo;
+    a.out_hi = out_hi;
+    a.centre = 2 * c + 1;
+    rc = fir1d_fixed_ex_device(a, ga.data(), false);
+    if (rc == 1) {
+        a.y = tb;
+        a.centre = 2 * c;
+        rc = fir1d_fixed_ex_device(a, gb.data(), false);
+    }
+    if (rc == 1) {
+        rc = 0;
+        if (rows == 1 || (ld_t == cols && ld_y == cols)) {           // one dense block (cols is even, so the parity carries over rows)
+            rc = launch_select_even_odd(ta, tb, y, rows * cols, os, stream);
+        } else {
+            for (int64_t r = 0; r < rows && !rc; ++r)
+                rc = launch_select_even_odd(ta + (size_t)r * ld_t * os, tb + (size_t)r * ld_t * os, (char *)y + (size_t)r * ld_y * os, cols, os, stream);
+        }
+    }
+    cudaFreeAsync(tmp, stream);
+    return rc;
+}
+
+int check_complex(const char *fn, const void *x, const void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                  int64_t ld_y, const int32_t *hq_re, const int32_t *hq_im, int n_taps, int frac_bits, int acc_bits, int64_t halo_left,
+                  int64_t halo_right, int in_lo, int in_hi, int out_lo, int out_hi)
+{
+    int rc = check_1d(fn, x, y, in_dtype, rows, cols, ld_x, ld_y, hq_re, n_taps, 1, halo_left, halo_right);
+    if (rc) return rc;
+    if (!hq_im) return set_error(FIRGPU_E_NULL, "%s: imaginary taps pointer is NULL", fn);
+    if ((rc = check_bits(fn, frac_bits, acc_bits))) return rc;
+    if ((rc = check_ex(fn, n_taps, n_taps / 2, in_lo, in_hi, out_lo, out_hi))) return rc;
+    if (2 * n_taps > FIRGPU_MAX_TAPS) return set_error(FIRGPU_E_TAPS, "%s: n_taps=%d exceeds %d complex taps", fn, n_taps, FIRGPU_MAX_TAPS / 2);
+    if (!out_size_fixed(out_dtype)) return set_error(FIRGPU_E_DTYPE, "%s: out_dtype must be U8 or I16, got %d", fn, out_dtype);
+    if ((out_dtype == FIRGPU_U8 && (out_lo < 0 || out_hi > 255)) || out_lo < -32768 || out_hi > 32767)
+        return set_error(FIRGPU_E_BITS, "%s: output range [%d,%d] does not fit the output container", fn, out_lo, out_hi);
+    if ((cols | halo_left | halo_right) & 1) return set_error(FIRGPU_E_SHAPE, "%s: cols and halos count interleaved scalars and must be even", fn);
+    for (int k = 0; k < n_taps; ++k)
+        if (hq_im[k] == INT32_MIN) return set_error(FIRGPU_E_TAPS, "%s: imaginary tap %d cannot be negated in int32", fn, k);
+    return 0;
+}
+}  // namespace
+
+int firgpu_fir1d_fixed_complex(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                               int64_t ld_y, const int32_t *hq_re, const int32_t *hq_im, int n_taps, int frac_bits, int acc_bits,
+                               int64_t halo_left_valid, int64_t halo_right_valid, int in_lo, int in_hi, int out_lo, int out_hi,
+                               void *stream)
+{
+    int rc = check_complex("firgpu_fir1d_fixed_complex", x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, hq_re, hq_im, n_taps, frac_bits,
+                           acc_bits, halo_left_valid, halo_right_valid, in_lo, in_hi, out_lo, out_hi);
+    if (rc) return rc;
+    if (rows == 0 || cols == 0) {
+        tl_path = FIRGPU_PATH_EMPTY;
+        return 0;
+    }
+    std::vector<int32_t> ga, gb;
+    complex_tap_filters(hq_re, hq_im, n_taps, ga, gb);
+    return complex_device(x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, ga, gb, n_taps, frac_bits, acc_bits, halo_left_valid,
+                          halo_right_valid, in_lo, in_hi, out_lo, out_hi, (cudaStream_t)stream);
+}
+
+int firgpu_fir1d_fixed_complex_host(const void *x, void *y, int in_dtype, int out_dtype, int64_t rows, int64_t cols, int64_t ld_x,
+                                    int64_t ld_y, const int32_t *hq_re, const int32_t *hq_im, int n_taps, int frac_bits,
+                                    int acc_bits, int in_lo, int in_hi, int out_lo, int out_hi, int device)
+{
+    int rc = check_complex("firgpu_fir1d_fixed_complex_host", x, y, in_dtype, out_dtype, rows, cols, ld_x, ld_y, hq_re, hq_im, n_taps,
+                           frac_bits, acc_bits, 0, 0, in_lo, in_hi, out_lo, out_hi);
+    if (rc) return rc;
+    std::vector<int32_t> ga, gb;
+    complex_tap_filters(hq_re, hq_im, n_taps, ga, gb);
+    const int64_t c = n_taps / 2;
+    // reach in interleaved scalars, rounded up to whole complex samples: filter B reads 2L-1-2c scalars back, A 2c+1 ahead
+    return pipeline_1d(x, y, dtype_size(in_dtype), out_size_fixed(out_dtype), rows, cols, ld_x, ld_y, 2 * (n_taps - c), 2 * c + 2, device,
+                       [&](const void *dx, void *dy, int64_t nr, int64_t nc, int64_t lx, int64_t ly, int64_t before, int64_t after,
+                           cudaStream_t s) {
+                           return complex_device(dx, dy, in_dtype, out_dtype, nr, nc, lx, ly, ga, gb, n_taps, frac_bits, acc_bits, before,
+                                                 after, in_lo, in_hi, out_lo, out_hi, s);
+                       });
 }
 
 int firgpu_fir1d_fixed_plan(const int32_t *hq, int n_taps, int frac_bits, int acc_bits, int *path, int *post, int *mac)

@@ -204,6 +204,8 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
 int launch_repitch(const void *x, int dtype, void *y, int64_t rows, int64_t cols, int64_t ld_x, int64_t ld_y, cudaStream_t s);
 int launch_prep_u8(const void *x, int in_dtype, uint8_t *y, int64_t rows, int64_t span, int64_t ld_x, int64_t ld_y,
                    int64_t before, int64_t shift, cudaStream_t s);
+// fir1d_complex.cu — y[i] = (i even) ? a[i] : b[i] over n scalars of es bytes
+int launch_select_even_odd(const void *a, const void *b, void *y, int64_t n, int es, cudaStream_t s);
 // fir1d_compare.cu
 int launch_fir1d_compare(const void *x, int in_dtype, int64_t rows, int64_t cols, int64_t ld_x, const int32_t *hq_host,
                          const double *h_host, int n_taps, int frac_bits, int acc_bits, double *out, cudaStream_t s);

@@ -7,8 +7,8 @@ partition planner for 1/2/4/8 GPUs, ``firgpu._lib`` the ctypes binding of
 paths (``fir_1d.model.python...``, ``fir_2d...``, ``pipeline_fir_1d``) live next to this
 package and call into it.  No CPU fallback exists.
 """
-from .ops import (DeviceArray, FirStream, PinnedArray, Recording, compare_metrics, fir1d_fixed, fir1d_fixed_iq,  # noqa: F401
+from .ops import (DeviceArray, FirStream, PinnedArray, Recording, compare_metrics, fir1d_fixed, fir1d_fixed_complex, fir1d_fixed_iq,  # noqa: F401
                   fir1d_fixed_multi, fir1d_fixed_multi_gpu, fir1d_fixed_plan, fir1d_fixed_q, fir1d_ideal, fir2d_fixed, fir2d_fixed_q, fir2d_ideal, record)
 
-__all__ = ["DeviceArray", "FirStream", "PinnedArray", "Recording", "compare_metrics", "fir1d_fixed", "fir1d_fixed_q", "fir1d_fixed_iq",
+__all__ = ["DeviceArray", "FirStream", "PinnedArray", "Recording", "compare_metrics", "fir1d_fixed", "fir1d_fixed_q", "fir1d_fixed_iq", "fir1d_fixed_complex",
            "fir1d_fixed_multi", "fir1d_fixed_multi_gpu", "fir1d_fixed_plan", "fir1d_ideal", "fir2d_fixed_q", "fir2d_fixed", "fir2d_ideal", "record"]

@@ -58,6 +58,8 @@ SIGNATURES = {
     "firgpu_graph_launch": (_ci, [_vp, _vp]),
     "firgpu_graph_nodes": (_ci, [_vp, C.POINTER(_i64)]),
     "firgpu_graph_destroy": (_ci, [_vp]),
+    "firgpu_fir1d_fixed_complex": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _i64, _i64, _ci, _ci, _ci, _ci, _vp]),
+    "firgpu_fir1d_fixed_complex_host": (_ci, [_vp, _vp, _ci, _ci, _i64, _i64, _i64, _i64, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci]),
     "firgpu_fir1d_fixed_plan": (_ci, [_vp, _ci, _ci, _ci, C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_ci)]),
     "firgpu_get_device": (_ci, [C.POINTER(_ci)]),
     "firgpu_set_device": (_ci, [_ci]),
