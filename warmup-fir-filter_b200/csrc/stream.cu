@@ -290,10 +290,10 @@ int firgpu_stream_create_fixed(firgpu_stream_t *out, int in_dtype, int out_dtype
     if (frac_bits < 1 || acc_bits < 1) return set_error(FIRGPU_E_BITS, "firgpu_stream_create_fixed: frac_bits=%d and acc_bits=%d must be >= 1", frac_bits, acc_bits);
     if (out_lo > out_hi || (out_dtype == FIRGPU_U8 && (out_lo < 0 || out_hi > 255)) || out_lo < -32768 || out_hi > 32767)
         return set_error(FIRGPU_E_BITS, "firgpu_stream_create_fixed: output range [%d,%d] does not fit the output container", out_lo, out_hi);
+    if (device < 0) FIRGPU_CUDA(cudaGetDevice(&device));
     StreamState *s = new (std::nothrow) StreamState();
     if (!s) return set_error(FIRGPU_E_NULL, "firgpu_stream_create_fixed: out of host memory");
     s->fixed = true;
-    if (device < 0) FIRGPU_CUDA(cudaGetDevice(&device));
     s->device = device;
     s->in_dtype = in_dtype;
     s->out_dtype = out_dtype;
@@ -317,10 +317,10 @@ int firgpu_stream_create_ideal(firgpu_stream_t *out, int in_dtype, int out_dtype
     if (rc) return rc;
     if (out_dtype != FIRGPU_F64 && out_dtype != FIRGPU_F32)
         return set_error(FIRGPU_E_DTYPE, "firgpu_stream_create_ideal: out_dtype must be F64 or F32, got %d", out_dtype);
+    if (device < 0) FIRGPU_CUDA(cudaGetDevice(&device));
     StreamState *s = new (std::nothrow) StreamState();
     if (!s) return set_error(FIRGPU_E_NULL, "firgpu_stream_create_ideal: out of host memory");
     s->fixed = false;
-    if (device < 0) FIRGPU_CUDA(cudaGetDevice(&device));
     s->device = device;
     s->in_dtype = in_dtype;
     s->out_dtype = out_dtype;
