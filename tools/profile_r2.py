@@ -62,7 +62,7 @@ elif case.startswith("2d"):
     if u8:
         img = img.clamp(0, 255).to(torch.uint8)
     out = torch.empty_like(img)
-    k = [[1 / 9] * 3] * 3 if "3x3" in case else np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist()
+    k = [[1 / 9] * 3] * 3 if "3x3" in case else (np.outer(LP5, LP5).tolist() if "rank1" in case else np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist())
     hq = quant.quantize_taps(np.asarray(k), 12, 16)
     fn = lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out_dtype=np.uint8 if u8 else np.int16, out=out)
 elif case == "ideal32":
