@@ -595,3 +595,42 @@ def test_complex_taps_on_interleaved_iq(fg, torch):
     big = rng.integers(-3000, 3000, size=40_000_000).astype(np.int16)
     want = onp.fir1d_fixed_complex(big, h, 12, 32, 16, in_range=full, out_range=full, out_dtype=np.int16)
     assert np.array_equal(fg.fir1d_fixed_complex(big, h, 12, 32, 16, in_range=full, out_range=full), want)
+
+
+def test_ideal_wide_groups_every_alignment_and_the_fallback():
+    """The floating-point model's 32-byte-group form (one 256-bit store per lane, aligned 4-sample chunk loads) is taken
+    where input and output rows share their alignment, the 16-byte form elsewhere; both must give the oracle's result —
+    float64 bit for bit, float32 within the stated tolerance — at every tap count, ragged widths and view offsets."""
+    import torch
+    import firgpu
+    from firgpu import _lib
+    rng = np.random.default_rng(77)
+    for dtype in (np.uint8, np.int16):
+        base = rng.integers(0, 256, size=(5, 9000)).astype(dtype)
+        if dtype == np.int16:
+            base[rng.random(base.shape) < 0.05] = -7
+            base[rng.random(base.shape) < 0.05] = 300
+        bt = torch.from_numpy(base).cuda()
+        for n_taps in (1, 2, 3, 5, 8, 9):
+            h = rng.uniform(-2, 2, size=n_taps).tolist()
+            tol = 1e-6 * 255 * float(np.sum(np.abs(h)))
+            for cx, cy, width in ((0, 0, 8192), (0, 0, 4107), (4, 4, 3001), (3, 3, 519), (1, 0, 2050), (0, 5, 777), (8, 0, 6), (2, 2, 31)):
+                want = onp.fir1d_ideal(base[:, cx:cx + width], h)
+                for odt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+                    out = torch.full((5, 9100), -3.0, dtype=tdt, device="cuda")
+                    firgpu.fir1d_ideal(bt[:, cx:cx + width], h, out_dtype=odt, out=out[:, cy:cy + width])
+                    assert _lib.last_path() == _lib.PATH_STAGED
+                    got = out.cpu().numpy()
+                    if odt is np.float64:
+                        assert np.array_equal(got[:, cy:cy + width], want), (dtype, n_taps, cx, cy, width)
+                    else:
+                        assert np.abs(got[:, cy:cy + width] - want).max() <= tol, (dtype, n_taps, cx, cy, width)
+                    assert (got[:, :cy] == -3.0).all() and (got[:, cy + width:] == -3.0).all()
+    # one long row with shard halos on the wide form
+    x = rng.integers(0, 256, size=(1 << 20) + 24).astype(np.uint8)
+    h = [0.1, 0.2, 0.4, 0.2, 0.1]
+    full = onp.fir1d_ideal(x, h)
+    xt = torch.from_numpy(x).cuda()
+    body = xt[8:8 + (1 << 20)]
+    y = firgpu.fir1d_ideal(body, h, halo_left_valid=2, halo_right_valid=2)
+    assert np.array_equal(y.cpu().numpy(), full[8:8 + (1 << 20)])
