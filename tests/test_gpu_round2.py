@@ -634,3 +634,48 @@ def test_ideal_wide_groups_every_alignment_and_the_fallback():
     body = xt[8:8 + (1 << 20)]
     y = firgpu.fir1d_ideal(body, h, halo_left_valid=2, halo_right_valid=2)
     assert np.array_equal(y.cpu().numpy(), full[8:8 + (1 << 20)])
+
+
+def test_2d_ideal_rows_kernel_bit_identical():
+    """fir2d_ideal_rows_kernel (four output rows per lane, 32-byte groups; taken when pitches and offsets are multiples of
+    the group): every window, heights that are not multiples of four, widths ragged inside an aligned pitch, view offsets,
+    several images, row bands with halo rows — float64 bit-identical to the oracle, float32 within the tolerance, and
+    nothing written outside the view."""
+    import torch
+    import firgpu
+    from firgpu import _lib, shard
+    rng = np.random.default_rng(123)
+    kernels = [rng.uniform(-2, 2, size=s).tolist() for s in ((3, 3), (5, 5), (3, 5), (5, 3))]
+    for dtype in (np.uint8, np.int16):
+        base = rng.integers(0, 256, size=(3, 43, 1024)).astype(dtype)
+        if dtype == np.int16:
+            base[rng.random(base.shape) < 0.05] = -9
+            base[rng.random(base.shape) < 0.05] = 999
+        bt = torch.from_numpy(base).cuda()
+        for k in kernels:
+            tol = 1e-6 * 255 * float(np.abs(k).sum())
+            for (r0, hgt), (c0, width) in (((0, 43), (0, 1024)), ((0, 1), (0, 1000)), ((2, 2), (8, 520)), ((1, 7), (16, 9)),
+                                           ((0, 40), (3, 800)), ((5, 13), (8, 1016))):
+                view = bt[:, r0:r0 + hgt, c0:c0 + width]
+                want = onp.fir2d_ideal(base[:, r0:r0 + hgt, c0:c0 + width], k)
+                for odt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+                    out = torch.full((3, 43, 1024), -5.0, dtype=tdt, device="cuda")
+                    firgpu.fir2d_ideal(view, k, out_dtype=odt, out=out[:, r0:r0 + hgt, c0:c0 + width])
+                    assert _lib.last_path() == _lib.PATH_STAGED
+                    got = out.cpu().numpy()
+                    inner = got[:, r0:r0 + hgt, c0:c0 + width]
+                    if odt is np.float64:
+                        assert np.array_equal(inner, want), (dtype, np.shape(k), r0, hgt, c0, width)
+                    else:
+                        assert np.abs(inner - want).max() <= tol, (dtype, np.shape(k), r0, hgt, c0, width)
+                    got[:, r0:r0 + hgt, c0:c0 + width] = -5.0
+                    assert (got == -5.0).all(), "wrote outside the view"
+    x = rng.integers(0, 256, size=(1, 301, 2048)).astype(np.uint8)
+    k = kernels[1]
+    want = onp.fir2d_ideal(x, k)
+    got = np.empty_like(want)
+    for band in shard.plan_bands(301, 3, 5):
+        buf, body = shard.scatter_band(x, band, "cuda")
+        y = firgpu.fir2d_ideal(body, k, halo_top_valid=band.before, halo_bottom_valid=band.after)
+        got[..., band.start:band.stop, :] = y.cpu().numpy()
+    assert np.array_equal(got, want)

@@ -288,11 +288,14 @@ int run(const Fir1dArgs &a, const double *h_host)
     // groups per lane per tile: 512-output warp tiles measured best for both output types (sweep in profiles/README.md)
     if constexpr (sizeof(InT) == 8) return run_groups<InT, double, L, 8, true>(a, h_host);
     else if (a.dilation == 2) {                         // wider windows (L pairs per group): fewer groups in flight per lane
-        // wide groups here too (2^26 complex int16 samples, 5 taps: float64 0.84 -> 0.92 of the HBM peak, float32 0.66 -> 0.79)
-        static const int wide_iq = getenv("FIRGPU_IDEAL_IQ_WIDE") ? atoi(getenv("FIRGPU_IDEAL_IQ_WIDE")) : 2;   // 0: A/B, the 16-byte form
+        // wide groups here too (2^26 complex int16 samples, 5 taps: float64 0.84 -> 1.02 of the HBM peak, float32 0.66 -> 0.91;
+        // 2 groups per lane instead of 4: 0.92 / 0.79)
+        static const int wide_iq = getenv("FIRGPU_IDEAL_IQ_WIDE") ? atoi(getenv("FIRGPU_IDEAL_IQ_WIDE")) : 4;   // 0: A/B, the 16-byte form
         if (a.out_dtype == FIRGPU_F32) {
-            if (wide_iq == 4 && chunks_aligned<InT, float>(a)) return run_groups<InT, float, L, 2, false, 2, 2>(a, h_host);
-            if (wide_iq && chunks_aligned<InT, float>(a)) return run_groups<InT, float, L, 1, false, 2, 2>(a, h_host);
+            if (wide_iq && chunks_aligned<InT, float>(a)) {
+                if (wide_iq == 4) return run_groups<InT, float, L, 2, false, 2, 2>(a, h_host);
+                return run_groups<InT, float, L, 1, false, 2, 2>(a, h_host);
+            }
             return run_groups<InT, float, L, 2, false, 2>(a, h_host);
         }
         if (wide_iq && chunks_aligned<InT, double>(a)) {

@@ -14,7 +14,9 @@
 // which never changes such a sum (see fir1d_ideal_fast.cu).
 //
 // Bound: the fp64 pipe for 5x5 (50 multiply/adds + 15 conversions per pixel at
-// 64 lanes/clk/SM ~ 280 Gpixel/s), HBM (9 B/pixel) for 3x3.
+// 64 lanes/clk/SM ~ 280 Gpixel/s), HBM (9 B/pixel) for 3x3.  Images whose rows
+// are aligned alike take fir2d_ideal_rows_kernel below (four output rows per
+// lane: 4 conversions per pixel); this kernel serves the rest.
 #include "common.cuh"
 #include "ideal_common.cuh"
 
@@ -143,9 +145,154 @@ fir2d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t he
     }
 }
 
+
+// Several output rows per lane (R), 32-byte output groups: a lane owns G = 4 float64 / 8 float32 adjacent columns of R
+// consecutive output rows and walks the R + KH - 1 image rows under them ONCE, from the bottom one up — so that every
+// output still receives its window rows in ascending m — converting each row's G + 4 samples once and feeding every output
+// row it belongs to.  Conversions per pixel: (R + KH - 1) (G + 4) / (R G) = 4 for 5x5 float64 at R = 4, against 15 for the
+// one-row form above; loads 3 aligned chunks per image row, one 256-bit store per output row.  Needs the rows' chunks
+// aligned alike (pitches multiples of the group, x and y at the same element offset modulo the group); other images take
+// the one-row kernel.
+constexpr int kThreadsRows = 128;
+
+template <typename InT, typename F, int KH, int KW, int R>
+__global__ void __launch_bounds__(kThreadsRows)
+fir2d_ideal_rows_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t height, int64_t width, int64_t ld_x, int64_t ld_y,
+                        int64_t img_stride_x, int64_t img_stride_y, uint32_t tiles_per_row, uint32_t row_blocks, uint32_t total_tiles,
+                        Taps2F64<KH * KW> h, int64_t halo_top, int64_t halo_bottom)
+{
+    constexpr int kWarps = kThreadsRows / 32;
+    constexpr int G = 32 / (int)sizeof(F);               // outputs per group: one 256-bit store
+    constexpr int ch = KH / 2, cw = KW / 2, lo = KW - 1 - cw;
+    static_assert(lo <= 4 && cw <= 4, "one chunk either side");
+    constexpr int NW = G + 8;                            // converted samples per image row: n0 - 4 ... n0 + G + 3
+    constexpr int WPC = (int)sizeof(InT);                // 32-bit words per 4-sample chunk
+    constexpr int NCH = G / 4 + 2;
+    const int lane = threadIdx.x & 31;
+    const int64_t row_lo = -halo_top, row_hi = height + halo_bottom;
+
+    const uint32_t tile = blockIdx.x * (uint32_t)kWarps + (threadIdx.x >> 5);
+    if (tile >= total_tiles) return;
+    const uint32_t gr = tile / tiles_per_row, tcol = tile - gr * tiles_per_row;
+    const uint32_t b = gr / row_blocks, rb = gr - b * row_blocks;
+    const int64_t i0 = (int64_t)rb * R;
+    const InT *xb = x + b * img_stride_x;
+    F *yb = y + b * img_stride_y;
+    const int pad = (int)((reinterpret_cast<uintptr_t>(yb) / sizeof(F)) % G);   // the same for every row: ld_y is a multiple of G
+    const int64_t n0 = (int64_t)tcol * (32 * G) - pad + lane * G;
+    if (n0 >= width || n0 + G <= 0) return;
+    const bool fast = n0 - 4 >= 0 && n0 + G + 4 <= width;                     // all chunks inside the row
+
+    F a[R][G];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < G; ++e) a[r][e] = (F)0;
+
+    uint32_t raw[R + KH - 1][NCH * WPC];
+    if (fast) {
+#pragma unroll
+        for (int t = 0; t < R + KH - 1; ++t) {
+            const int64_t s = i0 + R - 1 + ch - t;
+            if (s < row_lo || s >= row_hi) continue;
+            const InT *q = xb + s * ld_x + n0 - 4;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if constexpr (sizeof(InT) == 1) raw[t][c] = *reinterpret_cast<const uint32_t *>(q + 4 * c);
+                else {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(q + 4 * c);
+                    raw[t][2 * c] = v.x, raw[t][2 * c + 1] = v.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < R + KH - 1; ++t) {
+        const int64_t s = i0 + R - 1 + ch - t;                                 // image rows from the bottom up
+        if (s < row_lo || s >= row_hi) continue;                               // a row of +0.0 samples changes no sum
+        F w[NW];
+        if (fast) {
+#pragma unroll
+            for (int c = 4 - lo; c < 4 + G + cw; ++c) {
+                if constexpr (sizeof(InT) == 1 && sizeof(F) == 4)
+                    w[c] = __fadd_rn(__uint_as_float(__byte_perm(raw[t][c >> 2], 0x4b000000u, 0x7650u + (c & 3))), -8388608.0f);
+                else if constexpr (sizeof(InT) == 1)
+                    w[c] = pixel_to<F>((int)__byte_perm(raw[t][c >> 2], 0u, 0x4440u + (c & 3)));
+                else
+                    w[c] = pixel_to<F>(prep_sample((int16_t)(raw[t][c >> 1] >> (16 * (c & 1)))));
+            }
+        } else {
+            const InT *xr = xb + s * ld_x;
+#pragma unroll
+            for (int c = 4 - lo; c < 4 + G + cw; ++c) {
+                const int64_t g = n0 - 4 + c;
+                w[c] = (g >= 0 && g < width) ? pixel_to<F>(prep_sample(xr[g])) : (F)0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int m = r - (R - 1) + t;                                     // window row of output row i0 + r that image row s is
+            if (m < 0 || m >= KH) continue;
+#pragma unroll
+            for (int n = 0; n < KW; ++n) {
+#pragma unroll
+                for (int e = 0; e < G; ++e) {
+                    if constexpr (sizeof(F) == 8) a[r][e] = __dadd_rn(a[r][e], __dmul_rn(h.v[m * KW + n], w[4 + cw - n + e]));
+                    else a[r][e] = fmaf((float)h.v[m * KW + n], w[4 + cw - n + e], a[r][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (i0 + r >= height) break;
+        F *dst = yb + (i0 + r) * ld_y + n0;
+        if (n0 >= 0 && n0 + G <= width) {
+            if constexpr (sizeof(F) == 8)
+                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(a[r][0]), "d"(a[r][1]), "d"(a[r][2]), "d"(a[r][3]) : "memory");
+            else
+                asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a[r][0]), "f"(a[r][1]), "f"(a[r][2]),
+                             "f"(a[r][3]), "f"(a[r][4]), "f"(a[r][5]), "f"(a[r][6]), "f"(a[r][7]) : "memory");
+        } else {
+#pragma unroll
+            for (int e = 0; e < G; ++e)
+                if (n0 + e >= 0 && n0 + e < width) dst[e] = a[r][e];
+        }
+    }
+}
+
+template <typename InT, typename F, int KH, int KW>
+int run_rows(const Fir2dArgs &a, const double *h_host)
+{
+    constexpr int R = 4;
+    constexpr int G = 32 / (int)sizeof(F);
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(a.x), ya = reinterpret_cast<uintptr_t>(a.y);
+    const bool aligned = xa % sizeof(InT) == 0 && ya % sizeof(F) == 0 && (xa / sizeof(InT)) % G == (ya / sizeof(F)) % G &&
+                         a.ld_x % G == 0 && a.ld_y % G == 0 && (a.n_img == 1 || (a.img_stride_x % G == 0 && a.img_stride_y % G == 0));
+    if (!aligned) return 0;
+    Taps2F64<KH * KW> h;
+    for (int k = 0; k < KH * KW; ++k) h.v[k] = h_host[k];
+    const int64_t tiles_per_row = (a.width + G - 1 + 32 * G - 1) / (32 * G);      // room for the alignment shift
+    const int64_t row_blocks = (a.height + R - 1) / R;
+    const int64_t total = tiles_per_row * row_blocks * a.n_img;
+    if (total >= 0xffffffffLL) return 0;
+    constexpr int kWarps = kThreadsRows / 32;
+    fir2d_ideal_rows_kernel<InT, F, KH, KW, R><<<(unsigned)((total + kWarps - 1) / kWarps), kThreadsRows, 0, a.stream>>>(
+        (const InT *)a.x, (F *)a.y, a.height, a.width, a.ld_x, a.ld_y, a.img_stride_x, a.img_stride_y, (uint32_t)tiles_per_row,
+        (uint32_t)row_blocks, (uint32_t)total, h, a.halo_top, a.halo_bottom);
+    FIRGPU_CUDA(cudaGetLastError());
+    note_launch(FIRGPU_PATH_STAGED);
+    return 1;
+}
+
 template <typename InT, typename F, int KH, int KW>
 int run(const Fir2dArgs &a, const double *h_host)
 {
+    static const bool one_row = getenv("FIRGPU_IDEAL2D_ONE_ROW") != nullptr;       // A/B knob: the one-row-per-lane kernel
+    if (!one_row) {
+        const int served = run_rows<InT, F, KH, KW>(a, h_host);
+        if (served != 0) return served;
+    }
     constexpr int kGroups = 4;
     constexpr int kWarps = kThreads2I / 32;
     constexpr int kGroup = 16 / (int)sizeof(F);
