@@ -679,3 +679,25 @@ def test_2d_ideal_rows_kernel_bit_identical():
         y = firgpu.fir2d_ideal(body, k, halo_top_valid=band.before, halo_bottom_valid=band.after)
         got[..., band.start:band.stop, :] = y.cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_u8_in_int16_out_store_alignments():
+    """uint8 samples into an int16 container: a thread's 16 outputs are one 256-bit store where the destination is 32-byte
+    aligned and two 128-bit stores elsewhere; every alignment of the output view must give the oracle's values and write
+    nothing outside it."""
+    import torch
+    import firgpu
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, size=(3, 70_000)).astype(np.uint8)
+    xt = torch.from_numpy(x).cuda()
+    for h in ([0.0625, 0.25, 0.375, 0.25, 0.0625], [-0.25, 1.5, -0.25]):
+        for c0, width in ((0, 70_000), (8, 65_536), (16, 40_000), (3, 33_333), (24, 1_000)):
+            out = torch.full((3, 70_100), -77, dtype=torch.int16, device="cuda")
+            firgpu.fir1d_fixed(xt[:, c0:c0 + width], h, out_dtype=np.int16, out=out[:, c0:c0 + width])
+            got = out.cpu().numpy()
+            want = onp.fir1d_fixed(x[:, c0:c0 + width], h).astype(np.int16)
+            assert np.array_equal(got[:, c0:c0 + width], want), (len(h), c0, width)
+            assert (got[:, :c0] == -77).all() and (got[:, c0 + width:] == -77).all(), (len(h), c0, width)
+    flat = torch.from_numpy(x.reshape(-1)).cuda()
+    y = firgpu.fir1d_fixed(flat, [0.25, 0.5, 0.25], out_dtype=np.int16)
+    assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x.reshape(-1), [0.25, 0.5, 0.25]).astype(np.int16))

@@ -207,6 +207,18 @@ __device__ __forceinline__ void store_v4(void *ptr, uint32_t a, uint32_t b, uint
     *reinterpret_cast<uint4 *>(ptr) = make_uint4(a, b, c, d);
 #endif
 }
+// 32 bytes per lane in one instruction (STG.E.ENL2.256): a warp writes 1 KiB of whole sectors.  Two 16-byte stores at a
+// 32-byte lane stride half-fill every sector twice (uint8 in, int16 out: 0.83 of the HBM peak with them).
+__device__ __forceinline__ void store_v8(void *ptr, const uint32_t *o)
+{
+#if FIRGPU_STORE_CS
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+#else
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+#endif
+}
 __device__ __forceinline__ void store_v2(void *ptr, uint32_t a, uint32_t b)
 {
 #if FIRGPU_STORE_CS
@@ -537,6 +549,12 @@ __device__ __forceinline__ void store_chunk(OutT *dst, const uint32_t (&O)[SC * 
     if (vec) {
         if constexpr (NOUT == 2) {
             store_v2(dst, O[0], O[1]);
+        } else if constexpr (NOUT == 8) {
+            if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) store_v8(dst, O);
+            else {
+                store_v4(dst, O[0], O[1], O[2], O[3]);
+                store_v4(dst + 16 / OS, O[4], O[5], O[6], O[7]);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < NOUT; j += 4) store_v4(dst + j * 4 / OS, O[j], O[j + 1], O[j + 2], O[j + 3]);
