@@ -153,7 +153,7 @@ fir2d_ideal_fast_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t he
 // one-row form above; loads 3 aligned chunks per image row, one 256-bit store per output row.  Needs the rows' chunks
 // aligned alike (pitches multiples of the group, x and y at the same element offset modulo the group); other images take
 // the one-row kernel.
-constexpr int kThreadsRows = 128;
+constexpr int kThreadsRows = 128;                     // upper bound; 64 measured equal, 256 (with the looser register bound) 4-6 % slower
 
 template <typename InT, typename F, int KH, int KW, int R>
 __global__ void __launch_bounds__(kThreadsRows)
@@ -161,7 +161,7 @@ fir2d_ideal_rows_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t he
                         int64_t img_stride_x, int64_t img_stride_y, uint32_t tiles_per_row, uint32_t row_blocks, uint32_t total_tiles,
                         Taps2F64<KH * KW> h, int64_t halo_top, int64_t halo_bottom)
 {
-    constexpr int kWarps = kThreadsRows / 32;
+    const int kWarps = (int)(blockDim.x >> 5);
     constexpr int G = 32 / (int)sizeof(F);               // outputs per group: one 256-bit store
     constexpr int ch = KH / 2, cw = KW / 2, lo = KW - 1 - cw;
     static_assert(lo <= 4 && cw <= 4, "one chunk either side");
@@ -261,10 +261,9 @@ fir2d_ideal_rows_kernel(const InT *__restrict__ x, F *__restrict__ y, int64_t he
     }
 }
 
-template <typename InT, typename F, int KH, int KW>
-int run_rows(const Fir2dArgs &a, const double *h_host)
+template <typename InT, typename F, int KH, int KW, int R>
+int run_rows(const Fir2dArgs &a, const double *h_host, int threads)
 {
-    constexpr int R = 4;
     constexpr int G = 32 / (int)sizeof(F);
     const uintptr_t xa = reinterpret_cast<uintptr_t>(a.x), ya = reinterpret_cast<uintptr_t>(a.y);
     const bool aligned = xa % sizeof(InT) == 0 && ya % sizeof(F) == 0 && (xa / sizeof(InT)) % G == (ya / sizeof(F)) % G &&
@@ -276,8 +275,8 @@ int run_rows(const Fir2dArgs &a, const double *h_host)
     const int64_t row_blocks = (a.height + R - 1) / R;
     const int64_t total = tiles_per_row * row_blocks * a.n_img;
     if (total >= 0xffffffffLL) return 0;
-    constexpr int kWarps = kThreadsRows / 32;
-    fir2d_ideal_rows_kernel<InT, F, KH, KW, R><<<(unsigned)((total + kWarps - 1) / kWarps), kThreadsRows, 0, a.stream>>>(
+    const int kWarps = threads / 32;
+    fir2d_ideal_rows_kernel<InT, F, KH, KW, R><<<(unsigned)((total + kWarps - 1) / kWarps), threads, 0, a.stream>>>(
         (const InT *)a.x, (F *)a.y, a.height, a.width, a.ld_x, a.ld_y, a.img_stride_x, a.img_stride_y, (uint32_t)tiles_per_row,
         (uint32_t)row_blocks, (uint32_t)total, h, a.halo_top, a.halo_bottom);
     FIRGPU_CUDA(cudaGetLastError());
@@ -290,7 +289,10 @@ int run(const Fir2dArgs &a, const double *h_host)
 {
     static const bool one_row = getenv("FIRGPU_IDEAL2D_ONE_ROW") != nullptr;       // A/B knob: the one-row-per-lane kernel
     if (!one_row) {
-        const int served = run_rows<InT, F, KH, KW>(a, h_host);
+        static const int threads = getenv("FIRGPU_IDEAL2D_THREADS") ? atoi(getenv("FIRGPU_IDEAL2D_THREADS")) : 128;
+        // rows per lane 2 / 4 / 8 on 8192^2 uint8: 3x3 float64 0.61 / 0.69-0.72 / 0.69, 5x5 float64 0.31 / 0.35 / 0.30-0.33,
+        // float32 0.58 / 0.61 / 0.52 and 0.34 / 0.34 / 0.26 (profiles/r2_sweep_ideal2d_rows_threads.txt): only 4 is built
+        const int served = run_rows<InT, F, KH, KW, 4>(a, h_host, threads == 64 ? 64 : 128);
         if (served != 0) return served;
     }
     constexpr int kGroups = 4;
