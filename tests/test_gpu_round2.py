@@ -701,3 +701,54 @@ def test_u8_in_int16_out_store_alignments():
     flat = torch.from_numpy(x.reshape(-1)).cuda()
     y = firgpu.fir1d_fixed(flat, [0.25, 0.5, 0.25], out_dtype=np.int16)
     assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x.reshape(-1), [0.25, 0.5, 0.25]).astype(np.int16))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# general 5x5: the newest kernel rows accumulated by FFMA, exactly (csrc/fir2d_tiled.cuh, template parameter FR)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_general_5x5_ffma_rows_are_bit_exact(fg, torch, monkeypatch):
+    """0 / 1 / 2 kernel rows of the general 5x5 kernel run as float multiply-adds whose partial sums the host proved to
+    stay inside one 2^23-wide window of exactly representable integers.  Every setting must equal the integer oracle:
+    saturated regions (all pixels 255 under taps at the admission limit 255 * sum|taps| < 2^23, one count below it and
+    one above it, where the library must fall back to fewer rows), all-negative rows (the window's base), the
+    shift-by-16 pre-scale (Q1.15: float sum shifted left by one), plain shift, the live acc_bits wrap, uint8 / int16
+    pixels and the narrowing output, ragged strips and bands.  The FFMA variants were measured slower than dp2a alone
+    (profiles/README.md R2.5c) and are compiled only with -DFIRGPU_T2_FFMA=1; a library without them ignores the
+    setting and the three passes check the shipped kernel against the same edge cases."""
+    from firgpu import _lib
+    rng = np.random.default_rng(2025)
+
+    def kernel(row0, row1=None, scale=200):
+        hq = rng.integers(-scale, scale + 1, size=(5, 5)).astype(np.int32)
+        hq[0] = row0
+        if row1 is not None:
+            hq[1] = row1
+        return hq
+
+    kernels = [
+        ("random q4.12", rng.integers(-1200, 1201, size=(5, 5)).astype(np.int32), 12, 32),
+        ("random q1.15 (pre-scale 2)", rng.integers(-3000, 3001, size=(5, 5)).astype(np.int32), 15, 32),
+        ("random q4.12, 20-bit accumulator", rng.integers(-1200, 1201, size=(5, 5)).astype(np.int32), 12, 20),
+        ("random q4.12, live 16-bit wrap", rng.integers(-1200, 1201, size=(5, 5)).astype(np.int32), 12, 16),
+        ("row 0 all negative", kernel([-900, -1, -2000, -30, -1500]), 12, 32),
+        ("row 0 at the limit", kernel([8224, -8224, 8224, -8224, 0]), 12, 32),              # 255 * 32896 = 2^23 - 128
+        ("row 0 at the limit, negative", kernel([-8224, -8224, -8224, -8223, -1]), 12, 32),
+        ("row 0 one above the limit", kernel([8224, -8224, 8225, -8224, 0]), 12, 32),       # falls back to dp2a
+        ("rows 0 + 1 at the limit", kernel([4000, -4000, 4000, -4000, 448], [4000, 4000, -4000, -4000, 448]), 12, 32),
+        ("rows 0 + 1 above, row 0 below", kernel([4000, -4000, 4000, -4000, 448], [4000, 4000, -4000, -4000, 449]), 12, 32),
+        ("wide taps, plain shift q8.8", kernel([30000, -2000, 500, -300, 96], scale=3000), 8, 32),
+    ]
+    for dtype, out_dtypes, shape in ((np.int16, (np.int16, np.uint8), (2, 75, 2000)), (np.uint8, (np.uint8,), (1, 140, 4064))):
+        x = signal(rng, shape, dtype, wild=0.02)
+        x[..., 10:60, 100:700] = 255                     # saturated block: the extreme partial sums
+        x[..., 20:50, 900:1200] = np.where(rng.random((30, 300)) < 0.5, 255, 0).astype(dtype)
+        xt = torch.from_numpy(x).cuda()
+        for name, hq, frac, acc_bits in kernels:
+            for out_dtype in out_dtypes:
+                want = c_oracle.fir2d_fixed(x, hq, frac, acc_bits, out_dtype=out_dtype, threads=CORES)
+                for rows in ("0", "1", "2"):
+                    monkeypatch.setenv("FIRGPU_T2_FFMA_ROWS", rows)
+                    got = fg.fir2d_fixed_q(xt, hq, frac, acc_bits, out_dtype=out_dtype)
+                    assert _lib.last_path() == _lib.PATH_STAGED, (name, dtype, rows)
+                    assert np.array_equal(got.cpu().numpy(), want), (name, dtype, out_dtype, rows)
+    monkeypatch.delenv("FIRGPU_T2_FFMA_ROWS")

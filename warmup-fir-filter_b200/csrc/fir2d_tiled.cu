@@ -5,6 +5,7 @@
 #include "fastplan.h"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace firgpu {
 namespace {
@@ -145,10 +146,41 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
     } else {
         for (int m = 0; m < a.kh; ++m) build_pairs(f.taps + m * a.kw, a.kw, kMaxPairs2, p.cp_even[m], p.cp_odd[m]);
         if (a.kh == 5 && a.kw == 5) {
+            // Kernel rows 0 .. fr-1 (the newest input rows) as exact FFMA sums on the other FMA pipe (fir2d_tiled.cuh,
+            // fir2d_tiled_kernel): admitted when every partial sum of their products stays inside a 2^23-wide window.
+            // The float taps are the UNSCALED hq (the dp2a taps may carry the shift-by-16 pre-scale, applied to the
+            // float sum as a left shift when it joins the int32 accumulator).
+            int fr = 0;                                      // measured slower than dp2a alone (profiles/README.md R2.5c)
+#if FIRGPU_T2_FFMA
+            if (const char *e = getenv("FIRGPU_T2_FFMA_ROWS")) fr = atoi(e);
+#endif
+            if (fr < 0) fr = 0;
+            if (fr > 2) fr = 2;
+            const int fsh = f.hi16 ? 16 - a.frac_bits : 0;
+            for (; fr > 0; --fr) {
+                long long sum_abs = 0;
+                for (int k = 0; k < fr * a.kw; ++k) sum_abs += hq[k] < 0 ? -(long long)hq[k] : (long long)hq[k];
+                if (255LL * sum_abs < (1LL << 23)) break;
+            }
+            p.ffma_rows = fr;
+            if (fr > 0) {
+                long long neg = 0;
+                for (int m = 0; m < fr; ++m)
+                    for (int t = 0; t < 5; ++t) {
+                        const int32_t h = tap_at(hq + m * a.kw, 5, t - 2);      // multiplies the sample at offset t - 2
+                        p.ftap[m][t] = (float)h;                                // |h| < 2^23 / 255: exact
+                        if (h < 0) neg += -(long long)h;
+                    }
+                const uint32_t base_bits = 0x4b000000u + (uint32_t)(255LL * neg);   // bits of 2^23 + 255 * neg (< 2^24)
+                memcpy(&p.fbase, &base_bits, sizeof(float));
+                p.fsh = fsh;
+                p.acc0 = (uint32_t)f.bias - (base_bits << fsh);
+            }
             // the tap of a 5-wide kernel row that has no partner in its row: offset +2 (taps[0]) for windows that start on
-            // an even sample, offset -2 (taps[4]) for odd ones; rows (0,1) and (2,3) share a dp2a (fir2d_tiled.cuh, mac_cross)
-            for (int j = 0; j < 2; ++j) {
-                const int32_t *r0 = f.taps + (2 * j) * a.kw, *r1 = f.taps + (2 * j + 1) * a.kw;
+            // an even sample, offset -2 (taps[4]) for odd ones; the dp2a rows fr, fr+1 (and fr+2, fr+3) share a dp2a
+            // (fir2d_tiled.cuh, mac_cross)
+            for (int j = 0; j < (5 - fr) / 2; ++j) {
+                const int32_t *r0 = f.taps + (fr + 2 * j) * a.kw, *r1 = f.taps + (fr + 2 * j + 1) * a.kw;
                 p.xp_even[j] = pack_pair(tap_at(r0, 5, 2), tap_at(r1, 5, 2));
                 p.xp_odd[j] = pack_pair(tap_at(r0, 5, -2), tap_at(r1, 5, -2));
             }

@@ -81,6 +81,11 @@ using staged::store_v4;
 #ifndef FIRGPU_T2_MINBLOCKS
 #define FIRGPU_T2_MINBLOCKS 3
 #endif
+#ifndef FIRGPU_T2_FFMA
+#define FIRGPU_T2_FFMA 0          // 1: also build the general 5x5 kernel with 1 / 2 kernel rows on FFMA (FIRGPU_T2_FFMA_ROWS selects
+                                  // them at run time).  Bit-exact but measured SLOWER (0.57 -> 0.50 / 0.48 of the HBM peak,
+                                  // profiles/r2_ab_fir2d_5x5_ffma_rows.jsonl), so the shipped library does not carry them.
+#endif
 #ifndef FIRGPU_T2_WARPSPEC
 #define FIRGPU_T2_WARPSPEC 1      // 1: dedicated TMA producer warp + per-stage empty barriers; 0: __syncthreads per stage
 #endif
@@ -112,6 +117,12 @@ struct TiledParams {
     uint32_t xp_even[2], xp_odd[2];              // general 5x5: the odd tap of kernel rows (0,1) and (2,3) paired ACROSS rows
     uint32_t rp_even[kMaxPairs2], rp_odd[kMaxPairs2];   // separable: row-pass pairs (vector b)
     int32_t col_taps[kMaxKH];                    // separable: column taps (vector a, pre-scaled)
+    // general 5x5, FR > 0: the newest FR kernel rows run as FFMA on the other FMA pipe (see fir2d_tiled_kernel)
+    int ffma_rows;                               // FR chosen by the host (0: all 25 taps on dp2a)
+    float ftap[2][5];                            // UNSCALED integer taps of kernel rows 0 / 1 by sample offset (-2 .. +2)
+    float fbase;                                 // 2^23 + 255 * sum of the negative taps' magnitudes
+    uint32_t acc0;                               // accumulator start: bias - (bits(fbase) << fsh)  (mod 2^32)
+    int fsh;                                     // the dp2a taps' pre-scale (16 - frac_bits in the shift-by-16 form, else 0)
 };
 
 template <typename T, int KH, int KW> struct Geo2 {
@@ -215,7 +226,19 @@ __device__ __forceinline__ void mac_cross(uint32_t even, uint32_t odd, const uin
     }
 }
 
-template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T>
+// FR (general 5x5 only; an experiment kept for the record, compiled with -DFIRGPU_T2_FFMA=1 only): the dp2a pipe ("heavy"
+// FMA pipe, 64 lanes / clk / SM, shared with IMAD) is the busiest unit of this kernel (70 %), and FFMA issues on the
+// other FMA pipe alongside it (profiles/r1_ubench_pipes.jsonl: dp2a + ffma 119.5 lanes / clk / SM).
+// The newest FR input rows (kernel rows 0 .. FR-1) are therefore accumulated in float, EXACTLY: samples are integers
+// 0 .. 255, taps integers, and the host admits FR > 0 only when 255 * sum|taps of those rows| < 2^23, so that every
+// partial sum, started at fbase = 2^23 + 255 * sum|negative taps|, is an integer in [2^23, 2^24) — representable, hence
+// every FFMA result is exact whatever the order — and the float's low 23 bits ARE the integer sum.  Its bits are added
+// (shifted by the dp2a taps' pre-scale) to the int32 accumulator, whose start value carries minus the constant part.
+// Kernel rows FR .. 4 stay on dp2a: 10 per pixel (FR = 1) or 8 (FR = 2) instead of 13.
+// Measured (profiles/r2_ab_fir2d_5x5_ffma_rows.jsonl): bit-equal outputs, 15 - 20 % SLOWER — 3 dp2a per pixel become
+// 5 FFMA + 1.5 byte-to-float conversions (PRMT + FADD) + 1 add, and the kernel is not bound by the pipe's throughput but
+// by how many instructions three warps per scheduler get issued.  FR = 0 is what ships.
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0>
 __global__ void __launch_bounds__(kBlock2, FIRGPU_T2_MINBLOCKS)
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
@@ -331,6 +354,10 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     int Rw[SEP ? KH : 1][G1::S];                  // separable: horizontal sums
     constexpr bool kCross = !SEP && KH == 5 && KW == 5;      // general 5x5: left-over taps paired across kernel rows
     uint32_t Vw[kCross ? KH : 1][2 * G1::NB];     // ... row rr interleaved bytewise with the row before it
+    static_assert(FR == 0 || (kCross && FR <= 2), "FFMA rows exist for the general 5x5 kernel only");
+    constexpr int NC = kCross ? (KH - FR) / 2 : 0;           // cross-paired kernel-row pairs (FR + 2j, FR + 2j + 1)
+    constexpr int NF = G1::S + KW - 1;                       // float samples per row: offsets -lo .. S - 1 + hi
+    [[maybe_unused]] float Fprev[FR > 1 ? NF : 1];           // FR = 2: the previous row's float samples
 
     int stage = 0;
     uint32_t phase_bits = 0;
@@ -385,26 +412,53 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 }
                             }
                         }
+                        [[maybe_unused]] float Fnew[FR > 0 ? NF : 1];      // this row's samples as floats: 2^23 + byte, minus 2^23
+                        if constexpr (FR > 0) {
+#pragma unroll
+                            for (int e = 0; e < NF; ++e) {
+                                const int sidx = G1::HL4 - G1::lo + e;  // byte of the packed row
+                                const uint32_t bits = __byte_perm(Bnew[sidx >> 2], 0x4b000000u, 0x7440u | (uint32_t)(sidx & 3));
+                                Fnew[e] = __uint_as_float(bits) - 8388608.0f;
+                            }
+                        }
                         if (o >= 0 && o < rows_here) {
                             int acc[G1::S];
 #pragma unroll
-                            for (int i = 0; i < G1::S; ++i) acc[i] = p.bias;
+                            for (int i = 0; i < G1::S; ++i) acc[i] = FR > 0 ? (int)p.acc0 : p.bias;
+                            [[maybe_unused]] float accf[FR > 0 ? G1::S : 1];
+                            if constexpr (FR > 0) {
 #pragma unroll
-                            for (int m = 0; m < KH; ++m) {
+                                for (int i = 0; i < G1::S; ++i) accf[i] = p.fbase;
+#pragma unroll
+                                for (int m = 0; m < FR; ++m)
+#pragma unroll
+                                    for (int t = 0; t < KW; ++t)
+#pragma unroll
+                                        for (int i = 0; i < G1::S; ++i)
+                                            accf[i] = __fmaf_rn(p.ftap[m][t], m == 0 ? Fnew[i + t] : Fprev[i + t], accf[i]);
+                            }
+#pragma unroll
+                            for (int m = FR; m < KH; ++m) {
                                 const int slot = (rr - m + KH) % KH;   // input row (newest - m) <-> kernel row m
                                 if constexpr (SEP) {
 #pragma unroll
                                     for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
                                 } else if constexpr (kCross) {
-                                    if (m < 4) mac_row_pairs<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
+                                    if (m < FR + 2 * NC) mac_row_pairs<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                     else mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                 } else {
                                     mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                 }
                             }
-                            if constexpr (kCross) {       // kernel rows (0,1) <-> input rows (rr, rr-1); (2,3) <-> (rr-2, rr-3)
-                                mac_cross<G1>(p.xp_even[0], p.xp_odd[0], Vw[rr], acc);
-                                mac_cross<G1>(p.xp_even[1], p.xp_odd[1], Vw[(rr + KH - 2) % KH], acc);
+                            if constexpr (kCross) {       // kernel rows (FR+2j, FR+2j+1) <-> input rows (rr-FR-2j, rr-FR-2j-1)
+#pragma unroll
+                                for (int j = 0; j < NC; ++j)
+                                    mac_cross<G1>(p.xp_even[j], p.xp_odd[j], Vw[(rr + 2 * KH - FR - 2 * j) % KH], acc);
+                            }
+                            if constexpr (FR > 0) {
+#pragma unroll
+                                for (int i = 0; i < G1::S; ++i)
+                                    acc[i] = (int)((uint32_t)acc[i] + (__float_as_uint(accf[i]) << p.fsh));
                             }
                             uint32_t V[G1::S / 2];
 #pragma unroll
@@ -431,6 +485,10 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 }
                             }
                         }
+                        if constexpr (FR > 1) {
+#pragma unroll
+                            for (int e = 0; e < NF; ++e) Fprev[e] = Fnew[e];
+                        }
                     }
                 }
             }
@@ -447,11 +505,11 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 
 // ---- launch helpers -------------------------------------------------------------
-template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T>
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0>
 int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t stream)
 {
     using G = Geo2<T, KH, KW>;
-    auto kern = fir2d_tiled_kernel<T, KH, KW, POST, SEP, OutT>;
+    auto kern = fir2d_tiled_kernel<T, KH, KW, POST, SEP, OutT, FR>;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -521,6 +579,26 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
 template <typename T, int KH, int KW, bool SEP, typename OutT>
 int launch_tiled_post(const CUtensorMap &map, const TiledParams &p, int post, cudaStream_t s)
 {
+#if FIRGPU_T2_FFMA
+    if constexpr (!SEP && KH == 5 && KW == 5) {     // general 5x5: FFMA rows where the host proved them exact
+        if (p.ffma_rows == 1) {
+            switch (post) {
+            case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT, 1>(map, p, s);
+            case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT, 1>(map, p, s);
+            case POST_WRAP: return launch_tiled_one<T, KH, KW, POST_WRAP, SEP, OutT, 1>(map, p, s);
+            default: return 0;
+            }
+        }
+        if (p.ffma_rows == 2) {
+            switch (post) {
+            case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT, 2>(map, p, s);
+            case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT, 2>(map, p, s);
+            case POST_WRAP: return launch_tiled_one<T, KH, KW, POST_WRAP, SEP, OutT, 2>(map, p, s);
+            default: return 0;
+            }
+        }
+    }
+#endif
     switch (post) {
     case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT>(map, p, s);
     case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT>(map, p, s);
