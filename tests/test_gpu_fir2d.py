@@ -256,3 +256,59 @@ def test_full_size_image_properties():
         yt = firgpu.fir2d_fixed(x.transpose(1, 2).contiguous(), k, 12, 32, 16, out_dtype=np.int16)
         assert torch.equal(yt.transpose(1, 2), y)
         del y, yt
+
+
+def test_windows_up_to_7x7_and_even_sizes_run_on_the_tensor_map_kernel():
+    """Every window from 1x2 to 7x7 — odd sizes instantiated, even sizes by a zero row / column appended at the end, which
+    keeps the model's centre L // 2 — is served by the tensor-map kernel and is bit-exact against the oracle: general
+    and exactly rank-1 kernels, uint8 / int16 pixels, the narrowing output, Q4.12 / Q1.15, a live 16-bit accumulator
+    wrap, borders, ragged strips, several images, and row-band shards of an even-height window (asymmetric halo)."""
+    import firgpu
+    from firgpu import _lib, quant, shard
+    rng = np.random.default_rng(77)
+    g7 = np.array([1, 6, 15, 20, 15, 6, 1]) / 64.0
+    x16 = image(rng, (2, 90, 1000), np.int16)
+    x8 = image(rng, (1, 75, 2032), np.uint8)
+    t16, t8 = cuda(x16), cuda(x8)
+    n = 0
+    for kh in range(1, 8):
+        for kw in range(1, 8):
+            if kh == 1 and kw == 1:
+                continue
+            ks = [(rng.uniform(-0.25, 0.25, size=(kh, kw)), 12, 32)]
+            if max(kh, kw) >= 6 or (kh % 2 == 0 and kw % 2 == 0):
+                ks.append((np.outer(g7[:kh] / g7[:kh].sum(), g7[:kw] / g7[:kw].sum()), 15, 32))      # rank-1 before quantisation
+                ks.append((rng.uniform(-0.5, 0.5, size=(kh, kw)), 12, 16))                            # live wrap
+            for k, frac, acc in ks:
+                hq = quant.quantize_taps(k, frac, 16)
+                for x, xt, outs in ((x16, t16, (np.int16, np.uint8)), (x8, t8, (np.uint8,))):
+                    for out_dtype in outs:
+                        want = c_oracle.fir2d_fixed(x, hq, frac, acc, out_dtype=out_dtype, threads=8)
+                        got = firgpu.fir2d_fixed_q(xt, hq, frac, acc, out_dtype=out_dtype)
+                        assert _lib.last_path() == _lib.PATH_STAGED, (kh, kw, x.dtype)
+                        assert np.array_equal(got.cpu().numpy(), want), (kh, kw, frac, acc, x.dtype, out_dtype)
+                        n += 1
+    assert n >= 200
+    # an exactly rank-1 integer 7x7 kernel (the separable instantiation) and its row-band shards; a 6x4 window in bands
+    a = np.array([1, 6, 15, 20, 15, 6, 1], dtype=np.int32)
+    img = image(rng, (1, 400, 1024), np.int16)
+    it = cuda(img)
+    for hq, frac in ((np.outer(a, a), 12), (rng.integers(-300, 300, size=(6, 4)).astype(np.int32), 12)):
+        kh = hq.shape[0]
+        want = c_oracle.fir2d_fixed(img, hq, frac, 32, out_dtype=np.int16, threads=8)
+        assert np.array_equal(firgpu.fir2d_fixed_q(it, hq, frac, 32, out_dtype=np.int16).cpu().numpy(), want)
+        got = np.empty_like(want)
+        for band in shard.plan_bands(400, 3, kh):
+            buf, body = shard.scatter_band(img, band, "cuda")
+            y = firgpu.fir2d_fixed_q(body, hq, frac, 32, out_dtype=np.int16, halo_top_valid=band.before, halo_bottom_valid=band.after)
+            assert _lib.last_path() == _lib.PATH_STAGED
+            got[:, band.start:band.stop, :] = y.cpu().numpy()
+        assert np.array_equal(got, want), kh
+    # batches of short rows through the 1-D entry: 2, 4, 6 and 7 taps now take the row-streaming form as 3 and 5 do
+    rows = image(rng, (40, 1000), np.int16)
+    rt = cuda(rows)
+    for taps in (2, 4, 6, 7):
+        h = rng.uniform(-0.3, 0.3, size=taps).tolist()
+        got = firgpu.fir1d_fixed(rt, h, 12, 32, 16, out_dtype=np.int16)
+        assert _lib.last_path() == _lib.PATH_STAGED
+        assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(rows, h, 12, 32, 16, out_dtype=np.int16)), taps

@@ -246,6 +246,24 @@ def main():
             hq = quant.quantize_taps(np.asarray(k), 12, 16)
             s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out=out), args.reps)
             report(f"2d 2999x4499 u8->u8 {tag} q4.12 (odd pitch)", s, 2999 * 4499, 2)
+    if "2dwin" in cases:
+        # windows beyond 5x5 and even sizes on the tensor-map kernel (FIRGPU_FORCE_GENERIC=1 in the environment times the
+        # one-thread-per-pixel int64 kernel they ran on before)
+        img = rand_i16(8192 * 8192).view(1, 8192, 8192)
+        out = torch.empty_like(img)
+        g7 = np.array([1, 6, 15, 20, 15, 6, 1]) / 64.0
+        rng7 = np.random.default_rng(7)
+        for hq, tag in ((np.outer([1, 6, 15, 20, 15, 6, 1], [1, 6, 15, 20, 15, 6, 1]), "7x7 binomial rank-1"),
+                        (quant.quantize_taps(rng7.uniform(-0.1, 0.1, size=(7, 7)), 12, 16), "7x7 general"),
+                        (quant.quantize_taps(rng7.uniform(-0.2, 0.2, size=(3, 7)), 12, 16), "3x7 general"),
+                        (quant.quantize_taps(rng7.uniform(-0.2, 0.2, size=(7, 3)), 12, 16), "7x3 general"),
+                        (quant.quantize_taps(np.outer(g7, [0.25, 0.5, 0.25]), 12, 16), "7x3 as quantised"),
+                        (quant.quantize_taps(rng7.uniform(-0.2, 0.2, size=(4, 4)), 12, 16), "4x4 general (zero-padded to 5x5)"),
+                        (quant.quantize_taps(rng7.uniform(-0.3, 0.3, size=(2, 2)), 12, 16), "2x2 general (zero-padded to 3x3)")):
+            hq = np.ascontiguousarray(hq, dtype=np.int32)
+            s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out_dtype=np.int16, out=out), args.reps, warm=2)
+            report(f"2d 8192^2 i16->i16 {tag} q4.12", s, 8192 * 8192, 4)
+        del img, out
     if "compare" in cases:
         # fused fixed-vs-ideal metrics: 1 B read per sample, seven numbers out (the call synchronises to return them)
         for hgt, wid in ((64, 64), (2999, 4499), (8192, 16384)):

@@ -775,7 +775,7 @@ int firgpu_fir2d_fixed(const void *x, void *y, int in_dtype, int out_dtype, int6
     // Images the tensor-map kernel cannot read in place are copied once into an aligned temporary and filtered there:
     // int32 / float containers (rounded and clamped to uint8 pixels on the way), and uint8 / int16 images whose pitch
     // or base is not 16-byte aligned or whose uint8 width is odd (every row of the copy ends in zero bytes).
-    const bool windows_ok = (kh == 1 || kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5) && !(kh == 1 && kw == 1);
+    const bool windows_ok = fir2d_tiled_window_ok(kh, kw);
     const int es_in = dtype_size(in_dtype);
     const bool convert = out_dtype == FIRGPU_U8 && convert_first(in_dtype, n_img * height * width);
     const bool repitch = !convert && (in_dtype == FIRGPU_U8 || in_dtype == FIRGPU_I16) &&

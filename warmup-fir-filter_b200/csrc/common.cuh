@@ -219,6 +219,7 @@ int launch_fir2d_ideal(const Fir2dArgs &a, const double *h_host);
 // fir2d_ideal_fast.cu — 1 = served, 0 = not eligible
 int try_launch_fir2d_ideal_fast(const Fir2dArgs &a, const double *h_host);
 int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq_host);
+bool fir2d_tiled_window_ok(int kh, int kw);      // window sizes the tensor-map kernel serves (even sizes by zero padding)
 
 // api.cu — stream-ordered scratch memory from the library's own pool (keeps its pages between calls); free with
 // cudaFreeAsync on the same stream

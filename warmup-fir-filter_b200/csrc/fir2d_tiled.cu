@@ -91,8 +91,27 @@ bool factor_rank1(const int32_t *hq, int kh, int kw, long long *a, long long *b)
 
 }  // namespace
 
-int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a, const int32_t *hq)
+bool fir2d_tiled_window_ok(int kh, int kw)
 {
+    return kh >= 1 && kw >= 1 && kh <= kMaxWindow && kw <= kMaxWindow && shape_supported(kh | 1, kw | 1);
+}
+
+int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a_in, const int32_t *hq_in)
+{
+    // Even window sizes: a zero row / column appended at the END keeps the centre (L // 2 == (L + 1) // 2 for even L,
+    // fir_1d_fixed_ref.py:98-107 convention in both directions) and adds nothing to any sum or bound.
+    if (a_in.kh < 1 || a_in.kw < 1 || a_in.kh > kMaxKH || a_in.kw > kMaxKH) return 0;
+    Fir2dArgs a = a_in;
+    int32_t padded[kMaxKH * kMaxKH];
+    const int32_t *hq = hq_in;
+    if (!(a.kh & 1) || !(a.kw & 1)) {
+        a.kh = a_in.kh | 1;
+        a.kw = a_in.kw | 1;
+        if (a.kh > kMaxKH || a.kw > kMaxKH) return 0;
+        for (int m = 0; m < a.kh; ++m)
+            for (int n = 0; n < a.kw; ++n) padded[m * a.kw + n] = (m < a_in.kh && n < a_in.kw) ? hq_in[m * a_in.kw + n] : 0;
+        hq = padded;
+    }
     const bool narrowing = a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8;       // int16 pixels in, uint8 out
     if ((a.in_dtype != a.out_dtype && !narrowing) || (a.in_dtype != FIRGPU_U8 && a.in_dtype != FIRGPU_I16)) return 0;
     if (!shape_supported(a.kh, a.kw)) return 0;

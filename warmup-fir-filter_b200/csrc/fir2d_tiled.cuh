@@ -98,8 +98,8 @@ constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a st
 constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
 constexpr int kMapElemBytes = 2;                 // the tensor map always describes 16-bit elements: int16 pixels, or PAIRS of
                                                  // uint8 pixels (even widths), so that a box row is 512 bytes for both
-constexpr int kMaxKH = 5;
-constexpr int kMaxPairs2 = 3;                    // KW <= 5
+constexpr int kMaxKH = 7;
+constexpr int kMaxPairs2 = 4;                    // KW <= 7
 
 struct TiledParams {
     unsigned char *y;
@@ -239,7 +239,7 @@ __device__ __forceinline__ void mac_cross(uint32_t even, uint32_t odd, const uin
 // 5 FFMA + 1.5 byte-to-float conversions (PRMT + FADD) + 1 add, and the kernel is not bound by the pipe's throughput but
 // by how many instructions three warps per scheduler get issued.  FR = 0 is what ships.
 template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0>
-__global__ void __launch_bounds__(kBlock2, FIRGPU_T2_MINBLOCKS)
+__global__ void __launch_bounds__(kBlock2, (KH > 5 && SEP && sizeof(T) == 1 ? 2 : FIRGPU_T2_MINBLOCKS))   // 7 rows x 16 horizontal sums
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
     using G = Geo2<T, KH, KW>;
@@ -627,14 +627,30 @@ int launch_tiled_shape(const CUtensorMap &map, const TiledParams &p, int kh, int
     if (kh == 5 && kw == 1) return launch_tiled_modes<T, 5, 1, OutT>(map, p, post, sep, s);
     if (kh == 5 && kw == 3) return launch_tiled_modes<T, 5, 3, OutT>(map, p, post, sep, s);
     if (kh == 5 && kw == 5) return launch_tiled_modes<T, 5, 5, OutT>(map, p, post, sep, s);
+#if !FIRGPU_QUICK
+    if (kh == 1 && kw == 7) return launch_tiled_modes<T, 1, 7, OutT>(map, p, post, sep, s);
+    if (kh == 7 && kw == 1) return launch_tiled_modes<T, 7, 1, OutT>(map, p, post, sep, s);
+    if (kh == 3 && kw == 7) return launch_tiled_modes<T, 3, 7, OutT>(map, p, post, sep, s);
+    if (kh == 7 && kw == 3) return launch_tiled_modes<T, 7, 3, OutT>(map, p, post, sep, s);
+    if (kh == 5 && kw == 7) return launch_tiled_modes<T, 5, 7, OutT>(map, p, post, sep, s);
+    if (kh == 7 && kw == 5) return launch_tiled_modes<T, 7, 5, OutT>(map, p, post, sep, s);
+    if (kh == 7 && kw == 7) return launch_tiled_modes<T, 7, 7, OutT>(map, p, post, sep, s);
+#endif
     return 0;
 }
 
 // Does the (kh, kw) shape have a separable instantiation?
 inline bool shape_has_separable(int kh, int kw) { return kh > 1 && kw >= 3 && !(kh == 3 && kw == 3); }
+#if FIRGPU_QUICK
+constexpr int kMaxWindow = 5;
+#else
+constexpr int kMaxWindow = 7;
+#endif
+// Instantiated windows: odd heights and widths up to 7 (the QUICK build: 5), except 1x1.  Even sizes ride on the next
+// odd one (fir2d_tiled.cu appends a zero row / column, which keeps the reference's centre L // 2).
 inline bool shape_supported(int kh, int kw)
 {
-    return ((kh == 3 || kh == 5) && (kw == 1 || kw == 3 || kw == 5)) || (kh == 1 && (kw == 3 || kw == 5));
+    return (kh & 1) && (kw & 1) && kh >= 1 && kw >= 1 && kh <= kMaxWindow && kw <= kMaxWindow && !(kh == 1 && kw == 1);
 }
 int launch_tiled_u8(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s);
 int launch_tiled_i16(const CUtensorMap &map, const TiledParams &p, int kh, int kw, int post, bool sep, cudaStream_t s);
