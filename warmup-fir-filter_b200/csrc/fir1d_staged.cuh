@@ -72,6 +72,15 @@ template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<FIRGPU_K_THREADS
 template <> struct TuneFor<int16_t, int16_t> { using type = Cfg<256, 8, 2, 1, 1>; };   // 6592 GB/s
 template <> struct TuneFor<int16_t, uint8_t> { using type = Cfg<256, 6, 2, 1, 2>; };   // 6463 GB/s
 template <> struct TuneFor<uint8_t, uint8_t> { using type = Cfg<256, 4, 2, 2, 2>; };   // 6310 GB/s
+// uint8 in, int16 out writes two bytes per byte read: half the bulk reads in flight (8 KiB tiles, 32 KiB per SM) suit that
+// mix — 0.95 of the HBM peak against 0.84 with the 16 KiB default; 4 KiB tiles 0.72, 12 KiB 0.89, 32 KiB x 1 CTA 0.89,
+// three stages 0.88, three CTAs 0.86 (profiles/r2_sweep_u8_in_i16_out_tile_configs.txt)
+#ifndef FIRGPU_U8I16_SUB
+template <> struct TuneFor<uint8_t, int16_t> { using type = Cfg<256, 2, 2, 2, 2>; };
+#endif
+#ifdef FIRGPU_U8I16_SUB        // tools/build_u8i16_variants.sh: one explicit configuration of the uint8 -> int16 kernel
+template <> struct TuneFor<uint8_t, int16_t> { using type = Cfg<256, FIRGPU_U8I16_SUB, FIRGPU_U8I16_STAGES, FIRGPU_U8I16_MINBLOCKS, FIRGPU_U8I16_CTAS>; };
+#endif
 #endif
 // Rows shorter than two long-row tiles: 8 KiB tiles, three CTAs per SM.
 using SmallRowCfg = Cfg<256, 2, 3, 3, 3>;
