@@ -93,7 +93,10 @@ constexpr int kThreads2 = FIRGPU_T2_THREADS;
 constexpr int kStages2 = FIRGPU_T2_STAGES;
 constexpr int kBlock2 = kThreads2 + (FIRGPU_T2_WARPSPEC ? 32 : 0);   // consumer threads (+ one producer warp)
 constexpr int kBandTarget = 64;                  // output rows per band, about
-inline constexpr int rows_per_stage(int kh) { return kh == 1 ? 8 : kh * (kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
+#ifndef FIRGPU_T2_RPS7
+#define FIRGPU_T2_RPS7 1          // ... for KH == 7 (measured: one row group per stage 972 / 435 Gpixel/s rank-1 / general 7x7, two 758 / 358)
+#endif
+inline constexpr int rows_per_stage(int kh) { return kh == 1 ? 8 : kh * (kh >= 6 ? FIRGPU_T2_RPS7 : kh >= 4 ? FIRGPU_T2_RPS5 : FIRGPU_T2_RPS3); }
 constexpr int kStripBytes = kThreads2 * 16;      // staged bytes per row of a strip
 constexpr int kBoxElems = 256;                   // TMA box width limit (elements)
 constexpr int kMapElemBytes = 2;                 // the tensor map always describes 16-bit elements: int16 pixels, or PAIRS of
