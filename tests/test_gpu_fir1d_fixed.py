@@ -408,9 +408,7 @@ def test_float_and_int32_containers_use_the_fast_kernels(fg, torch):
         for h, frac in ((SIMPLE_LP5, 15), ([0.25, 0.5, 0.25], 12), ((np.ones(21) / 42).tolist(), 15)):
             for out_dtype in (np.uint8, np.int16):
                 y = fg.fir1d_fixed(torch.from_numpy(x).cuda(), h, frac, 32, 16, out_dtype=out_dtype)
-                # (filters longer than 9 taps are instantiated for equal container types only)
-                want_path = _lib.PATH_GENERIC if len(h) > 9 and out_dtype is np.int16 else _lib.PATH_STAGED
-                assert _lib.last_path() == want_path, (x.dtype, len(h), out_dtype)
+                assert _lib.last_path() == _lib.PATH_STAGED, (x.dtype, len(h), out_dtype)
                 assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h, frac, 32, 16, out_dtype=out_dtype)), (x.dtype, len(h), out_dtype)
     x = rng.uniform(-30, 300, size=150_000)
     want = onp.fir1d_fixed(x, SIMPLE_LP5, 15, 32, 16)
@@ -531,3 +529,27 @@ def test_long_filters_int16_in_uint8_out(fg, torch):
     rows = signal(rng, (5, 40_000), np.int16)
     h = (np.ones(17) / 17).tolist()
     assert np.array_equal(fg.fir1d_fixed(torch.from_numpy(rows).cuda(), h).cpu().numpy(), onp.fir1d_fixed(rows, h))
+
+
+def test_long_filters_uint8_in_int16_out(fg, torch):
+    """10..65 taps on uint8 samples with the values delivered in an int16 container (32-byte stores per 16-byte input
+    chunk): the last container pair to get long-filter buckets — bit-exact, every bucket, odd lengths and offsets,
+    a live accumulator wrap, rows, and a column view whose stores are not 32-byte aligned."""
+    from firgpu import _lib
+    rng = np.random.default_rng(321)
+    x = signal(rng, 300_001, np.uint8)
+    xt = torch.from_numpy(x).cuda()
+    for n_taps in (10, 13, 16, 21, 33, 50, 64, 65):
+        h = (rng.uniform(-1, 1, size=n_taps) / n_taps * 4).tolist()
+        for frac, acc in ((12, 32), (15, 32), (12, 16)):
+            got = fg.fir1d_fixed(xt, h, frac, acc, 16, out_dtype=np.int16)
+            assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, frac, acc)
+            assert got.dtype == torch.int16
+            assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x, h, frac, acc, 16, out_dtype=np.int16)), (n_taps, frac, acc)
+    rows = signal(rng, (6, 40_016), np.uint8)
+    rt = torch.from_numpy(rows).cuda()
+    h = (rng.uniform(-1, 1, size=25) / 8).tolist()
+    for c0, width in ((0, 40_016), (16, 40_000), (3, 39_999)):
+        view = rt[:, c0:c0 + width]
+        got = fg.fir1d_fixed(view, h, 12, 32, 16, out_dtype=np.int16)
+        assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(rows[:, c0:c0 + width], h, 12, 32, 16, out_dtype=np.int16)), (c0, width)

@@ -75,8 +75,7 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     int32_t padded[kMaxFastTaps];
     const int32_t *taps_in = hq_host;
     if (a.n_taps > kMaxWideTaps) {
-        const bool long_pair = a.in_dtype == a.out_dtype || (a.in_dtype == FIRGPU_I16 && a.out_dtype == FIRGPU_U8);
-        if (n_filters != 1 || a.dilation != 1 || !long_pair) return 0;
+        if (n_filters != 1 || a.dilation != 1) return 0;
         for (int b : kLongBuckets)
             if (!bucket && b >= a.n_taps) bucket = b;
         const int off = bucket / 2 - a.n_taps / 2;
@@ -124,7 +123,9 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     for (int f = 0; f < n_filters; ++f) build_pairs(plans[f].taps, n_taps, kMaxPairs, p.cp_even[f], p.cp_odd[f]);
     for (int k = 0; k < n_taps && k < kMaxWideTaps; ++k) p.hq[k] = f0.taps[k];
     if (bucket) {
-        if (a.in_dtype == FIRGPU_U8) return launch_staged_long_u8(p, bucket, post, a.stream);
+        if (a.in_dtype == FIRGPU_U8)
+            return a.out_dtype == FIRGPU_U8 ? launch_staged_long_u8(p, bucket, post, a.stream)
+                                            : launch_staged_long_u8i16(p, bucket, post, a.stream);
         return a.out_dtype == FIRGPU_U8 ? launch_staged_long_i16u8(p, bucket, post, a.stream)
                                         : launch_staged_long_i16(p, bucket, post, a.stream);
     }

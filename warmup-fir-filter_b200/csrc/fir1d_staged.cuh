@@ -970,6 +970,7 @@ int launch_long(const StagedParams &p, int bucket, int post, cudaStream_t s)
 int launch_staged_long_u8(const StagedParams &p, int bucket, int post, cudaStream_t s);
 int launch_staged_long_i16(const StagedParams &p, int bucket, int post, cudaStream_t s);
 int launch_staged_long_i16u8(const StagedParams &p, int bucket, int post, cudaStream_t s);   // int16 samples in, uint8 out
+int launch_staged_long_u8i16(const StagedParams &p, int bucket, int post, cudaStream_t s);   // uint8 samples in, int16 container out
 
 // One translation unit per (input, output, dilation) combination instantiates these
 // (fir1d_staged_inst.cu compiled eight times), which keeps the build parallel.
