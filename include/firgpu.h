@@ -114,7 +114,9 @@ int firgpu_fir1d_fixed(const void *x, void *y, int in_dtype, int out_dtype,
  *   *path  FIRGPU_PATH_STAGED (a fast kernel) or FIRGPU_PATH_GENERIC (int64 kernel)
  *   *post  0 = shift, 1 = taps pre-scaled to a 16-bit shift, 2 = live acc_bits
  *          wrap evaluated in the post stage (fir_1d_fixed_ref.py:110-118)
- *   *mac   0 = dp2a (taps fit int16), 1 = IMAD with 32-bit taps */
+ *   *mac   0 = dp2a (taps fit int16), 1 = IMAD with 32-bit taps
+ * Filters of 66 .. 129 taps: the answer given is the one for int16 samples
+ * (uint8 samples beyond 65 taps run on the generic kernel). */
 int firgpu_fir1d_fixed_plan(const int32_t *hq, int n_taps, int frac_bits, int acc_bits,
                             int *path, int *post, int *mac);
 

@@ -149,7 +149,7 @@ def test_generic_kernel_serves_what_staged_declines(fg, torch):
     cases = [
         (12, 16, 16, [0.9, -0.7, 0.8, 0.3, -0.2], S),     # acc_bits wrap is live
         (28, 32, 32, [7.5, -7.5, 0.001], S),              # 32-bit taps, wrap live
-        (12, 32, 16, rng.uniform(-0.1, 0.1, size=70).tolist(), G),   # longer than the largest staged bucket (65)
+        (12, 32, 16, rng.uniform(-0.1, 0.1, size=130).tolist(), G),  # longer than the largest staged bucket (129)
         (12, 20, 16, [1.0], S),                           # SURVEY 8(c)5 wrap case
         (3, 12, 8, [7.0, -6.5, 3.25, 1.0], S),            # tiny frac_bits, 8-bit taps, wrap live
         (30, 64, 32, [0.4, 0.3], G),                      # 64-bit accumulator, sums beyond int32
@@ -367,19 +367,21 @@ def test_wide_signed_int16_fast_path(fg, torch):
 
 
 def test_long_filters_run_in_staged_buckets(fg, torch):
-    """10..65 taps: served by the staged kernel through zero-padded tap-count
-    buckets (13/17/25/33/49/65) that keep the centre tap in place — bit-exact,
+    """10..129 taps: served by the staged kernel through zero-padded tap-count
+    buckets (13/17/25/33/49/65/97/129) that keep the centre tap in place — bit-exact,
     even and odd lengths, both containers, tile edges and shard halos."""
     from firgpu import _lib, shard
     rng = np.random.default_rng(88)
-    for n_taps in (10, 11, 13, 14, 16, 17, 21, 32, 33, 40, 48, 49, 63, 64, 65):
+    for n_taps in (10, 11, 13, 14, 16, 17, 21, 32, 33, 40, 48, 49, 63, 64, 65, 66, 96, 97, 98, 128, 129):
         h = (rng.uniform(-1, 1, size=n_taps) / n_taps).tolist()
         for dtype in (np.uint8, np.int16):
             for frac in (15, 12):
                 for n in (1, 50, 4095, 16384, 70_001):
                     x = signal(rng, n, dtype)
                     y = fg.fir1d_fixed(torch.from_numpy(x).cuda(), h, frac, 32, 16, out_dtype=dtype)
-                    assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, dtype, frac, n)
+                    # (the 97 / 129-tap buckets exist for int16 samples; uint8 samples beyond 65 taps: generic kernel)
+                    want_path = _lib.PATH_GENERIC if dtype is np.uint8 and n_taps > 65 else _lib.PATH_STAGED
+                    assert _lib.last_path() == want_path, (n_taps, dtype, frac, n)
                     assert np.array_equal(y.cpu().numpy(), onp.fir1d_fixed(x, h, frac, 32, 16, out_dtype=dtype)), (n_taps, dtype, frac, n)
     h = (rng.uniform(-1, 1, size=31) / 31).tolist()
     x = signal(rng, 5 * 9000, np.int16).reshape(5, 9000)
@@ -515,13 +517,13 @@ def test_dense_rows_of_odd_pitch_take_the_flattened_pass(fg, torch):
 
 
 def test_long_filters_int16_in_uint8_out(fg, torch):
-    """10..65 taps on an int16 container with the drop-in's default uint8 output:
+    """10..129 taps on an int16 container with the drop-in's default uint8 output:
     served by the long-filter buckets of the staged kernel, bit-exact."""
     from firgpu import _lib
     rng = np.random.default_rng(123)
     x = signal(rng, 300_001, np.int16)
     xt = torch.from_numpy(x).cuda()
-    for n_taps in (10, 13, 21, 33, 50, 65):
+    for n_taps in (10, 13, 21, 33, 50, 65, 80, 129):
         h = (rng.uniform(-1, 1, size=n_taps) / n_taps * 4).tolist()
         got = fg.fir1d_fixed(xt, h, 12, 32, 16)
         assert _lib.last_path() == _lib.PATH_STAGED, n_taps
@@ -539,11 +541,11 @@ def test_long_filters_uint8_in_int16_out(fg, torch):
     rng = np.random.default_rng(321)
     x = signal(rng, 300_001, np.uint8)
     xt = torch.from_numpy(x).cuda()
-    for n_taps in (10, 13, 16, 21, 33, 50, 64, 65):
+    for n_taps in (10, 13, 16, 21, 33, 50, 64, 65, 90):
         h = (rng.uniform(-1, 1, size=n_taps) / n_taps * 4).tolist()
         for frac, acc in ((12, 32), (15, 32), (12, 16)):
             got = fg.fir1d_fixed(xt, h, frac, acc, 16, out_dtype=np.int16)
-            assert _lib.last_path() == _lib.PATH_STAGED, (n_taps, frac, acc)
+            assert _lib.last_path() == (_lib.PATH_STAGED if n_taps <= 65 else _lib.PATH_GENERIC), (n_taps, frac, acc)
             assert got.dtype == torch.int16
             assert np.array_equal(got.cpu().numpy(), onp.fir1d_fixed(x, h, frac, acc, 16, out_dtype=np.int16)), (n_taps, frac, acc)
     rows = signal(rng, (6, 40_016), np.uint8)

@@ -79,7 +79,7 @@ def test_reference_wrap_vectors_on_the_fast_kernels(fg, torch):
 
 
 def test_golden_wrap_cases_now_run_on_the_staged_kernel(fg, torch, golden_cases):
-    """Every reference-made golden case whose accumulator is at most 32 bits wide and whose filter has at most 65
+    """Every reference-made golden case whose accumulator is at most 32 bits wide and whose filter has at most 9
     taps is served by a fast kernel, bit-exact (device path; the golden file also holds the wrap-live cases)."""
     from firgpu import _lib
     served = wrap_live = 0

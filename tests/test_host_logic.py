@@ -306,7 +306,9 @@ def test_image_view_addressing():
     ([0.001, 0.002], 28, 40, 32, ("staged", "wrap", "imad")),                                 # wider accumulator, sums fit int32
     ([0.4, 0.3], 30, 64, 32, ("generic", None, None)),                                        # sums beyond int32 in a 64-bit accumulator
     ([0.01] * 21, 12, 18, 16, ("staged", "wrap", "dp2a")),                                    # long-filter bucket under a live wrap
-    ([0.01] * 70, 12, 32, 16, ("generic", None, None)),                                       # beyond the largest bucket
+    ([0.01] * 70, 12, 32, 16, ("staged", "hi16", "dp2a")),                                    # 97-tap bucket
+    ([0.005] * 129, 12, 32, 16, ("staged", "hi16", "dp2a")),                                  # the largest bucket
+    ([0.005] * 130, 12, 32, 16, ("generic", None, None)),                                     # beyond the largest bucket
 ])
 def test_fixed_point_datapath_is_chosen_from_the_taps_alone(h, frac, acc, cb, want):
     import firgpu

@@ -165,13 +165,13 @@ def main():
             h = (np.ones(L) / (2 * L)).tolist()
             s = timed(lambda: firgpu.fir1d_fixed(x, h, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
             report(f"stream 2^28 i16->i16 {L}tap q1.15", s, n, 4)
-        for L in (13, 17, 33, 65):
+        for L in (13, 17, 33, 65, 97, 129):
             hl = (np.ones(L) / (2 * L)).tolist()
             s = timed(lambda: firgpu.fir1d_fixed(x, hl, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
             report(f"stream 2^28 i16->i16 {L}tap q1.15 (long-filter bucket)", s, n, 4)
-        h70 = (np.ones(70) / 140).tolist()
-        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], h70, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 26], validate=False), 5)
-        report("stream 2^26 i16->i16 70tap (generic kernel)", s, 1 << 26, 4)
+        h130 = (np.ones(130) / 260).tolist()
+        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 26], h130, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 26], validate=False), 5)
+        report("stream 2^26 i16->i16 130tap (generic kernel)", s, 1 << 26, 4)
         del x, y
     if "batched" in cases:
         for rows, cols in ((8192, 1 << 20), (8192, 1_000_000), (1 << 16, 4096), (1 << 20, 256)):
@@ -246,6 +246,23 @@ def main():
             hq = quant.quantize_taps(np.asarray(k), 12, 16)
             s = timed(lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out=out), args.reps)
             report(f"2d 2999x4499 u8->u8 {tag} q4.12 (odd pitch)", s, 2999 * 4499, 2)
+    if "longtaps" in cases:
+        # the long-filter buckets alone (the last session of round 2 added 97 / 129 taps and uint8 in / int16 out)
+        x = rand_i16(1 << 27)
+        y = torch.empty_like(x)
+        x8 = x.clamp(0, 255).to(torch.uint8)
+        for L in (65, 97, 129):
+            hl = (np.ones(L) / (2 * L)).tolist()
+            s = timed(lambda: firgpu.fir1d_fixed(x, hl, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^27 i16->i16 {L}tap q1.15 (long-filter bucket)", s, 1 << 27, 4)
+        for L in (21, 65):
+            hl = (np.ones(L) / (2 * L)).tolist()
+            s = timed(lambda: firgpu.fir1d_fixed(x8, hl, 15, 32, 16, out_dtype=np.int16, out=y, validate=False), args.reps)
+            report(f"stream 2^27 u8->i16 {L}tap q1.15 (long-filter bucket)", s, 1 << 27, 3)
+        h130 = (np.ones(130) / 260).tolist()
+        s = timed(lambda: firgpu.fir1d_fixed(x[: 1 << 24], h130, 15, 32, 16, out_dtype=np.int16, out=y[: 1 << 24], validate=False), 3)
+        report("stream 2^24 i16->i16 130tap (generic kernel)", s, 1 << 24, 4)
+        del x, y, x8
     if "2dwin" in cases:
         # windows beyond 5x5 and even sizes on the tensor-map kernel (FIRGPU_FORCE_GENERIC=1 in the environment times the
         # one-thread-per-pixel int64 kernel they ran on before)

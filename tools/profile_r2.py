@@ -3,7 +3,7 @@
 
     python tools/profile_r2.py CASE [REPS]
 
-CASE: headline | wrap | wrap_u8 | imad | narrow128 | narrow4096 | image | multi | 2d5x5 | 2d5x5_u8 | 2d3x3 | iq | ideal32
+CASE: headline | wrap | wrap_u8 | imad | u8i16 | narrow128 | narrow4096 | image | multi | 2d5x5 | 2d5x5_u8 | 2d3x3 | 2d7x7 | 2d7x7rank1 | iq | ideal32
 """
 import sys
 from pathlib import Path
@@ -42,6 +42,10 @@ elif case == "wrap_u8":
     x = i16((1 << 28,)).clamp(0, 255).to(torch.uint8)
     y = torch.empty_like(x)
     fn = lambda: firgpu.fir1d_fixed(x, HW, 12, 16, 16, out=y, validate=False)
+elif case == "u8i16":
+    x = i16((1 << 28,)).clamp(0, 255).to(torch.uint8)
+    y = torch.empty(1 << 28, dtype=torch.int16, device="cuda")
+    fn = lambda: firgpu.fir1d_fixed(x, LP5, 12, 32, 16, out_dtype=np.int16, out=y, validate=False)
 elif case.startswith("narrow"):
     cols = int(case[6:])
     x = i16(((1 << 27) // cols, cols))
@@ -62,7 +66,8 @@ elif case.startswith("2d"):
     if u8:
         img = img.clamp(0, 255).to(torch.uint8)
     out = torch.empty_like(img)
-    k = [[1 / 9] * 3] * 3 if "3x3" in case else (np.outer(LP5, LP5).tolist() if "rank1" in case else np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist())
+    g7 = np.array([1, 6, 15, 20, 15, 6, 1]) / 64.0
+    k = [[1 / 9] * 3] * 3 if "3x3" in case else np.outer(g7, g7).tolist() if "7x7rank1" in case else np.random.default_rng(7).uniform(-0.1, 0.1, size=(7, 7)).tolist() if "7x7" in case else (np.outer(LP5, LP5).tolist() if "rank1" in case else np.random.default_rng(0).uniform(-0.2, 0.2, size=(5, 5)).tolist())
     hq = quant.quantize_taps(np.asarray(k), 12, 16)
     fn = lambda: firgpu.fir2d_fixed_q(img, hq, 12, 32, out_dtype=np.uint8 if u8 else np.int16, out=out)
 elif case == "ideal32":

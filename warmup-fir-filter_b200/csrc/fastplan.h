@@ -9,7 +9,7 @@
 
 namespace firgpu {
 
-constexpr int kFastPlanMaxTaps = 65;
+constexpr int kFastPlanMaxTaps = 129;
 
 struct FastPlan {
     bool ok = false;

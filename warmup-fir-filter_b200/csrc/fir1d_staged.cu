@@ -69,13 +69,14 @@ int try_launch_fir1d_fixed_staged_multi(const Fir1dArgs &a, const int32_t *hq_ho
     if (force_generic()) return 0;
     const bool force_imad = mac_mode() == 1 && n_filters == 1 && a.n_taps <= kMaxWideTaps;   // FIRGPU_MAC=1: A/B runs of the IMAD datapath
     if (a.n_taps > kMaxFastTaps) return 0;
-    // 10..65 taps: zero-pad to the next bucket, keeping the centre tap where it is
+    // 10..129 taps: zero-pad to the next bucket, keeping the centre tap where it is
     // (output n reads x[n - (k - L/2)], so the padded filter must keep h[L/2] at LB/2).
     int n_taps = a.n_taps, bucket = 0;
     int32_t padded[kMaxFastTaps];
     const int32_t *taps_in = hq_host;
     if (a.n_taps > kMaxWideTaps) {
         if (n_filters != 1 || a.dilation != 1) return 0;
+        if (a.in_dtype == FIRGPU_U8 && a.n_taps > kMaxLongTapsU8) return 0;
         for (int b : kLongBuckets)
             if (!bucket && b >= a.n_taps) bucket = b;
         const int off = bucket / 2 - a.n_taps / 2;

@@ -100,9 +100,9 @@ using FlatCfg = Cfg<256, FIRGPU_FLAT_SUB, 2, FIRGPU_FLAT_CTAS, FIRGPU_FLAT_CTAS>
 #endif
 using WrapCfg = Cfg<FIRGPU_WRAP_CFG>;
 
-constexpr int kMaxFastTaps = 65;                // dp2a datapath (taps > 9 run in zero-padded buckets, see launch_long)
+constexpr int kMaxFastTaps = 129;               // dp2a datapath (taps > 9 run in zero-padded buckets, see launch_long)
 constexpr int kMaxWideTaps = 9;                 // IMAD / wide datapaths
-constexpr int kMaxPairs = 33;
+constexpr int kMaxPairs = 65;
 constexpr int kMaxFilters = 4;                 // tap sets applied to one staged input (multi-filter mode)
 
 struct StagedParams {
@@ -937,11 +937,12 @@ int launch_taps(const StagedParams &p, int n_taps, int post, int mac, cudaStream
     }
 }
 
-// Long filters (10..65 taps): the same kernel, instantiated for a few tap-count
+// Long filters (10..129 taps): the same kernel, instantiated for a few tap-count
 // buckets; the host zero-pads the taps to the bucket (keeping the centre) —
 // zero taps cost dp2a slots but no accuracy.  8 KiB tiles, two CTAs per SM.
 using LongTapCfg = Cfg<256, 2, 2, 1, 2>;
-constexpr int kLongBuckets[] = {13, 17, 25, 33, 49, 65};
+constexpr int kLongBuckets[] = {13, 17, 25, 33, 49, 65, 97, 129};
+constexpr int kMaxLongTapsU8 = 65;              // uint8 samples: buckets up to here (see launch_long)
 template <typename T, typename OutT, int LB>
 int launch_long_bucket(const StagedParams &p, int post, cudaStream_t s)
 {
@@ -963,6 +964,14 @@ int launch_long(const StagedParams &p, int bucket, int post, cudaStream_t s)
     case 33: return launch_long_bucket<T, OutT, 33>(p, post, s);
     case 49: return launch_long_bucket<T, OutT, 49>(p, post, s);
     case 65: return launch_long_bucket<T, OutT, 65>(p, post, s);
+    // 97 / 129 taps: int16 samples only — with uint8 samples (16 per chunk) these kernels unroll to > 1000 dp2a per
+    // sub-step and ptxas needs over 40 minutes per translation unit; such calls run on the generic kernel
+    case 97:
+        if constexpr (sizeof(T) == 2) return launch_long_bucket<T, OutT, 97>(p, post, s);
+        else return 0;
+    case 129:
+        if constexpr (sizeof(T) == 2) return launch_long_bucket<T, OutT, 129>(p, post, s);
+        else return 0;
 #endif
     default: return 0;
     }

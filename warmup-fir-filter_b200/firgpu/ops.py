@@ -332,7 +332,7 @@ def fir1d_fixed(x, h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int =
 def fir1d_fixed_plan(h, frac_bits: int = 12, acc_bits: int = 32, coeff_bits: int = 16) -> dict:
     """Which datapath would serve these taps on uint8 / int16 samples — answered on the host from the quantised taps
     alone (``firgpu_fir1d_fixed_plan``): ``{"path": "staged" | "generic", "post": "shift" | "hi16" | "wrap", "mac":
-    "dp2a" | "imad"}``."""
+    "dp2a" | "imad"}``.  Between 66 and 129 taps the answer is the one for int16 samples (uint8 samples: generic)."""
     quant.validate_taps(h)
     quant.check_bits(frac_bits, acc_bits, coeff_bits)
     hq = np.ascontiguousarray(quant.quantize_taps(h, frac_bits, coeff_bits), dtype=np.int32)
