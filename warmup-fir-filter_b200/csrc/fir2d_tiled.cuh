@@ -1,5 +1,5 @@
 // Tiled 2-D fixed-point FIR for sm_100a (device code and launch templates):
-// the fast path behind firgpu_fir2d_fixed for 3- and 5-row kernels on uint8 /
+// the fast path behind firgpu_fir2d_fixed for windows of up to 7 x 7 taps on uint8 /
 // int16 images.  The reference has no fir_2d; arithmetic = the 1-D model's
 // pre/post-processing (fir_1d/model/python/fir_1d_fixed_ref.py:79-81,110-126)
 // around y[i,j] = sum_m sum_n hq[m][n] * xs[i-m+kh/2][j-n+kw/2].
