@@ -1,6 +1,8 @@
 """A/B of the general 5x5 tensor-map kernel with 0 / 1 / 2 kernel rows accumulated by FFMA (FIRGPU_T2_FFMA_ROWS,
 read by the library on every call): 16384^2 int16 -> int16, int16 -> uint8 and uint8 -> uint8, CUDA events around
 back-to-back launches, every output hashed (the three settings must be bit-equal).  One JSON line per setting.
+The FFMA variants are compiled only into a library built with `make EXTRA=-DFIRGPU_T2_FFMA=1` (they measured slower,
+profiles/README.md R2.5c); the shipped library ignores the setting and every line then times the all-dp2a kernel.
 
     python tools/ffma_rows_ab.py [--reps 10] [--size 16384]
 """
