@@ -162,6 +162,9 @@ int try_launch_fir2d_fixed_tiled(const Fir2dArgs &a_in, const int32_t *hq_in)
         for (int n = 0; n < a.kw; ++n) b32[n] = (int32_t)fb[n];
         build_pairs(b32, a.kw, kMaxPairs2, p.rp_even, p.rp_odd);
         for (int m = 0; m < a.kh; ++m) p.col_taps[m] = (int32_t)(fa[m] * scale);
+        p.col_sym = getenv("FIRGPU_NO_COL_SYM") ? 0 : 1;     // symmetric column vector: mirrored rows are added before the multiply
+        for (int m = 0; m < a.kh; ++m)
+            if (fa[m] != fa[a.kh - 1 - m]) p.col_sym = 0;
     } else {
         for (int m = 0; m < a.kh; ++m) build_pairs(f.taps + m * a.kw, a.kw, kMaxPairs2, p.cp_even[m], p.cp_odd[m]);
         if (a.kh == 5 && a.kw == 5) {

@@ -120,6 +120,7 @@ struct TiledParams {
     uint32_t xp_even[2], xp_odd[2];              // general 5x5: the odd tap of kernel rows (0,1) and (2,3) paired ACROSS rows
     uint32_t rp_even[kMaxPairs2], rp_odd[kMaxPairs2];   // separable: row-pass pairs (vector b)
     int32_t col_taps[kMaxKH];                    // separable: column taps (vector a, pre-scaled)
+    int col_sym;                                 // separable: a[m] == a[KH-1-m] for every m (host-checked)
     // general 5x5, FR > 0: the newest FR kernel rows run as FFMA on the other FMA pipe (see fir2d_tiled_kernel)
     int ffma_rows;                               // FR chosen by the host (0: all 25 taps on dp2a)
     float ftap[2][5];                            // UNSCALED integer taps of kernel rows 0 / 1 by sample offset (-2 .. +2)
@@ -241,7 +242,7 @@ __device__ __forceinline__ void mac_cross(uint32_t even, uint32_t odd, const uin
 // Measured (profiles/r2_ab_fir2d_5x5_ffma_rows.jsonl): bit-equal outputs, 15 - 20 % SLOWER — 3 dp2a per pixel become
 // 5 FFMA + 1.5 byte-to-float conversions (PRMT + FADD) + 1 add, and the kernel is not bound by the pipe's throughput but
 // by how many instructions three warps per scheduler get issued.  FR = 0 is what ships.
-template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0>
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0, bool SYM = false>
 __global__ void __launch_bounds__(kBlock2, (KH > 5 && SEP && sizeof(T) == 1 ? 2 : FIRGPU_T2_MINBLOCKS))   // 7 rows x 16 horizontal sums
 fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TiledParams p)
 {
@@ -352,6 +353,7 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             }
     }
 
+    constexpr bool col_sym = SEP && SYM;          // separable with a symmetric column vector (host-checked, p.col_sym)
     // rolling window of the last KH input rows
     uint32_t Bw[SEP ? 1 : KH][G1::NB];            // general: byte-packed samples
     int Rw[SEP ? KH : 1][G1::S];                  // separable: horizontal sums
@@ -444,8 +446,22 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             for (int m = FR; m < KH; ++m) {
                                 const int slot = (rr - m + KH) % KH;   // input row (newest - m) <-> kernel row m
                                 if constexpr (SEP) {
+                                    if constexpr (col_sym) {
+                                        // symmetric column vector (every low-pass / binomial / Gaussian kernel): the two rows
+                                        // that share a tap are added first — an add on the ALU pipe replaces a multiply-add
+                                        // on the heavy FMA pipe, the busiest unit of this kernel
+                                        if (m < KH / 2) {
+                                            const int mirror = (rr - (KH - 1 - m) + KH) % KH;
 #pragma unroll
-                                    for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
+                                            for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * (Rw[slot][i] + Rw[mirror][i]);
+                                        } else if (m == KH / 2) {
+#pragma unroll
+                                            for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < G1::S; ++i) acc[i] += p.col_taps[m] * Rw[slot][i];
+                                    }
                                 } else if constexpr (kCross) {
                                     if (m < FR + 2 * NC) mac_row_pairs<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
                                     else mac_row<G1, KW>(cpe[m], cpo[m], Bw[slot], acc);
@@ -508,11 +524,11 @@ fir2d_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 
 // ---- launch helpers -------------------------------------------------------------
-template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0>
+template <typename T, int KH, int KW, int POST, bool SEP, typename OutT = T, int FR = 0, bool SYM = false>
 int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t stream)
 {
     using G = Geo2<T, KH, KW>;
-    auto kern = fir2d_tiled_kernel<T, KH, KW, POST, SEP, OutT, FR>;
+    auto kern = fir2d_tiled_kernel<T, KH, KW, POST, SEP, OutT, FR, SYM>;
     static std::mutex mu;
     static int ctas_per_sm[64] = {0};
     int dev = 0;
@@ -579,7 +595,7 @@ int launch_tiled_one(const CUtensorMap &map, const TiledParams &p, cudaStream_t 
     return 1;
 }
 
-template <typename T, int KH, int KW, bool SEP, typename OutT>
+template <typename T, int KH, int KW, bool SEP, typename OutT, bool SYM = false>
 int launch_tiled_post(const CUtensorMap &map, const TiledParams &p, int post, cudaStream_t s)
 {
 #if FIRGPU_T2_FFMA
@@ -603,9 +619,9 @@ int launch_tiled_post(const CUtensorMap &map, const TiledParams &p, int post, cu
     }
 #endif
     switch (post) {
-    case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT>(map, p, s);
-    case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT>(map, p, s);
-    case POST_WRAP: return launch_tiled_one<T, KH, KW, POST_WRAP, SEP, OutT>(map, p, s);
+    case POST_SHIFT: return launch_tiled_one<T, KH, KW, POST_SHIFT, SEP, OutT, 0, SYM>(map, p, s);
+    case POST_HI16: return launch_tiled_one<T, KH, KW, POST_HI16, SEP, OutT, 0, SYM>(map, p, s);
+    case POST_WRAP: return launch_tiled_one<T, KH, KW, POST_WRAP, SEP, OutT, 0, SYM>(map, p, s);
     default: return 0;
     }
 }
@@ -614,7 +630,8 @@ template <typename T, int KH, int KW, typename OutT = T>
 int launch_tiled_modes(const CUtensorMap &map, const TiledParams &p, int post, bool sep, cudaStream_t s)
 {
     if constexpr (KH > 1 && KW >= 3 && !(KH == 3 && KW == 3)) {
-        if (sep) return launch_tiled_post<T, KH, KW, true, OutT>(map, p, post, s);
+        if (sep) return p.col_sym ? launch_tiled_post<T, KH, KW, true, OutT, true>(map, p, post, s)
+                                  : launch_tiled_post<T, KH, KW, true, OutT, false>(map, p, post, s);
     }
     return launch_tiled_post<T, KH, KW, false, OutT>(map, p, post, s);
 }
